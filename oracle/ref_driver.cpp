@@ -1,0 +1,566 @@
+// TEST INFRASTRUCTURE ONLY — never linked into, or called from, the product path.
+//
+// Driver that links the UNMODIFIED reference (stock MFEM 4.9.1-dev sources under
+// /root/reference, compiled by oracle/Makefile into oracle/_ref/libmfem_ref.a) and
+//   * dumps golden vectors for every row of SURVEY.md §8(a): the arrays the hot path
+//     consumes (B, G, W, gather_map/offsets/indices, J, detJ, q-data) and what the
+//     reference computes from them (pa_data, E- and L-vector applies, diagonals,
+//     Jacobi, PCG iterates, q-point values/gradients, RHS, the bioheat/RF step);
+//   * times the reference CPU path (serial "cpu" or OpenMP "omp" device) for
+//     bench.py's cpu_baseline / --impl reference arm.
+// It reads nothing from /root/reference at run time (meshes are generated with
+// Mesh::MakeCartesian3D; config 1's data/inline-hex.mesh is the INLINE 4x4x4 hex
+// mesh, i.e. MakeCartesian3D(4,4,4), see `--check-inline`).
+//
+// Output format of `dump_*`: one raw little-endian file per array in <outdir>
+// (<name>.f64 / <name>.i32) plus <outdir>/manifest.txt with "name dtype count".
+#include "mfem.hpp"
+#include "fem/integ/bilininteg_diffusion_kernels.hpp"
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace mfem;
+using namespace std;
+
+static double now()
+{
+   return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- dump helpers
+struct Dumper
+{
+   string dir;
+   ofstream man;
+   explicit Dumper(const string &d) : dir(d)
+   {
+      mkdir(dir.c_str(), 0755);
+      man.open(dir + "/manifest.txt");
+   }
+   void raw(const string &name, const char *ext, const void *p, size_t bytes, size_t n)
+   {
+      ofstream f(dir + "/" + name + "." + ext, ios::binary);
+      f.write((const char *)p, bytes);
+      man << name << " " << ext << " " << n << "\n";
+   }
+   void f64(const string &name, const double *p, size_t n) { raw(name, "f64", p, 8 * n, n); }
+   void i32(const string &name, const int *p, size_t n) { raw(name, "i32", p, 4 * n, n); }
+   void vec(const string &name, const Vector &v) { f64(name, v.HostRead(), v.Size()); }
+   void arr(const string &name, const Array<int> &a) { i32(name, a.HostRead(), a.Size()); }
+   void arr(const string &name, const Array<double> &a) { f64(name, a.HostRead(), a.Size()); }
+   void scalar(const string &name, double v) { f64(name, &v, 1); }
+   void iscalar(const string &name, int v) { i32(name, &v, 1); }
+};
+
+struct NormRecorder : public IterativeSolverMonitor
+{
+   vector<double> norms;
+   void MonitorResidual(int it, real_t norm, const Vector &, bool final) override
+   {
+      if (!final) { if ((int)norms.size() <= it) { norms.resize(it + 1); } norms[it] = norm; }
+   }
+};
+
+// Mesh kinds: "cart" = MakeCartesian3D(nx,ny,nz,HEX,sx,sy,sz) (SFC element order);
+//             "skew" = the same + the vertex remap of tests/unit/fem/test_pa_coeff.cpp:33-39;
+//             "inline3" = config 1: MakeCartesian3D(4,4,4) + 3 uniform refinements.
+static Mesh make_mesh(const string &kind, int nx, int ny, int nz, double sx, double sy, double sz)
+{
+   if (kind == "inline3")
+   {
+      Mesh m = Mesh::MakeCartesian3D(4, 4, 4, Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+      for (int l = 0; l < nx; l++) { m.UniformRefinement(); }
+      return m;
+   }
+   Mesh m = Mesh::MakeCartesian3D(nx, ny, nz, Element::HEXAHEDRON, sx, sy, sz);
+   if (kind == "skew")
+   {
+      for (int i = 0; i < m.GetNV(); ++i)
+      {
+         real_t *v = m.GetVertex(i);
+         v[1] += 0.2 * v[0];
+         v[2] += 0.3 * v[0];
+      }
+   }
+   return m;
+}
+
+// Coefficient functions used for the "func" coefficient kind (q-data sampled by the
+// reference's own Coefficient::Project).  Same shape as test_pa_coeff.cpp:45-58.
+static double kfun(const Vector &x)
+{
+   return sin(8.0 * M_PI * x[0]) * cos(6.0 * M_PI * x[1]) * sin(4.0 * M_PI * x[2]) + 2.0;
+}
+static double mfun(const Vector &x)
+{
+   return 3.0 + x[0] * x[1] + 0.5 * cos(3.0 * x[2]);
+}
+
+struct MassPA : public MassIntegrator
+{
+   using MassIntegrator::MassIntegrator;
+   const Vector &PAData() const { return pa_data; }
+};
+
+// ------------------------------------------------------------------ dump_case
+// Everything §8(a) a1–a16, a20, a21 for one (mesh, order, coefficient kind, BC) case.
+static int dump_case(int argc, char **argv)
+{
+   if (argc < 12)
+   {
+      cerr << "dump_case OUT p kind nx ny nz sx sy sz coef(const|func) bc(none|all|zfaces) [pcg_iters]\n";
+      return 2;
+   }
+   Dumper D(argv[2]);
+   const int p = atoi(argv[3]);
+   const string kind = argv[4];
+   const int nx = atoi(argv[5]), ny = atoi(argv[6]), nz = atoi(argv[7]);
+   const double sx = atof(argv[8]), sy = atof(argv[9]), sz = atof(argv[10]);
+   const string coef = argv[11];
+   const string bc = argc > 12 ? argv[12] : "none";
+   const int pcg_iters = argc > 13 ? atoi(argv[13]) : 10;
+
+   Device device("cpu");
+   Mesh mesh = make_mesh(kind, nx, ny, nz, sx, sy, sz);
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   const FiniteElement &el = *fes.GetTypicalFE();
+   const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+   {
+      // the mass rule must be the same rule; verify, do not assume
+      ElementTransformation &T0 = *mesh.GetTypicalElementTransformation();
+      const IntegrationRule &irm = MassIntegrator::GetRule(el, el, T0);
+      MFEM_VERIFY(irm.GetNPoints() == ir.GetNPoints(), "mass/diffusion rules differ");
+   }
+   const DofToQuad &maps = el.GetDofToQuad(ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = mesh.GetNE(), ND = fes.GetNDofs();
+   const int NQ = ir.GetNPoints();
+   D.iscalar("p", p); D.iscalar("D1D", D1D); D.iscalar("Q1D", Q1D); D.iscalar("NE", NE);
+   D.iscalar("ndofs", ND);
+   D.arr("B", maps.B); D.arr("G", maps.G); D.arr("Bt", maps.Bt); D.arr("Gt", maps.Gt);
+   D.arr("W", ir.GetWeights());
+
+   // a1: restriction tables
+   const ElementRestriction *R = dynamic_cast<const ElementRestriction *>(
+                                    fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   MFEM_VERIFY(R, "no ElementRestriction");
+   D.arr("gather_map", R->GatherMap()); D.arr("offsets", R->Offsets()); D.arr("indices", R->Indices());
+
+   // a20: geometric factors; also vertices (inputs of the product-side builder)
+   const GeometricFactors *geom = mesh.GetGeometricFactors(
+                                     ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS |
+                                     GeometricFactors::COORDINATES);
+   D.vec("J", geom->J); D.vec("detJ", geom->detJ); D.vec("Xq", geom->X);
+   {
+      Vector vx(3 * mesh.GetNV());
+      for (int i = 0; i < mesh.GetNV(); i++) { for (int d = 0; d < 3; d++) { vx(3 * i + d) = mesh.GetVertex(i)[d]; } }
+      D.vec("vertices", vx);
+      Array<int> ev(8 * NE);
+      for (int e = 0; e < NE; e++) { const int *v = mesh.GetElement(e)->GetVertices(); for (int j = 0; j < 8; j++) { ev[8 * e + j] = v[j]; } }
+      D.arr("elem_vertices", ev);
+   }
+
+   // coefficients → q-data through the reference's own projection (a19)
+   QuadratureSpace qs(mesh, ir);
+   ConstantCoefficient kc_const(0.5), mc_const(3.6);
+   FunctionCoefficient kc_fun(kfun), mc_fun(mfun);
+   Coefficient &kc = (coef == "const") ? (Coefficient &)kc_const : (Coefficient &)kc_fun;
+   Coefficient &mc = (coef == "const") ? (Coefficient &)mc_const : (Coefficient &)mc_fun;
+   CoefficientVector kq(kc, qs, CoefficientStorage::COMPRESSED);
+   CoefficientVector mq(mc, qs, CoefficientStorage::COMPRESSED);
+   D.vec("kq", kq); D.vec("mq", mq);   // size 1 (constant) or NQ*NE
+
+   // a5: diffusion pa_data via the reference setup kernel itself
+   Vector pa_diff(6 * NQ * NE);
+   internal::PADiffusionSetup(3, 3, D1D, Q1D, 1, NE, ir.GetWeights(), geom->J, kq, pa_diff);
+   D.vec("pa_diff", pa_diff);
+
+   // integrators (a6–a10) at E-vector level
+   DiffusionIntegrator *di = new DiffusionIntegrator(kc);
+   MassPA *mi = new MassPA(mc);
+   BilinearForm a(&fes);
+   a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   a.AddDomainIntegrator(di);
+   a.AddDomainIntegrator(mi);
+   a.Assemble();
+   D.vec("pa_mass", mi->PAData());
+
+   Vector x(ND); x.Randomize(1);
+   D.vec("x", x);
+   Vector xE(R->Height()); R->Mult(x, xE); D.vec("xE", xE);             // a2
+   Vector yE(R->Height());
+   yE = 0.0; di->AddMultPA(xE, yE); D.vec("yE_diff", yE);                 // a6
+   { Vector yL(ND); R->MultTranspose(yE, yL); D.vec("y_diff", yL); }      // a3
+   yE = 0.0; mi->AddMultPA(xE, yE); D.vec("yE_mass", yE);                 // a9
+   { Vector yL(ND); R->MultTranspose(yE, yL); D.vec("y_mass", yL); }
+   yE = 0.0; di->AddMultPA(xE, yE); mi->AddMultPA(xE, yE); D.vec("yE", yE);
+   Vector y(ND); a.Mult(x, y); D.vec("y", y);                             // a11 L→L
+   yE = 0.0; di->AssembleDiagonalPA(yE); D.vec("dE_diff", yE);            // a7
+   yE = 0.0; mi->AssembleDiagonalPA(yE); D.vec("dE_mass", yE);            // a10
+   Vector diag(ND); a.AssembleDiagonal(diag); D.vec("diag", diag);        // a4+a7+a10
+
+   // a12: essential dofs + constrained operator
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()); ess_bdr = 0;
+   if (bc == "all") { ess_bdr = 1; }
+   else if (bc == "zfaces") { ess_bdr[0] = 1; ess_bdr[5] = 1; }   // z=0 is attr 1, z=sz is attr 6
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.arr("ess", ess);
+   {
+      GridFunction xg(&fes); xg = 0.0;
+      FunctionCoefficient bcf([&](const Vector &X) { return 30.0 * (1.0 - X(2) / sz) + X(0); });
+      if (ess.Size()) { xg.ProjectBdrCoefficient(bcf, ess_bdr); }
+      LinearForm b(&fes);
+      ConstantCoefficient one(1.0);
+      b.AddDomainIntegrator(new DomainLFIntegrator(one));
+      b.Assemble();
+      D.vec("b_L", b); D.vec("x0_L", xg);
+      OperatorPtr A; Vector X, B;
+      a.FormLinearSystem(ess, xg, b, A, X, B);
+      D.vec("B_rhs", B); D.vec("X0", X);
+      Vector yc(ND); A->Mult(x, yc); D.vec("y_constrained", yc);
+      OperatorJacobiSmoother M(a, ess);                                   // a13
+      { Vector r(ND), z(ND); r = x; M.Mult(r, z); D.vec("jacobi_z", z); }
+      // a14: PCG — fixed iteration counts, then to tolerance
+      Array<int> its;
+      its.Append(1); its.Append(2); its.Append(pcg_iters);
+      for (int k = 0; k < its.Size(); k++)
+      {
+         CGSolver cg; NormRecorder rec;
+         cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(its[k]); cg.SetPrintLevel(-1);
+         cg.SetOperator(*A); cg.SetPreconditioner(M); cg.SetMonitor(rec);
+         cg.iterative_mode = true;
+         Vector Xk(X);
+         cg.Mult(B, Xk);
+         D.vec("X_pcg" + to_string(its[k]), Xk);
+         if (k == its.Size() - 1) { D.f64("pcg_norms", rec.norms.data(), rec.norms.size()); }
+      }
+      {
+         CGSolver cg; NormRecorder rec;
+         cg.SetRelTol(1e-8); cg.SetAbsTol(0.0); cg.SetMaxIter(5000); cg.SetPrintLevel(-1);
+         cg.SetOperator(*A); cg.SetPreconditioner(M); cg.SetMonitor(rec);
+         cg.iterative_mode = true;
+         Vector Xk(X);
+         cg.Mult(B, Xk);
+         D.vec("X_pcg_tol", Xk);
+         D.iscalar("pcg_tol_iters", cg.GetNumIterations());
+         D.iscalar("pcg_tol_converged", cg.GetConverged());
+         D.scalar("pcg_tol_final_norm", cg.GetFinalNorm());
+         D.f64("pcg_tol_norms", rec.norms.data(), rec.norms.size());
+      }
+   }
+   // a17/a18: q-point values and physical gradients of x; K15 RHS with q-data source
+   {
+      const QuadratureInterpolator *qi = fes.GetQuadratureInterpolator(qs);
+      qi->SetOutputLayout(QVectorLayout::byVDIM);
+      Vector vq(NQ * NE), gq(3 * NQ * NE);
+      qi->Values(xE, vq); D.vec("xq_values", vq);
+      qi->PhysDerivatives(xE, gq); D.vec("xq_physgrad", gq);
+      QuadratureFunction fq(qs);
+      for (int i = 0; i < fq.Size(); i++) { fq(i) = 1.0 + vq(i) * vq(i); }
+      QuadratureFunctionCoefficient fqc(fq);
+      LinearForm lf(&fes);
+      lf.AddDomainIntegrator(new DomainLFIntegrator(fqc, &ir));
+      lf.UseFastAssembly(true);
+      lf.Assemble();
+      D.vec("lf_fq", fq); D.vec("lf_b", lf);
+   }
+   cout << "dump_case ok: p=" << p << " NE=" << NE << " ndofs=" << ND << " Q1D=" << Q1D
+        << setprecision(17) << " |y|=" << y.Norml2() << " |diag|=" << diag.Norml2() << endl;
+   return 0;
+}
+
+// --------------------------------------------------------------- bioheat step
+// One RF-ablation coupled step expressed with the reference's own PA API
+// (parameters §8d).  Used both for dumps and for timing.
+struct BioheatParams
+{
+   double dt = 0.5, rc = 3.6e6, wbcb = 4.0e4, Ta = 37.0, k0 = 0.5, ak = 0.02, s0 = 0.3, as = 0.015, V = 30.0;
+};
+
+static int bioheat(int argc, char **argv, bool dump)
+{
+   // dump_bioheat OUT p N iters [dev]    |   time_bioheat p N iters dev
+   int ai = 2;
+   Dumper *D = nullptr;
+   if (dump) { D = new Dumper(argv[ai++]); }
+   if (argc < ai + 3) { cerr << "usage: [dump_bioheat OUT|time_bioheat] p N iters [dev]\n"; return 2; }
+   const int p = atoi(argv[ai++]), N = atoi(argv[ai++]), iters = atoi(argv[ai++]);
+   const char *dev = argc > ai ? argv[ai] : "cpu";
+   Device device(dev);
+   const BioheatParams P;
+   double t0 = now();
+   Mesh mesh = Mesh::MakeCartesian3D(N, N, N, Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   const FiniteElement &el = *fes.GetTypicalFE();
+   const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+   QuadratureSpace qs(mesh, ir);
+   const double t_mesh = now() - t0;
+   GridFunction T0(&fes), T1(&fes), phi(&fes);
+   FunctionCoefficient Tinit([](const Vector &x)
+   {
+      const double r2 = (x(0) - .5) * (x(0) - .5) + (x(1) - .5) * (x(1) - .5) + (x(2) - .5) * (x(2) - .5);
+      return 37.0 + 20.0 * exp(-40.0 * r2);
+   });
+   T0.ProjectCoefficient(Tinit);
+   // T at q-points → k(T), sigma(T), mass coefficient
+   t0 = now();
+   QuadratureFunction Tq(qs), kq(qs), sq(qs), mq(qs);
+   Tq.ProjectGridFunction(T0);
+   {
+      const int n = Tq.Size();
+      auto t = Tq.Read(); auto k = kq.Write(); auto s = sq.Write(); auto m = mq.Write();
+      const double k0 = P.k0, ak = P.ak, s0 = P.s0, as = P.as, mval = P.rc / P.dt + P.wbcb;
+      mfem::forall(n, [=] MFEM_HOST_DEVICE (int i)
+      {
+         k[i] = k0 * (1.0 + ak * (t[i] - 37.0));
+         s[i] = s0 * (1.0 + as * (t[i] - 37.0));
+         m[i] = mval;
+      });
+   }
+   const double t_coef = now() - t0;
+   QuadratureFunctionCoefficient kc(kq), sc(sq), mc(mq);
+   // (1) electrostatics
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()); ess_bdr = 0; ess_bdr[0] = 1; ess_bdr[5] = 1;
+   Array<int> ess; fes.GetEssentialTrueDofs(ess_bdr, ess);
+   const double V = P.V;
+   FunctionCoefficient phibc([=](const Vector &x) { return V * (1.0 - x(2)); });
+   phi = 0.0; phi.ProjectBdrCoefficient(phibc, ess_bdr);
+   BilinearForm ae(&fes); ae.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   ae.AddDomainIntegrator(new DiffusionIntegrator(sc));
+   t0 = now(); ae.Assemble(); const double t_asm_e = now() - t0;
+   LinearForm be(&fes); be.Assemble();
+   OperatorPtr Ae; Vector Xe, Be; ae.FormLinearSystem(ess, phi, be, Ae, Xe, Be);
+   OperatorJacobiSmoother Me(ae, ess);
+   CGSolver cge; cge.SetRelTol(0.0); cge.SetAbsTol(0.0); cge.SetMaxIter(iters); cge.SetPrintLevel(-1);
+   cge.SetOperator(*Ae); cge.SetPreconditioner(Me);
+   if (D) { D->vec("T0", T0); D->vec("Tq", Tq); D->vec("kq", kq); D->vec("sq", sq); D->vec("mq", mq);
+            D->arr("ess", ess); D->vec("phi0", phi); D->vec("Be", Be); }
+   t0 = now(); cge.Mult(Be, Xe); const double t_cg_e = now() - t0;
+   ae.RecoverFEMSolution(Xe, be, phi);
+   // (2) Joule source at q-points
+   t0 = now();
+   const Operator *R = fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+   Vector ephi(R->Height()); R->Mult(phi, ephi);
+   const QuadratureInterpolator *qi = fes.GetQuadratureInterpolator(qs);
+   qi->SetOutputLayout(QVectorLayout::byVDIM);
+   Vector gq(3 * qs.GetSize()); qi->PhysDerivatives(ephi, gq);
+   QuadratureFunction rq(qs);
+   {
+      const int n = qs.GetSize();
+      auto g = gq.Read(); auto s = sq.Read(); auto r = rq.Write();
+      const double src0 = P.wbcb * P.Ta;
+      mfem::forall(n, [=] MFEM_HOST_DEVICE (int i)
+      {
+         const double gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
+         r[i] = s[i] * (gx * gx + gy * gy + gz * gz) + src0;
+      });
+   }
+   const double t_joule = now() - t0;
+   QuadratureFunctionCoefficient rcf(rq);
+   // (3) bioheat backward-Euler step
+   BilinearForm at(&fes); at.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   at.AddDomainIntegrator(new DiffusionIntegrator(kc));
+   at.AddDomainIntegrator(new MassIntegrator(mc));
+   t0 = now(); at.Assemble(); const double t_asm_t = now() - t0;
+   ConstantCoefficient rcdt(P.rc / P.dt);
+   BilinearForm mrc(&fes); mrc.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   mrc.AddDomainIntegrator(new MassIntegrator(rcdt)); mrc.Assemble();
+   LinearForm bt(&fes); bt.AddDomainIntegrator(new DomainLFIntegrator(rcf, &ir)); bt.UseFastAssembly(true);
+   t0 = now(); bt.Assemble(); Vector mT(fes.GetVSize()); mrc.Mult(T0, mT); bt += mT;
+   const double t_rhs = now() - t0;
+   Array<int> noess; T1 = T0; OperatorPtr At; Vector Xt, Bt; at.FormLinearSystem(noess, T1, bt, At, Xt, Bt, 1);
+   OperatorJacobiSmoother Mt(at, noess);
+   CGSolver cgt; cgt.SetRelTol(0.0); cgt.SetAbsTol(0.0); cgt.SetMaxIter(iters); cgt.SetPrintLevel(-1);
+   cgt.SetOperator(*At); cgt.SetPreconditioner(Mt); cgt.iterative_mode = true;
+   t0 = now(); cgt.Mult(Bt, Xt); const double t_cg_t = now() - t0;
+   at.RecoverFEMSolution(Xt, bt, T1);
+   if (D)
+   {
+      D->vec("phi", phi); D->vec("gradphi_q", gq); D->vec("src_q", rq); D->vec("rhs_T", bt); D->vec("T1", T1);
+      D->iscalar("iters", iters);
+      // iterations to rel 1e-8 for both solves (iteration-count parity, ±1)
+      CGSolver c2; c2.SetRelTol(1e-8); c2.SetAbsTol(0.0); c2.SetMaxIter(5000); c2.SetPrintLevel(-1);
+      c2.SetOperator(*At); c2.SetPreconditioner(Mt); c2.iterative_mode = true;
+      Vector X2(T0); c2.Mult(Bt, X2);
+      D->iscalar("iters_tol_T", c2.GetNumIterations()); D->vec("T1_tol", X2);
+      CGSolver c3; c3.SetRelTol(1e-8); c3.SetAbsTol(0.0); c3.SetMaxIter(5000); c3.SetPrintLevel(-1);
+      c3.SetOperator(*Ae); c3.SetPreconditioner(Me); c3.iterative_mode = true;
+      GridFunction p3(&fes); p3 = 0.0; p3.ProjectBdrCoefficient(phibc, ess_bdr);
+      Vector X3(p3); c3.Mult(Be, X3);
+      D->iscalar("iters_tol_phi", c3.GetNumIterations()); D->vec("phi_tol", X3);
+   }
+   int nthreads = 1;
+#ifdef _OPENMP
+   if (string(dev) == "omp") { nthreads = omp_get_max_threads(); }
+#endif
+   cout << setprecision(17)
+        << "{\"kind\":\"bioheat_step\",\"p\":" << p << ",\"N\":" << N << ",\"ndofs\":" << fes.GetNDofs()
+        << ",\"iters\":" << iters << ",\"device\":\"" << dev << "\",\"threads\":" << nthreads
+        << ",\"phi_norm\":" << phi.Norml2() << ",\"src_sum\":" << rq.Sum() << ",\"T1_norm\":" << T1.Norml2()
+        << ",\"T1_max\":" << T1.Max()
+        << ",\"t_mesh\":" << t_mesh << ",\"t_coef\":" << t_coef << ",\"t_asm_e\":" << t_asm_e
+        << ",\"t_cg_e\":" << t_cg_e << ",\"t_joule\":" << t_joule << ",\"t_asm_t\":" << t_asm_t
+        << ",\"t_rhs\":" << t_rhs << ",\"t_cg_t\":" << t_cg_t << "}" << endl;
+   delete D;
+   return 0;
+}
+
+// ---------------------------------------------------------------- time_apply
+// CPU reference timing of the PA diffusion+mass apply (L→L, A.Mult) and of a fixed
+// number of Jacobi-PCG iterations, on MakeCartesian3D(N^3), order p, q-data
+// coefficients (bioheat-like k(T), mass) — the same operator bench.py times on the GPU.
+static int time_apply(int argc, char **argv)
+{
+   if (argc < 7) { cerr << "time_apply p N reps warmup dev [pcg_iters]\n"; return 2; }
+   const int p = atoi(argv[2]), N = atoi(argv[3]), reps = atoi(argv[4]), warm = atoi(argv[5]);
+   const char *dev = argv[6];
+   const int pcg_iters = argc > 7 ? atoi(argv[7]) : 0;
+   Device device(dev);
+   double t0 = now();
+   Mesh mesh = Mesh::MakeCartesian3D(N, N, N, Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   const FiniteElement &el = *fes.GetTypicalFE();
+   const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+   QuadratureSpace qs(mesh, ir);
+   QuadratureFunction kq(qs), mq(qs);
+   {
+      const BioheatParams P;
+      GridFunction T0(&fes);
+      FunctionCoefficient Tinit([](const Vector &x)
+      {
+         const double r2 = (x(0) - .5) * (x(0) - .5) + (x(1) - .5) * (x(1) - .5) + (x(2) - .5) * (x(2) - .5);
+         return 37.0 + 20.0 * exp(-40.0 * r2);
+      });
+      T0.ProjectCoefficient(Tinit);
+      QuadratureFunction Tq(qs); Tq.ProjectGridFunction(T0);
+      for (int i = 0; i < Tq.Size(); i++) { kq(i) = P.k0 * (1.0 + P.ak * (Tq(i) - 37.0)); mq(i) = P.rc / P.dt + P.wbcb; }
+   }
+   QuadratureFunctionCoefficient kc(kq), mc(mq);
+   BilinearForm a(&fes); a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   a.AddDomainIntegrator(new DiffusionIntegrator(kc));
+   a.AddDomainIntegrator(new MassIntegrator(mc));
+   a.Assemble();
+   const double t_setup = now() - t0;
+   const int ND = fes.GetNDofs();
+   Vector x(ND), y(ND); x.Randomize(1); y = 0.0;
+   x.UseDevice(true); y.UseDevice(true);
+   for (int i = 0; i < warm; i++) { a.Mult(x, y); }
+   vector<double> ts(reps);
+   for (int i = 0; i < reps; i++) { t0 = now(); a.Mult(x, y); ts[i] = now() - t0; }
+   double tsum = 0, tmin = 1e300, tmax = 0;
+   for (double t : ts) { tsum += t; tmin = min(tmin, t); tmax = max(tmax, t); }
+   double t_pcg = 0.0;
+   if (pcg_iters > 0)
+   {
+      Array<int> noess;
+      OperatorJacobiSmoother M(a, noess);
+      CGSolver cg; cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(pcg_iters); cg.SetPrintLevel(-1);
+      cg.SetOperator(a); cg.SetPreconditioner(M);
+      Vector X(ND); X = 0.0;
+      t0 = now(); cg.Mult(x, X); t_pcg = now() - t0;
+   }
+   int nthreads = 1;
+#ifdef _OPENMP
+   if (string(dev) == "omp") { nthreads = omp_get_max_threads(); }
+#endif
+   cout << setprecision(17)
+        << "{\"kind\":\"time_apply\",\"p\":" << p << ",\"N\":" << N << ",\"NE\":" << mesh.GetNE() << ",\"ndofs\":" << ND
+        << ",\"device\":\"" << dev << "\",\"threads\":" << nthreads << ",\"reps\":" << reps << ",\"warmup\":" << warm
+        << ",\"t_setup\":" << t_setup << ",\"t_apply_mean\":" << tsum / reps << ",\"t_apply_min\":" << tmin
+        << ",\"t_apply_max\":" << tmax << ",\"y_norm\":" << y.Norml2()
+        << ",\"pcg_iters\":" << pcg_iters << ",\"t_pcg\":" << t_pcg << "}" << endl;
+   return 0;
+}
+
+// ------------------------------------------------------------------------ ex1
+// Config 1: examples/ex1.cpp -pa -o 3 on the INLINE 4^3 hex mesh with 3 refinements:
+// Jacobi-PCG iteration count to (Br,r) <= 1e-12 (Br,r)_0 (197).
+static int ex1(int argc, char **argv)
+{
+   // ex1 [OUT|-] order refinements dev
+   const string out = argc > 2 ? argv[2] : "-";
+   const int order = argc > 3 ? atoi(argv[3]) : 3;
+   const int ref = argc > 4 ? atoi(argv[4]) : 3;
+   const char *dev = argc > 5 ? argv[5] : "cpu";
+   Device device(dev);
+   Mesh mesh = make_mesh("inline3", ref, 0, 0, 1, 1, 1);
+   H1_FECollection fec(order, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess; fes.GetEssentialTrueDofs(ess_bdr, ess);
+   LinearForm b(&fes); ConstantCoefficient one(1.0);
+   b.AddDomainIntegrator(new DomainLFIntegrator(one)); b.Assemble();
+   GridFunction x(&fes); x = 0.0;
+   BilinearForm a(&fes); a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   a.AddDomainIntegrator(new DiffusionIntegrator(one));
+   a.Assemble();
+   OperatorPtr A; Vector B, X;
+   a.FormLinearSystem(ess, x, b, A, X, B);
+   OperatorJacobiSmoother M(a, ess);
+   CGSolver cg; NormRecorder rec;
+   cg.SetRelTol(sqrt(1e-12)); cg.SetAbsTol(0.0); cg.SetMaxIter(400); cg.SetPrintLevel(-1);
+   cg.SetOperator(*A); cg.SetPreconditioner(M); cg.SetMonitor(rec);
+   double t0 = now(); cg.Mult(B, X); const double t_pcg = now() - t0;
+   if (out != "-")
+   {
+      Dumper D(out);
+      const FiniteElement &el = *fes.GetTypicalFE();
+      const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+      const DofToQuad &maps = el.GetDofToQuad(ir, DofToQuad::TENSOR);
+      const ElementRestriction *R = dynamic_cast<const ElementRestriction *>(
+                                       fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+      const GeometricFactors *geom = mesh.GetGeometricFactors(ir, GeometricFactors::JACOBIANS);
+      D.iscalar("p", order); D.iscalar("D1D", maps.ndof); D.iscalar("Q1D", maps.nqpt);
+      D.iscalar("NE", mesh.GetNE()); D.iscalar("ndofs", fes.GetNDofs());
+      D.arr("B", maps.B); D.arr("G", maps.G); D.arr("W", ir.GetWeights());
+      D.arr("gather_map", R->GatherMap()); D.arr("offsets", R->Offsets()); D.arr("indices", R->Indices());
+      D.vec("J", geom->J); D.arr("ess", ess); D.vec("B_rhs", B); D.vec("X", X);
+      D.f64("pcg_norms", rec.norms.data(), rec.norms.size());
+      D.iscalar("pcg_iters", cg.GetNumIterations());
+   }
+   cout << setprecision(17) << "{\"kind\":\"ex1\",\"order\":" << order << ",\"ref\":" << ref << ",\"ndofs\":" << fes.GetNDofs()
+        << ",\"iters\":" << cg.GetNumIterations() << ",\"converged\":" << cg.GetConverged()
+        << ",\"final_norm\":" << cg.GetFinalNorm() << ",\"t_pcg\":" << t_pcg << ",\"X_norm\":" << X.Norml2() << "}" << endl;
+   return 0;
+}
+
+// Verify (in the build container only) that data/inline-hex.mesh is MakeCartesian3D(4,4,4).
+static int check_inline(const char *path)
+{
+   Mesh a(path, 1, 1), b = Mesh::MakeCartesian3D(4, 4, 4, Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+   bool same = a.GetNE() == b.GetNE() && a.GetNV() == b.GetNV() && a.GetNBE() == b.GetNBE();
+   for (int e = 0; same && e < a.GetNE(); e++)
+   {
+      const int *u = a.GetElement(e)->GetVertices(), *v = b.GetElement(e)->GetVertices();
+      for (int j = 0; j < 8; j++) { same = same && u[j] == v[j]; }
+   }
+   for (int i = 0; same && i < a.GetNV(); i++) { for (int d = 0; d < 3; d++) { same = same && a.GetVertex(i)[d] == b.GetVertex(i)[d]; } }
+   cout << "inline-hex == MakeCartesian3D(4,4,4): " << (same ? "yes" : "NO") << endl;
+   return same ? 0 : 1;
+}
+
+int main(int argc, char **argv)
+{
+   const string cmd = argc > 1 ? argv[1] : "";
+   if (cmd == "dump_case") { return dump_case(argc, argv); }
+   if (cmd == "dump_bioheat") { return bioheat(argc, argv, true); }
+   if (cmd == "time_bioheat") { return bioheat(argc, argv, false); }
+   if (cmd == "time_apply") { return time_apply(argc, argv); }
+   if (cmd == "ex1") { return ex1(argc, argv); }
+   if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }
+   cerr << "usage: ref_driver dump_case|dump_bioheat|time_bioheat|time_apply|ex1|--check-inline ...\n";
+   return 2;
+}
