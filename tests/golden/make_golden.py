@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Regenerate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs oracle/_ref/ref_driver, i.e. `make -C oracle ref`,
+which compiles the reference sources under /root/reference).  The reference ships no stored
+golden vectors for this path — its tests compare assembly levels — so the
+vectors here are outputs of the reference itself, which is what pins oracle/pa_oracle.c.
+
+    python tests/golden/make_golden.py
+
+Fixtures (all float64 / int32, reference layouts):
+  case_<tag>.npz      everything `ref_driver dump_case` writes for one small case
+  numbering.npz       gather_map / ndofs for many (nx,ny,nz,p): pins the product-side hex builder
+  bioheat_p2_n4.npz   the RF + bioheat coupled step of SURVEY §3.2/3.3 on a 4^3 mesh
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def load_dump(d):
+    out = {}
+    for line in open(os.path.join(d, "manifest.txt")):
+        name, ext, n = line.split()
+        dt = np.float64 if ext == "f64" else np.int32
+        a = np.fromfile(os.path.join(d, f"{name}.{ext}"), dtype=dt)
+        assert a.size == int(n), (name, a.size, n)
+        out[name] = a
+    return out
+
+
+def run(args):
+    with tempfile.TemporaryDirectory() as t:
+        d = os.path.join(t, "d")
+        cmd = [DRIVER, args[0], d] + [str(a) for a in args[1:]]
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+        return load_dump(d)
+
+
+# tag: (p, kind, nx, ny, nz, sx, sy, sz, coef, bc, pcg_iters)
+CASES = {
+    "p1_skew3_func_z": (1, "skew", 3, 3, 3, 1, 1, 1, "func", "zfaces", 10),
+    "p2_skew3_func_z": (2, "skew", 3, 3, 3, 1, 1, 1, "func", "zfaces", 10),
+    "p2_cart432_const_all": (2, "cart", 4, 3, 2, 1.0, 0.7, 0.4, "const", "all", 10),
+    "p2_skew2_func_none": (2, "skew", 2, 2, 2, 1, 1, 1, "func", "none", 5),
+    "p3_skew2_func_z": (3, "skew", 2, 2, 2, 1, 1, 1, "func", "zfaces", 10),
+    "p3_cart322_const_all": (3, "cart", 3, 2, 2, 1, 1, 1, "const", "all", 10),
+    "p4_skew2_func_z": (4, "skew", 2, 2, 2, 1, 1, 1, "func", "zfaces", 10),
+    "p5_skew2_func_all": (5, "skew", 2, 2, 2, 1, 1, 1, "func", "all", 10),
+    "p6_skew2_func_z": (6, "skew", 2, 1, 2, 1, 1, 1, "func", "zfaces", 10),
+}
+
+NUMBERING = [(1, 1, 1), (2, 2, 2), (3, 3, 3), (4, 3, 2), (2, 5, 3), (5, 5, 5), (6, 4, 7), (3, 8, 5),
+             (8, 8, 8), (7, 2, 9)]
+
+
+def main():
+    if not os.path.exists(DRIVER):
+        sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle ref` in the build container")
+    for tag, c in CASES.items():
+        d = run(["dump_case"] + list(c))
+        np.savez_compressed(os.path.join(HERE, f"case_{tag}.npz"), **d)
+        print(tag, sum(v.nbytes for v in d.values()) // 1024, "KiB raw")
+    num = {}
+    for (nx, ny, nz) in NUMBERING:
+        for p in (1, 2, 3, 4):
+            if p >= 3 and nx * ny * nz > 200:
+                continue
+            d = run(["dump_case", p, "cart", nx, ny, nz, 1, 1, 1, "const", "all", 1])
+            key = f"n{nx}_{ny}_{nz}_p{p}"
+            num[key + "_gather"] = d["gather_map"]
+            num[key + "_ndofs"] = d["ndofs"]
+            num[key + "_ess_all"] = d["ess"]
+            num[key + "_ev"] = d["elem_vertices"]
+    np.savez_compressed(os.path.join(HERE, "numbering.npz"), **num)
+    d = run(["dump_bioheat", 2, 4, 8])
+    np.savez_compressed(os.path.join(HERE, "bioheat_p2_n4.npz"), **d)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""Pins oracle/pa_oracle.c against outputs of the unmodified reference (tests/golden/*.npz,
+made by tests/golden/make_golden.py from oracle/_ref/ref_driver).  CPU only.
+
+The reference build has no FMA and the oracle is compiled with -ffp-contract=off and the same
+loop order, so agreement is expected to be bit-for-bit; the asserts allow 2e-15 relative so
+that a different libm / compiler version on another box does not turn this red.
+"""
+import numpy as np
+
+import orc
+
+RTOL = 2e-15
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    err = np.max(np.abs(a - b)) / scale
+    assert err <= rtol, f"rel err {err:.3e}"
+
+
+def make_op(c, diff=True, mass=True, ess=True):
+    return orc.Operator(c["D1D"], c["Q1D"], c["NE"], c["ndofs"], c["gather_map"], c["B"], c["G"],
+                        c["pa_diff"] if diff else None, c["pa_mass"] if mass else None,
+                        c["ess"] if ess else None)
+
+
+def test_restriction_tables(case):
+    op = make_op(case)
+    assert np.array_equal(op.offsets, case["offsets"])
+    assert np.array_equal(op.indices, case["indices"])
+
+
+def test_gather_scatter(case):
+    nd = case["D1D"] ** 3
+    xE = orc.restrict_mult(case["NE"], nd, case["gather_map"], case["x"])
+    assert np.array_equal(xE, case["xE"])
+    y = orc.restrict_mult_transpose(case["ndofs"], case["offsets"], case["indices"], case["yE_diff"])
+    assert np.array_equal(y, case["y_diff"])
+
+
+def test_setup(case):
+    D = orc.diffusion_setup(case["Q1D"], case["NE"], case["W"], case["J"], case["kq"])
+    close(D, case["pa_diff"])
+    v = orc.mass_setup(case["Q1D"], case["NE"], case["W"], case["detJ"], case["mq"])
+    close(v, case["pa_mass"])
+
+
+def test_apply_E(case):
+    c = case
+    y = orc.diffusion_apply(c["NE"], c["D1D"], c["Q1D"], c["B"], c["G"], c["pa_diff"], c["xE"])
+    close(y, c["yE_diff"])
+    y = orc.mass_apply(c["NE"], c["D1D"], c["Q1D"], c["B"], c["pa_mass"], c["xE"])
+    close(y, c["yE_mass"])
+    y = orc.diffusion_apply(c["NE"], c["D1D"], c["Q1D"], c["B"], c["G"], c["pa_diff"], c["xE"])
+    y = orc.mass_apply(c["NE"], c["D1D"], c["Q1D"], c["B"], c["pa_mass"], c["xE"], y)
+    close(y, c["yE"])
+
+
+def test_apply_L_and_diag(case):
+    op = make_op(case)
+    close(op.mult(case["x"]), case["y"])
+    close(op.diag(), case["diag"])
+    c = case
+    close(orc.diffusion_diag(c["NE"], c["D1D"], c["Q1D"], c["B"], c["G"], c["pa_diff"]), c["dE_diff"])
+    close(orc.mass_diag(c["NE"], c["D1D"], c["Q1D"], c["B"], c["pa_mass"]), c["dE_mass"])
+
+
+def test_constrained_and_rhs(case):
+    op = make_op(case)
+    close(op.constrained_mult(case["x"]), case["y_constrained"])
+    B = op.eliminate_rhs(case["x0_L"], case["b_L"])
+    close(B, case["B_rhs"])
+    dinv = op.jacobi_dinv()
+    close(orc.jacobi_mult(dinv, case["x"]), case["jacobi_z"])
+
+
+def test_pcg(case):
+    op = make_op(case)
+    dinv = op.jacobi_dinv()
+    for k in (1, 2):
+        x, it, conv, fn, norms = op.pcg(dinv, case["B_rhs"], case["X0"], 0.0, 0.0, k)
+        close(x, case[f"X_pcg{k}"], 1e-14)
+    kmax = len(case["pcg_norms"]) - 1
+    x, it, conv, fn, norms = op.pcg(dinv, case["B_rhs"], case["X0"], 0.0, 0.0, kmax)
+    assert it == kmax
+    close(x, case[f"X_pcg{kmax}"], 1e-13)
+    close(norms, case["pcg_norms"], 1e-12)
+    x, it, conv, fn, norms = op.pcg(dinv, case["B_rhs"], case["X0"], 1e-8, 0.0, 5000)
+    assert it == int(case["pcg_tol_iters"][0])
+    assert conv == bool(case["pcg_tol_converged"][0])
+    close(fn, case["pcg_tol_final_norm"][0], 1e-9)
+    close(x, case["X_pcg_tol"], 1e-12)
+
+
+def test_qpoint_ops(case):
+    c = case
+    close(orc.qvalues(c["NE"], c["D1D"], c["Q1D"], c["B"], c["xE"]), c["xq_values"])
+    close(orc.qphysgrad(c["NE"], c["D1D"], c["Q1D"], c["B"], c["G"], c["J"], c["xE"]), c["xq_physgrad"], 1e-14)
+    bE = orc.domain_lf(c["NE"], c["D1D"], c["Q1D"], c["B"], c["detJ"], c["W"], c["lf_fq"])
+    b = orc.restrict_mult_transpose(c["ndofs"], c["offsets"], c["indices"], bE)
+    close(b, c["lf_b"])
