@@ -1,0 +1,1069 @@
+// libb200pa.so — C ABI (include/b200pa.h) over the sm_100a kernels.  Contexts, level-1
+// kernel entry points, space / form handles, the fused L->L operator and the device-resident
+// Jacobi-PCG.  Multi-GPU exchange lives in comm.cu, the host-side mesh builder in hexmesh.cpp.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "elem_launch.cuh"
+#include "kernels_misc.cuh"
+#include "comm.cuh"
+
+namespace b200pa
+{
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+bool is_device_ptr(const void *p)
+{
+   if (!p) { return false; }
+   cudaPointerAttributes at;
+   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int alloc(DevBuf &buf, size_t bytes)
+{
+   if (buf.owned && buf.bytes >= bytes && buf.p) { return 0; }
+   buf.release();
+   if (bytes == 0) { bytes = 8; }
+   B200PA_CK(cudaMalloc(&buf.p, bytes));
+   buf.bytes = bytes;
+   buf.owned = true;
+   return 0;
+}
+
+int to_device(b200pa_ctx ctx, const void *src, size_t bytes, DevBuf &buf, const void **out)
+{
+   if (is_device_ptr(src)) { *out = src; return 0; }
+   if (alloc(buf, bytes)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+   *out = buf.p;
+   return 0;
+}
+
+// copies `n` doubles that may live on either side into a host vector (synchronous)
+static int to_host(b200pa_ctx ctx, const double *src, size_t n, std::vector<double> &dst)
+{
+   dst.resize(n);
+   if (is_device_ptr(src))
+   {
+      B200PA_CK(cudaMemcpyAsync(dst.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   }
+   else { std::memcpy(dst.data(), src, n * sizeof(double)); }
+   return 0;
+}
+
+static inline int grid1d(b200pa_ctx c, long long n, int bs = 256)
+{
+   long long g = (n + bs - 1) / bs;
+   const long long cap = (long long)c->num_sms * 8;
+   if (g > cap) { g = cap; }
+   return g < 1 ? 1 : (int)g;
+}
+
+static bool supported(int d1d, int q1d) { return q1d == d1d + 1 && d1d >= 2 && d1d <= 7; }
+
+int launch_element(int d1d, int q1d, int variant, const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   if (q1d != d1d + 1) { return (int)cudaErrorInvalidValue; }
+   switch (d1d)
+   {
+      case 2: return launch_element_2_3(variant, a, num_sms, stream);
+      case 3: return launch_element_3_4(variant, a, num_sms, stream);
+      case 4: return launch_element_4_5(variant, a, num_sms, stream);
+      case 5: return launch_element_5_6(variant, a, num_sms, stream);
+      case 6: return launch_element_6_7(variant, a, num_sms, stream);
+      case 7: return launch_element_7_8(variant, a, num_sms, stream);
+      default: return (int)cudaErrorInvalidValue;
+   }
+}
+
+static int run_element(b200pa_ctx ctx, int d1d, int q1d, int variant, const ElemArgs &a)
+{
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D): only orders 1..6 with Q1D = D1D+1 (no fallback kernel)");
+   const int e = launch_element(d1d, q1d, variant, a, ctx->num_sms, ctx->stream);
+   if (e != 0) { return fail(std::string("element kernel launch: ") + cudaGetErrorString((cudaError_t)e)); }
+   g_launches.fetch_add(1, std::memory_order_relaxed);
+   return 0;
+}
+
+template <int D1, int Q1>
+static void launch_diag(b200pa_ctx ctx, long long ne, const double *B, const double *G, const double *pd,
+                        const double *pm, double *dE)
+{
+   k_diag<D1, Q1><<<grid1d(ctx, ne * D1 * D1 * D1, 128), 128, 0, ctx->stream>>>(ne, B, G, pd, pm, dE);
+}
+
+static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *Bdev, const double *Gdev,
+                    const double *pd, const double *pm, double *dE)
+{
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   if (ne <= 0) { return 0; }
+   switch (d1d)
+   {
+      case 2: launch_diag<2, 3>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 3: launch_diag<3, 4>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 4: launch_diag<4, 5>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 5: launch_diag<5, 6>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 6: launch_diag<6, 7>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 7: launch_diag<7, 8>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+   }
+   B200PA_LAUNCHED();
+   return 0;
+}
+} // namespace b200pa
+
+using namespace b200pa;
+
+// ------------------------------------------------------------------------ handles
+struct b200pa_space_s
+{
+   b200pa_ctx ctx = nullptr;
+   int d1d = 0, q1d = 0, ne = 0, ndofs = 0, nd = 0;
+   long long nE = 0, nQ = 0; // E-vector entries, q-points (all elements)
+   std::vector<double> hB, hG;
+   DevBuf dB, dG;
+   DevBuf gmap, offsets, indices, slot;
+   DevBuf W, J, detJ;
+   DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
+};
+
+struct b200pa_form_s
+{
+   b200pa_space sp = nullptr;
+   DevBuf pa_diff, pa_mass;
+   bool has_diff = false, has_mass = false;
+   int n_ess = 0;
+   DevBuf ess, ess_mask, cgmap;
+   DevBuf w1, w2;       // L-sized work vectors (EliminateRHS, host entry points)
+   DevBuf r, d, z;      // PCG work vectors (linalg/solvers.cpp:855-867)
+   DevBuf state, norms; // device-resident PCG scalars
+   b200pa_comm comm = nullptr;
+};
+
+// ------------------------------------------------------------------------ misc
+extern "C" int b200pa_version(void) { return B200PA_VERSION; }
+extern "C" const char *b200pa_last_error(void) { return g_err.c_str(); }
+extern "C" long long b200pa_launch_count(void) { return g_launches.load(); }
+
+// --------------------------------------------------------------------- context
+extern "C" int b200pa_ctx_create(int device, void *stream, b200pa_ctx *out)
+{
+   B200PA_REQUIRE(out, "ctx_create: out is NULL");
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+   {
+      cudaGetLastError();
+      return fail("b200pa: no CUDA device available (this library has no CPU fallback)");
+   }
+   B200PA_REQUIRE(device >= 0 && device < ndev, "ctx_create: bad device index");
+   B200PA_CK(cudaSetDevice(device));
+   cudaDeviceProp prop;
+   B200PA_CK(cudaGetDeviceProperties(&prop, device));
+   B200PA_REQUIRE(prop.major >= 10, "b200pa: kernels are built for sm_100a only (Blackwell B200 required)");
+   b200pa_ctx c = new b200pa_ctx_s;
+   c->device = device;
+   c->num_sms = prop.multiProcessorCount;
+   if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+   else
+   {
+      B200PA_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->own_stream = true;
+   }
+   B200PA_CK(cudaMalloc(&c->d_partials, sizeof(double) * MAX_RED_BLOCKS * 2));
+   B200PA_CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
+   B200PA_CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
+   B200PA_CK(cudaMalloc(&c->d_result, sizeof(double) * 8));
+   B200PA_CK(cudaMallocHost(&c->h_result, sizeof(double) * 8));
+   B200PA_CK(cudaDeviceSynchronize());
+   *out = c;
+   return 0;
+}
+
+extern "C" int b200pa_ctx_destroy(b200pa_ctx c)
+{
+   if (!c) { return 0; }
+   cudaSetDevice(c->device);
+   cudaStreamSynchronize(c->stream);
+   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFreeHost(c->h_result);
+   if (c->own_stream) { cudaStreamDestroy(c->stream); }
+   delete c;
+   return 0;
+}
+
+extern "C" int b200pa_ctx_sync(b200pa_ctx c)
+{
+   B200PA_REQUIRE(c, "ctx is NULL");
+   B200PA_CK(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+extern "C" void *b200pa_ctx_stream(b200pa_ctx c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int b200pa_ctx_upload(b200pa_ctx c, void *dst_dev, const void *src_host, size_t bytes)
+{
+   B200PA_REQUIRE(c && (bytes == 0 || (dst_dev && src_host)), "ctx_upload: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   if (bytes) { B200PA_CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream)); }
+   B200PA_CK(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+extern "C" int b200pa_ctx_download(b200pa_ctx c, void *dst_host, const void *src_dev, size_t bytes)
+{
+   B200PA_REQUIRE(c && (bytes == 0 || (dst_host && src_dev)), "ctx_download: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   if (bytes) { B200PA_CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream)); }
+   B200PA_CK(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// --------------------------------------------------------- level 1: kernel-level
+#define NEED_CTX(c) B200PA_REQUIRE((c) != nullptr, "ctx is NULL"); B200PA_CK(cudaSetDevice((c)->device))
+
+extern "C" int b200pa_restrict_mult(b200pa_ctx ctx, int ne, int nd, const int *gmap, const double *x, double *y)
+{
+   NEED_CTX(ctx);
+   const long long n = (long long)ne * nd;
+   if (n == 0) { return 0; }
+   k_restrict_mult<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, gmap, x, y);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_restrict_mult_transpose(b200pa_ctx ctx, int ndofs, const int *offsets, const int *indices,
+                                              const double *xE, double *yL, int abs)
+{
+   NEED_CTX(ctx);
+   if (ndofs == 0) { return 0; }
+   k_restrict_mult_transpose<<<grid1d(ctx, ndofs), 256, 0, ctx->stream>>>(ndofs, offsets, indices, xE, yL, abs);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_diffusion_setup(b200pa_ctx ctx, int q1d, int ne, const double *W, const double *J,
+                                      const double *C, long long nc, double *D)
+{
+   NEED_CTX(ctx);
+   const long long NQ = (long long)q1d * q1d * q1d;
+   B200PA_REQUIRE(nc == 1 || nc == NQ * ne, "diffusion_setup: coefficient must have 1 or Q^3*NE entries");
+   if (ne == 0) { return 0; }
+   k_diffusion_setup<<<grid1d(ctx, NQ * ne), 256, 0, ctx->stream>>>(NQ, ne, W, J, C, nc == 1, D);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_mass_setup(b200pa_ctx ctx, int nq, int ne, const double *W, const double *detJ,
+                                 const double *C, long long nc, double *v)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(nc == 1 || nc == (long long)nq * ne, "mass_setup: coefficient must have 1 or NQ*NE entries");
+   if (ne == 0) { return 0; }
+   k_mass_setup<<<grid1d(ctx, (long long)nq * ne), 256, 0, ctx->stream>>>(nq, ne, W, detJ, C, nc == 1, v);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+namespace
+{
+// B/G that may be host or device -> host vectors for the kernel-parameter constant bank
+struct HostBG
+{
+   std::vector<double> B, G;
+   int get(b200pa_ctx ctx, int d1d, int q1d, const double *B_any, const double *G_any)
+   {
+      B200PA_REQUIRE(B_any, "B is NULL");
+      if (to_host(ctx, B_any, (size_t)d1d * q1d, B)) { return 1; }
+      if (G_any) { if (to_host(ctx, G_any, (size_t)d1d * q1d, G)) { return 1; } }
+      else { G.assign((size_t)d1d * q1d, 0.0); }
+      return 0;
+   }
+};
+} // namespace
+
+extern "C" int b200pa_diffusion_apply(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G,
+                                      const double *D, const double *xE, double *yE)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, G)) { return 1; }
+   ElemArgs a;
+   a.B = h.B.data(); a.G = h.G.data(); a.NE = ne; a.x = xE; a.y = yE; a.pa_diff = D;
+   return run_element(ctx, d1d, q1d, EV_APPLY_E, a);
+}
+
+extern "C" int b200pa_mass_apply(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *v,
+                                 const double *xE, double *yE)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, nullptr)) { return 1; }
+   ElemArgs a;
+   a.B = h.B.data(); a.G = h.G.data(); a.NE = ne; a.x = xE; a.y = yE; a.pa_mass = v;
+   return run_element(ctx, d1d, q1d, EV_APPLY_E, a);
+}
+
+static int diag_common(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G, const double *pd,
+                       const double *pm, double *dE)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   DevBuf bB, bG;
+   const void *dB = nullptr, *dG = nullptr;
+   std::vector<double> zero((size_t)d1d * q1d, 0.0);
+   int rc = to_device(ctx, B, sizeof(double) * d1d * q1d, bB, &dB);
+   if (!rc) { rc = to_device(ctx, G ? G : zero.data(), sizeof(double) * d1d * q1d, bG, &dG); }
+   if (!rc) { rc = run_diag(ctx, d1d, q1d, ne, (const double *)dB, (const double *)dG, pd, pm, dE); }
+   if (!rc && (bB.owned || bG.owned)) { cudaStreamSynchronize(ctx->stream); }
+   bB.release(); bG.release();
+   return rc;
+}
+
+extern "C" int b200pa_diffusion_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G,
+                                     const double *D, double *dE)
+{
+   return diag_common(ctx, ne, d1d, q1d, B, G, D, nullptr, dE);
+}
+extern "C" int b200pa_mass_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *v, double *dE)
+{
+   return diag_common(ctx, ne, d1d, q1d, B, nullptr, nullptr, v, dE);
+}
+
+extern "C" int b200pa_qvalues(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *xE, double *yq)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, nullptr)) { return 1; }
+   ElemArgs a;
+   a.B = h.B.data(); a.G = h.G.data(); a.NE = ne; a.x = xE; a.y = yq;
+   return run_element(ctx, d1d, q1d, EV_VALUES_E, a);
+}
+
+extern "C" int b200pa_qphysgrad(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G,
+                                const double *J, const double *xE, double *gq)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, G)) { return 1; }
+   ElemArgs a;
+   a.B = h.B.data(); a.G = h.G.data(); a.NE = ne; a.x = xE; a.y = gq; a.J = J;
+   return run_element(ctx, d1d, q1d, EV_PHYSGRAD_E, a);
+}
+
+extern "C" int b200pa_domain_lf(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *detJ,
+                                const double *W, const double *f, long long nf, double *bE)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
+   B200PA_REQUIRE(nf == 1 || nf == (long long)q1d * q1d * q1d * ne, "domain_lf: f must have 1 or Q^3*NE entries");
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, nullptr)) { return 1; }
+   ElemArgs a;
+   a.B = h.B.data(); a.G = h.G.data(); a.NE = ne; a.y = bE; a.detJ = detJ; a.W = W; a.f = f; a.nf = nf;
+   return run_element(ctx, d1d, q1d, EV_LF_E, a);
+}
+
+static int dot_async(b200pa_ctx ctx, long long n, const double *a, const double *b, double *out_dev)
+{
+   k_dot<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, a, b, ctx->d_partials, ctx->d_ticket, out_dev);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_dot(b200pa_ctx ctx, long long n, const double *a, const double *b, double *result_host)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(result_host, "dot: result is NULL");
+   if (dot_async(ctx, n, a, b, ctx->d_result)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   *result_host = ctx->h_result[0];
+   return 0;
+}
+
+extern "C" int b200pa_add(b200pa_ctx ctx, long long n, const double *v1, double alpha, const double *v2, double *v)
+{
+   NEED_CTX(ctx);
+   if (n == 0) { return 0; }
+   k_add<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, v1, alpha, v2, v);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_jacobi_setup(b200pa_ctx ctx, int n, const double *diag, int n_ess, const int *ess, double damping,
+                                   double *dinv)
+{
+   NEED_CTX(ctx);
+   int *flag = (int *)(ctx->d_ticket + 2);
+   B200PA_CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+   if (n > 0)
+   {
+      k_jacobi_setup<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, diag, damping, dinv, flag);
+      B200PA_LAUNCHED();
+   }
+   if (n_ess > 0)
+   {
+      // linalg/solvers.cpp:419-424: dinv = damping on essential dofs (diag treated as 1)
+      k_set_indexed<<<grid1d(ctx, n_ess), 256, 0, ctx->stream>>>(n_ess, ess, damping, dinv);
+      B200PA_LAUNCHED();
+   }
+   int h = 0;
+   B200PA_CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   // the reference aborts on a zero diagonal entry (linalg/solvers.cpp:410-413); a zero on an
+   // essential dof is overwritten above, exactly as there the check runs before the overwrite
+   B200PA_REQUIRE(h == 0, "jacobi_setup: zero diagonal entry in OperatorJacobiSmoother");
+   return 0;
+}
+
+extern "C" int b200pa_jacobi_mult(b200pa_ctx ctx, int n, const double *dinv, const double *r, double *z)
+{
+   NEED_CTX(ctx);
+   if (n == 0) { return 0; }
+   k_jacobi_mult<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, dinv, r, z);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_coeff_eval(b200pa_ctx ctx, int kind, long long n, double a, double b, double T0, const double *T,
+                                 const double *s, const double *g, double *out)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(kind >= 0 && kind <= 2, "coeff_eval: kind must be 0, 1 or 2");
+   if (n == 0) { return 0; }
+   k_coeff_eval<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(kind, n, a, b, T0, T, s, g, out);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+// ------------------------------------------------------------------------ space
+extern "C" int b200pa_space_create(b200pa_ctx ctx, int d1d, int q1d, int ne, int ndofs, const int *gather_map_any,
+                                   const double *B_any, const double *G_any, b200pa_space *out)
+{
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(out, "space_create: out is NULL");
+   B200PA_REQUIRE(supported(d1d, q1d),
+                  "space_create: unsupported (D1D,Q1D); orders 1..6 with the default rule only, no fallback kernel");
+   B200PA_REQUIRE(ne >= 0 && ndofs >= 0 && gather_map_any && B_any && G_any, "space_create: bad arguments");
+   const long long nE = (long long)ne * d1d * d1d * d1d;
+   B200PA_REQUIRE(nE < (1LL << 31), "space_create: E-vector exceeds int32 indexing (split the mesh over ranks)");
+   b200pa_space sp = new b200pa_space_s;
+   sp->ctx = ctx; sp->d1d = d1d; sp->q1d = q1d; sp->ne = ne; sp->ndofs = ndofs; sp->nd = d1d * d1d * d1d;
+   sp->nE = nE; sp->nQ = (long long)ne * q1d * q1d * q1d;
+   auto bail = [&](int rc) { b200pa_space_destroy(sp); return rc; };
+   if (to_host(ctx, B_any, (size_t)d1d * q1d, sp->hB) || to_host(ctx, G_any, (size_t)d1d * q1d, sp->hG)) { return bail(1); }
+   if (alloc(sp->dB, sizeof(double) * d1d * q1d) || alloc(sp->dG, sizeof(double) * d1d * q1d)) { return bail(1); }
+   cudaMemcpyAsync(sp->dB.p, sp->hB.data(), sizeof(double) * d1d * q1d, cudaMemcpyHostToDevice, ctx->stream);
+   cudaMemcpyAsync(sp->dG.p, sp->hG.data(), sizeof(double) * d1d * q1d, cudaMemcpyHostToDevice, ctx->stream);
+
+   if (alloc(sp->gmap, sizeof(int) * std::max<long long>(nE, 1))) { return bail(1); }
+   if (nE > 0)
+   {
+      cudaMemcpyAsync(sp->gmap.p, gather_map_any, sizeof(int) * nE,
+                      is_device_ptr(gather_map_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+   }
+   if (alloc(sp->offsets, sizeof(int) * ((size_t)ndofs + 1)) || alloc(sp->indices, sizeof(int) * std::max<long long>(nE, 1)) ||
+       alloc(sp->slot, sizeof(int) * std::max<long long>(nE, 1)))
+   {
+      return bail(1);
+   }
+   if (nE > 0)
+   {
+      // reject sign-encoded / out-of-range entries (H1 has none; fem/restriction.cpp:96-97)
+      int *flag = (int *)(ctx->d_ticket + 2);
+      cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
+      k_check_nonneg<<<grid1d(ctx, nE), 256, 0, ctx->stream>>>(nE, sp->gmap.as<int>(), ndofs, flag);
+      g_launches++;
+      int h = 0;
+      cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { fail("space_create: CUDA error while checking gather_map"); return bail(1); }
+      if (h) { fail("space_create: gather_map has negative (sign-encoded) or out-of-range entries"); return bail(1); }
+
+      // CSR (offsets, indices) as fem/restriction.cpp:66-106: entries of one L-dof in ascending
+      // E-index order == stable sort of E-positions by their L-dof
+      DevBuf keys_out, iota, temp;
+      if (alloc(keys_out, sizeof(int) * nE) || alloc(iota, sizeof(int) * nE)) { return bail(1); }
+      k_iota<<<grid1d(ctx, nE), 256, 0, ctx->stream>>>(nE, iota.as<int>());
+      g_launches++;
+      size_t tb = 0;
+      int end_bit = 1;
+      while ((1LL << end_bit) < ndofs && end_bit < 31) { ++end_bit; }
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, sp->gmap.as<int>(), keys_out.as<int>(), iota.as<int>(),
+                                      sp->indices.as<int>(), (int)nE, 0, end_bit, ctx->stream);
+      if (alloc(temp, tb)) { keys_out.release(); iota.release(); return bail(1); }
+      cudaError_t e = cub::DeviceRadixSort::SortPairs(temp.p, tb, sp->gmap.as<int>(), keys_out.as<int>(), iota.as<int>(),
+                                                      sp->indices.as<int>(), (int)nE, 0, end_bit, ctx->stream);
+      if (e == cudaSuccess)
+      {
+         k_offsets_from_sorted<<<grid1d(ctx, ndofs + 1), 256, 0, ctx->stream>>>(ndofs, nE, keys_out.as<int>(), sp->offsets.as<int>());
+         k_invert_perm<<<grid1d(ctx, nE), 256, 0, ctx->stream>>>(nE, sp->indices.as<int>(), sp->slot.as<int>());
+         g_launches += 2;
+         e = cudaStreamSynchronize(ctx->stream);
+      }
+      keys_out.release(); iota.release(); temp.release();
+      if (e != cudaSuccess) { fail(std::string("space_create: CSR build failed: ") + cudaGetErrorString(e)); return bail(1); }
+   }
+   else
+   {
+      cudaMemsetAsync(sp->offsets.p, 0, sizeof(int) * ((size_t)ndofs + 1), ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+   }
+   *out = sp;
+   return 0;
+}
+
+extern "C" int b200pa_space_destroy(b200pa_space sp)
+{
+   if (!sp) { return 0; }
+   cudaSetDevice(sp->ctx->device);
+   cudaStreamSynchronize(sp->ctx->stream);
+   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->scratchE})
+   {
+      b->release();
+   }
+   delete sp;
+   return 0;
+}
+
+static int borrow_or_copy(b200pa_ctx ctx, const double *src, size_t n, DevBuf &buf)
+{
+   buf.release();
+   if (is_device_ptr(src)) { buf.p = (void *)src; buf.bytes = n * sizeof(double); buf.owned = false; return 0; }
+   if (alloc(buf, n * sizeof(double))) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(buf.p, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+extern "C" int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, const double *J_any, const double *detJ_any)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   const size_t q3 = (size_t)sp->q1d * sp->q1d * sp->q1d;
+   if (W_any)
+   {
+      std::vector<double> w;
+      if (to_host(sp->ctx, W_any, q3, w)) { return 1; }
+      if (alloc(sp->W, q3 * sizeof(double))) { return 1; }
+      B200PA_CK(cudaMemcpyAsync(sp->W.p, w.data(), q3 * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(sp->ctx->stream));
+   }
+   if (J_any) { if (borrow_or_copy(sp->ctx, J_any, 9 * (size_t)sp->nQ, sp->J)) { return 1; } }
+   if (detJ_any) { if (borrow_or_copy(sp->ctx, detJ_any, (size_t)sp->nQ, sp->detJ)) { return 1; } }
+   return 0;
+}
+
+// Gauss-Legendre points on [0,1] (fem/intrules.cpp GaussLegendre: Newton on the Legendre recurrence)
+static void gauss_legendre_01(int n, double *x)
+{
+   for (int i = 0; i < n; ++i)
+   {
+      double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 0.0;
+      for (int it = 0; it < 100; ++it)
+      {
+         double p1 = 1.0, p2 = 0.0;
+         for (int j = 1; j <= n; ++j) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j; }
+         pp = n * (z * p1 - p2) / (z * z - 1.0);
+         const double dz = p1 / pp;
+         z -= dz;
+         if (fabs(dz) < 1e-16) { break; }
+      }
+      x[n - 1 - i] = 0.5 * (1.0 + z);
+   }
+}
+
+extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv, const double *vertices_any,
+                                                   const int *elem_vertices_any)
+{
+   B200PA_REQUIRE(sp && W_any && vertices_any && elem_vertices_any, "geometry_from_vertices: NULL argument");
+   NEED_CTX(sp->ctx);
+   b200pa_ctx ctx = sp->ctx;
+   if (b200pa_space_set_geometry(sp, W_any, nullptr, nullptr)) { return 1; }
+   DevBuf bv, bev, bxi;
+   const void *dv = nullptr, *dev = nullptr;
+   int rc = to_device(ctx, vertices_any, sizeof(double) * 3 * (size_t)nv, bv, &dv);
+   if (!rc && !is_device_ptr(elem_vertices_any))
+   {
+      rc = alloc(bev, sizeof(int) * 8 * (size_t)std::max(sp->ne, 1));
+      if (!rc) { cudaMemcpyAsync(bev.p, elem_vertices_any, sizeof(int) * 8 * (size_t)sp->ne, cudaMemcpyHostToDevice, ctx->stream); dev = bev.p; }
+   }
+   else { dev = elem_vertices_any; }
+   double xi[16];
+   gauss_legendre_01(sp->q1d, xi);
+   if (!rc) { rc = alloc(bxi, sizeof(double) * 16); }
+   if (!rc) { cudaMemcpyAsync(bxi.p, xi, sizeof(double) * sp->q1d, cudaMemcpyHostToDevice, ctx->stream); }
+   sp->J.release(); sp->detJ.release();
+   if (!rc) { rc = alloc(sp->J, sizeof(double) * 9 * (size_t)std::max<long long>(sp->nQ, 1)); }
+   if (!rc) { rc = alloc(sp->detJ, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1)); }
+   if (!rc && sp->ne > 0)
+   {
+      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, bxi.as<double>(), (const double *)dv,
+                                                                       (const int *)dev, sp->J.as<double>(), sp->detJ.as<double>());
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("geometry kernel launch failed"); }
+   }
+   cudaStreamSynchronize(ctx->stream);
+   bv.release(); bev.release(); bxi.release();
+   return rc;
+}
+
+extern "C" const int *b200pa_space_offsets(b200pa_space sp) { return sp ? sp->offsets.as<int>() : nullptr; }
+extern "C" const int *b200pa_space_indices(b200pa_space sp) { return sp ? sp->indices.as<int>() : nullptr; }
+extern "C" const int *b200pa_space_gather_map(b200pa_space sp) { return sp ? sp->gmap.as<int>() : nullptr; }
+extern "C" const double *b200pa_space_J(b200pa_space sp) { return sp ? sp->J.as<double>() : nullptr; }
+extern "C" const double *b200pa_space_detJ(b200pa_space sp) { return sp ? sp->detJ.as<double>() : nullptr; }
+extern "C" const double *b200pa_space_W(b200pa_space sp) { return sp ? sp->W.as<double>() : nullptr; }
+
+static int need_scratch(b200pa_space sp)
+{
+   return alloc(sp->scratchE, sizeof(double) * (size_t)std::max<long long>(sp->nE, 1));
+}
+
+static ElemArgs space_args(b200pa_space sp)
+{
+   ElemArgs a;
+   a.B = sp->hB.data(); a.G = sp->hG.data(); a.NE = sp->ne;
+   return a;
+}
+
+// ---- q-point operators straight from an L-vector (gather fused in)
+extern "C" int b200pa_space_qvalues(b200pa_space sp, const double *xL_dev, double *yq_dev)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   ElemArgs a = space_args(sp);
+   a.x = xL_dev; a.gmap = sp->gmap.as<int>(); a.y = yq_dev;
+   return run_element(sp->ctx, sp->d1d, sp->q1d, EV_VALUES_L, a);
+}
+
+extern "C" int b200pa_space_qphysgrad(b200pa_space sp, const double *xL_dev, double *gq_dev)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   B200PA_REQUIRE(sp->J.p, "space has no geometry (call b200pa_space_set_geometry)");
+   ElemArgs a = space_args(sp);
+   a.x = xL_dev; a.gmap = sp->gmap.as<int>(); a.y = gq_dev; a.J = sp->J.as<double>();
+   return run_element(sp->ctx, sp->d1d, sp->q1d, EV_PHYSGRAD_L, a);
+}
+
+extern "C" int b200pa_space_coeff_linear(b200pa_space sp, double a0, double b0, double T0, const double *TL_dev, double *out_q_dev)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   ElemArgs a = space_args(sp);
+   a.x = TL_dev; a.gmap = sp->gmap.as<int>(); a.y = out_q_dev; a.ca = a0; a.cb = b0; a.cT0 = T0;
+   return run_element(sp->ctx, sp->d1d, sp->q1d, EV_COEFF_L, a);
+}
+
+extern "C" int b200pa_space_joule(b200pa_space sp, const double *phiL_dev, const double *sigma_q_dev, double add,
+                                  double *out_q_dev)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   B200PA_REQUIRE(sp->J.p, "space has no geometry (call b200pa_space_set_geometry)");
+   ElemArgs a = space_args(sp);
+   a.x = phiL_dev; a.gmap = sp->gmap.as<int>(); a.y = out_q_dev; a.J = sp->J.as<double>(); a.s = sigma_q_dev; a.ca = add;
+   return run_element(sp->ctx, sp->d1d, sp->q1d, EV_JOULE_L, a);
+}
+
+// LinearForm with DomainLFIntegrator + UseFastAssembly (fem/linearform.cpp:162-184): b_L = R^T b_E
+extern "C" int b200pa_space_domain_lf(b200pa_space sp, const double *f_dev, long long nf, double *bL_dev)
+{
+   B200PA_REQUIRE(sp, "space is NULL");
+   NEED_CTX(sp->ctx);
+   B200PA_REQUIRE(sp->detJ.p && sp->W.p, "space has no geometry (call b200pa_space_set_geometry)");
+   B200PA_REQUIRE(nf == 1 || nf == sp->nQ, "domain_lf: f must have 1 or Q^3*NE entries");
+   if (need_scratch(sp)) { return 1; }
+   ElemArgs a = space_args(sp);
+   a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>(); a.detJ = sp->detJ.as<double>(); a.W = sp->W.as<double>();
+   a.f = f_dev; a.nf = nf;
+   if (run_element(sp->ctx, sp->d1d, sp->q1d, EV_LF_S, a)) { return 1; }
+   if (sp->ndofs > 0)
+   {
+      k_segment_sum<false, false, false><<<grid1d(sp->ctx, sp->ndofs), 256, 0, sp->ctx->stream>>>(
+         sp->ndofs, sp->offsets.as<int>(), sp->scratchE.as<double>(), bL_dev, nullptr, nullptr, nullptr, nullptr, nullptr,
+         nullptr, nullptr);
+      B200PA_LAUNCHED();
+   }
+   return 0;
+}
+
+// ------------------------------------------------------------------------- form
+extern "C" int b200pa_form_create(b200pa_space sp, b200pa_form *out)
+{
+   B200PA_REQUIRE(sp && out, "form_create: NULL argument");
+   NEED_CTX(sp->ctx);
+   b200pa_form f = new b200pa_form_s;
+   f->sp = sp;
+   if (need_scratch(sp)) { delete f; return 1; }
+   *out = f;
+   return 0;
+}
+
+extern "C" int b200pa_form_destroy(b200pa_form f)
+{
+   if (!f) { return 0; }
+   cudaSetDevice(f->sp->ctx->device);
+   cudaStreamSynchronize(f->sp->ctx->stream);
+   for (DevBuf *b : {&f->pa_diff, &f->pa_mass, &f->ess, &f->ess_mask, &f->cgmap, &f->w1, &f->w2, &f->r, &f->d, &f->z, &f->state, &f->norms})
+   {
+      b->release();
+   }
+   delete f;
+   return 0;
+}
+
+extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any, long long nc)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   b200pa_space sp = f->sp;
+   NEED_CTX(sp->ctx);
+   if (!C_any) { f->pa_diff.release(); f->has_diff = false; return 0; }
+   B200PA_REQUIRE(sp->J.p && sp->W.p, "assemble_diffusion: space has no geometry");
+   B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_diffusion: coefficient must have 1 or Q^3*NE entries");
+   DevBuf cb;
+   const void *dC = nullptr;
+   if (to_device(sp->ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
+   if (!f->pa_diff.owned) { f->pa_diff.release(); }
+   int rc = alloc(f->pa_diff, sizeof(double) * 6 * (size_t)std::max<long long>(sp->nQ, 1));
+   if (!rc) { rc = b200pa_diffusion_setup(sp->ctx, sp->q1d, sp->ne, sp->W.as<double>(), sp->J.as<double>(), (const double *)dC, nc, f->pa_diff.as<double>()); }
+   if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
+   f->has_diff = (rc == 0);
+   return rc;
+}
+
+extern "C" int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, long long nc)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   b200pa_space sp = f->sp;
+   NEED_CTX(sp->ctx);
+   if (!C_any) { f->pa_mass.release(); f->has_mass = false; return 0; }
+   B200PA_REQUIRE(sp->detJ.p && sp->W.p, "assemble_mass: space has no geometry");
+   B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_mass: coefficient must have 1 or Q^3*NE entries");
+   DevBuf cb;
+   const void *dC = nullptr;
+   if (to_device(sp->ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
+   if (!f->pa_mass.owned) { f->pa_mass.release(); }
+   int rc = alloc(f->pa_mass, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1));
+   if (!rc) { rc = b200pa_mass_setup(sp->ctx, sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(), sp->detJ.as<double>(), (const double *)dC, nc, f->pa_mass.as<double>()); }
+   if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
+   f->has_mass = (rc == 0);
+   return rc;
+}
+
+extern "C" int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev, const double *pa_mass_dev)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   f->pa_diff.release(); f->pa_mass.release();
+   f->has_diff = pa_diff_dev != nullptr; f->has_mass = pa_mass_dev != nullptr;
+   if (pa_diff_dev)
+   {
+      B200PA_REQUIRE(is_device_ptr(pa_diff_dev), "set_pa_data: pa_diff must be a device pointer");
+      f->pa_diff.p = (void *)pa_diff_dev;
+   }
+   if (pa_mass_dev)
+   {
+      B200PA_REQUIRE(is_device_ptr(pa_mass_dev), "set_pa_data: pa_mass must be a device pointer");
+      f->pa_mass.p = (void *)pa_mass_dev;
+   }
+   return 0;
+}
+extern "C" const double *b200pa_form_pa_diff(b200pa_form f) { return f && f->has_diff ? f->pa_diff.as<double>() : nullptr; }
+extern "C" const double *b200pa_form_pa_mass(b200pa_form f) { return f && f->has_mass ? f->pa_mass.as<double>() : nullptr; }
+
+extern "C" int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(n_ess >= 0 && (n_ess == 0 || ess_any), "set_essential: bad arguments");
+   f->n_ess = n_ess;
+   if (alloc(f->ess_mask, (size_t)std::max(sp->ndofs, 1))) { return 1; }
+   B200PA_CK(cudaMemsetAsync(f->ess_mask.p, 0, (size_t)std::max(sp->ndofs, 1), ctx->stream));
+   if (alloc(f->ess, sizeof(int) * (size_t)std::max(n_ess, 1))) { return 1; }
+   if (n_ess > 0)
+   {
+      B200PA_CK(cudaMemcpyAsync(f->ess.p, ess_any, sizeof(int) * (size_t)n_ess,
+                                is_device_ptr(ess_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      int *flag = (int *)(ctx->d_ticket + 2);
+      B200PA_CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      k_check_nonneg<<<grid1d(ctx, n_ess), 256, 0, ctx->stream>>>(n_ess, f->ess.as<int>(), sp->ndofs, flag);
+      B200PA_LAUNCHED();
+      int h = 0;
+      B200PA_CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(ctx->stream));
+      B200PA_REQUIRE(h == 0, "set_essential: essential dof index out of range");
+      k_mask_indexed<<<grid1d(ctx, n_ess), 256, 0, ctx->stream>>>(n_ess, f->ess.as<int>(), f->ess_mask.as<unsigned char>());
+      B200PA_LAUNCHED();
+   }
+   if (alloc(f->cgmap, sizeof(int) * (size_t)std::max<long long>(sp->nE, 1))) { return 1; }
+   if (sp->nE > 0)
+   {
+      k_constrain_gmap<<<grid1d(ctx, sp->nE), 256, 0, ctx->stream>>>(sp->nE, sp->gmap.as<int>(), f->ess_mask.as<unsigned char>(), f->cgmap.as<int>());
+      B200PA_LAUNCHED();
+   }
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+// y = A x (constrained: ConstrainedOperator::Mult, DIAG_ONE).  dot_out != NULL adds x.y (owned dofs)
+// into the segmented reduction's epilogue.  done: PCG early-exit flag.
+static int form_apply(b200pa_form f, const double *x, double *y, bool constrained, double *dot_out, const int *done)
+{
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   B200PA_REQUIRE(f->has_diff || f->has_mass, "form has no assembled integrator");
+   if (constrained) { B200PA_REQUIRE(f->cgmap.p, "form has no essential-dof list (call b200pa_form_set_essential, n_ess may be 0)"); }
+   const unsigned char *own = f->comm ? comm_owner_mask(f->comm) : nullptr;
+   // multi-GPU: x is a consistent L-vector (ghost copies equal the owner's value); see comm.cu
+   ElemArgs a = space_args(sp);
+   a.x = x; a.gmap = constrained ? f->cgmap.as<int>() : sp->gmap.as<int>();
+   a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>();
+   a.pa_diff = f->has_diff ? f->pa_diff.as<double>() : nullptr;
+   a.pa_mass = f->has_mass ? f->pa_mass.as<double>() : nullptr;
+   a.done = done;
+   if (run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
+   if (sp->ndofs == 0) { return 0; }
+   const int grid = grid1d(ctx, sp->ndofs);
+   const int *off = sp->offsets.as<int>();
+   const double *yS = sp->scratchE.as<double>();
+   const unsigned char *em = f->ess_mask.as<unsigned char>();
+   if (f->comm)
+   {
+      // partial sums -> exchange over NVLink -> constrained fix-up + dot in a second pass
+      k_segment_sum<false, false, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr, nullptr, done);
+      B200PA_LAUNCHED();
+      if (comm_exchange_sum(f->comm, y, done)) { return 1; }
+      if (constrained || dot_out)
+      {
+         k_fixup_dot<<<grid, 256, 0, ctx->stream>>>(sp->ndofs, y, constrained ? em : nullptr, x, own, dot_out != nullptr,
+                                                   ctx->d_partials, ctx->d_ticket, dot_out, done);
+         B200PA_LAUNCHED();
+      }
+      return 0;
+   }
+   if (constrained && dot_out)
+   {
+      k_segment_sum<true, true, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, own, ctx->d_partials,
+                                                                    ctx->d_ticket, dot_out, done);
+   }
+   else if (constrained)
+   {
+      k_segment_sum<true, false, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, own, nullptr, nullptr, nullptr, done);
+   }
+   else if (dot_out)
+   {
+      k_segment_sum<false, true, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, own, ctx->d_partials,
+                                                                     ctx->d_ticket, dot_out, done);
+   }
+   else
+   {
+      k_segment_sum<false, false, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr, nullptr, done);
+   }
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_form_mult(b200pa_form f, const double *x_dev, double *y_dev)
+{
+   B200PA_REQUIRE(f && x_dev && y_dev, "form_mult: NULL argument");
+   NEED_CTX(f->sp->ctx);
+   return form_apply(f, x_dev, y_dev, false, nullptr, nullptr);
+}
+
+extern "C" int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_dev)
+{
+   B200PA_REQUIRE(f && x_dev && y_dev, "form_constrained_mult: NULL argument");
+   NEED_CTX(f->sp->ctx);
+   return form_apply(f, x_dev, y_dev, true, nullptr, nullptr);
+}
+
+static int need_work(b200pa_form f)
+{
+   const size_t b = sizeof(double) * (size_t)std::max(f->sp->ndofs, 1);
+   return alloc(f->w1, b) || alloc(f->w2, b);
+}
+
+extern "C" int b200pa_form_mult_host(b200pa_form f, int constrained, const double *x_host, double *y_host)
+{
+   B200PA_REQUIRE(f && x_host && y_host, "form_mult_host: NULL argument");
+   b200pa_ctx ctx = f->sp->ctx;
+   NEED_CTX(ctx);
+   if (need_work(f)) { return 1; }
+   const size_t b = sizeof(double) * (size_t)f->sp->ndofs;
+   B200PA_CK(cudaMemcpyAsync(f->w1.p, x_host, b, cudaMemcpyHostToDevice, ctx->stream));
+   if (form_apply(f, f->w1.as<double>(), f->w2.as<double>(), constrained != 0, nullptr, nullptr)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(y_host, f->w2.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
+{
+   B200PA_REQUIRE(f && diag_dev, "form_assemble_diagonal: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(f->has_diff || f->has_mass, "form has no assembled integrator");
+   // fem/bilinearform_ext.cpp:401-423: localY = 0; every integrator adds; AbsMultTranspose
+   B200PA_CK(cudaMemsetAsync(sp->scratchE.p, 0, sizeof(double) * (size_t)sp->nE, ctx->stream));
+   if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->dB.as<double>(), sp->dG.as<double>(),
+                f->has_diff ? f->pa_diff.as<double>() : nullptr, f->has_mass ? f->pa_mass.as<double>() : nullptr,
+                sp->scratchE.as<double>()))
+   {
+      return 1;
+   }
+   if (b200pa_restrict_mult_transpose(ctx, sp->ndofs, sp->offsets.as<int>(), sp->indices.as<int>(), sp->scratchE.as<double>(),
+                                      diag_dev, 1))
+   {
+      return 1;
+   }
+   // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293-330): P^T of the local diagonal
+   if (f->comm) { return comm_exchange_sum(f->comm, diag_dev, nullptr); }
+   return 0;
+}
+
+extern "C" int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, double *b_dev)
+{
+   B200PA_REQUIRE(f && x_dev && b_dev, "form_eliminate_rhs: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(f->cgmap.p, "form has no essential-dof list");
+   if (need_work(f)) { return 1; }
+   const int n = sp->ndofs;
+   // linalg/operator.cpp:559-584: w = 0; w[ess] = x[ess]; z = A w; b -= z; b[ess] = x[ess]
+   B200PA_CK(cudaMemsetAsync(f->w1.p, 0, sizeof(double) * (size_t)n, ctx->stream));
+   if (f->n_ess > 0)
+   {
+      k_copy_indexed<<<grid1d(ctx, f->n_ess), 256, 0, ctx->stream>>>(f->n_ess, f->ess.as<int>(), x_dev, f->w1.as<double>());
+      B200PA_LAUNCHED();
+   }
+   if (form_apply(f, f->w1.as<double>(), f->w2.as<double>(), false, nullptr, nullptr)) { return 1; }
+   if (n > 0)
+   {
+      k_sub_inplace<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, b_dev, f->w2.as<double>());
+      B200PA_LAUNCHED();
+   }
+   if (f->n_ess > 0)
+   {
+      k_copy_indexed<<<grid1d(ctx, f->n_ess), 256, 0, ctx->stream>>>(f->n_ess, f->ess.as<int>(), x_dev, b_dev);
+      B200PA_LAUNCHED();
+   }
+   return 0;
+}
+
+// -------------------------------------------------------------------------- PCG
+extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const double *b_dev, double *x_dev, double rel_tol,
+                                double abs_tol, int max_iter, b200pa_pcg_result *res, double *norms_host)
+{
+   B200PA_REQUIRE(f && dinv_dev && b_dev && x_dev && res, "pcg_solve: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(max_iter >= 0, "pcg_solve: max_iter < 0");
+   B200PA_REQUIRE(f->cgmap.p, "pcg_solve: call b200pa_form_set_essential first (n_ess may be 0)");
+   const int n = sp->ndofs;
+   const size_t vb = sizeof(double) * (size_t)std::max(n, 1);
+   if (alloc(f->r, vb) || alloc(f->d, vb) || alloc(f->z, vb)) { return 1; }
+   if (alloc(f->state, sizeof(PcgState))) { return 1; }
+   if (alloc(f->norms, sizeof(double) * ((size_t)max_iter + 2))) { return 1; }
+   double *r = f->r.as<double>(), *d = f->d.as<double>(), *z = f->z.as<double>();
+   PcgState *st = f->state.as<PcgState>();
+   double *norms = f->norms.as<double>();
+   const unsigned char *own = f->comm ? comm_owner_mask(f->comm) : nullptr;
+   cudaStream_t s = ctx->stream;
+   const int grid = grid1d(ctx, n);
+
+   PcgState h0;
+   std::memset(&h0, 0, sizeof(h0));
+   h0.rel_tol = rel_tol; h0.abs_tol = abs_tol; h0.max_iter = max_iter; h0.iter = 1;
+   B200PA_CK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
+   B200PA_CK(cudaMemsetAsync(norms, 0, sizeof(double) * ((size_t)max_iter + 2), s));
+
+   // r = b - A x; z = B r; d = z; nom = (d, r)                              (solvers.cpp:875-895)
+   if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
+   k_pcg_init<<<grid, 256, 0, s>>>(n, b_dev, dinv_dev, r, d, own, ctx->d_partials, ctx->d_ticket, st);
+   B200PA_LAUNCHED();
+   if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
+   k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms);
+   B200PA_LAUNCHED();
+   // z = A d; den = (z, d)                                                   (:921-938)
+   if (form_apply(f, d, z, true, &st->dot_b, &st->done)) { return 1; }
+   if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
+   k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
+   B200PA_LAUNCHED();
+
+   // the loop (:952-1027).  Scalars stay on the device; the host only polls `done` every few
+   // iterations (kernels after convergence return immediately on the flag).
+   int *h_done = (int *)(ctx->h_result + 4);
+   *h_done = 0;
+   const int poll = 8;
+   for (int it = 1; it <= std::max(max_iter, 1); ++it)
+   {
+      k_pcg_update<<<grid, 256, 0, s>>>(n, x_dev, r, z, d, dinv_dev, own, ctx->d_partials, ctx->d_ticket, st);
+      B200PA_LAUNCHED();
+      if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
+      k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms);
+      B200PA_LAUNCHED();
+      k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st);
+      B200PA_LAUNCHED();
+      if (form_apply(f, d, z, true, &st->dot_b, &st->done)) { return 1; }
+      if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
+      k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
+      B200PA_LAUNCHED();
+      if (it % poll == 0)
+      {
+         B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+         B200PA_CK(cudaStreamSynchronize(s));
+         if (*h_done) { break; }
+      }
+   }
+   PcgState hs;
+   B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
+   B200PA_CK(cudaStreamSynchronize(s));
+   B200PA_REQUIRE(!hs.nonfinite, "pcg_solve: non-finite (B r, r) or (A d, d) (MFEM_VERIFY(IsFinite(...)), linalg/solvers.cpp:897,932,969,1011)");
+   B200PA_REQUIRE(hs.done, "pcg_solve: internal error (loop ended without a terminal state)");
+   res->final_iter = hs.final_iter;
+   res->converged = hs.converged;
+   res->initial_norm = hs.nom0 >= 0.0 ? sqrt(hs.nom0) : hs.nom0;
+   res->final_norm = (hs.nom0 < 0.0) ? hs.nom0 : sqrt(hs.betanom);
+   if (norms_host)
+   {
+      B200PA_CK(cudaMemcpyAsync(norms_host, norms, sizeof(double) * ((size_t)hs.final_iter + 1), cudaMemcpyDeviceToHost, s));
+      B200PA_CK(cudaStreamSynchronize(s));
+   }
+   return 0;
+}
+
+extern "C" int b200pa_pcg_solve_host(b200pa_form f, const double *dinv_dev, const double *b_host, double *x_host,
+                                     double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res, double *norms_host)
+{
+   B200PA_REQUIRE(f && b_host && x_host, "pcg_solve_host: NULL argument");
+   b200pa_ctx ctx = f->sp->ctx;
+   NEED_CTX(ctx);
+   if (need_work(f)) { return 1; }
+   const size_t b = sizeof(double) * (size_t)f->sp->ndofs;
+   B200PA_CK(cudaMemcpyAsync(f->w1.p, b_host, b, cudaMemcpyHostToDevice, ctx->stream));
+   B200PA_CK(cudaMemcpyAsync(f->w2.p, x_host, b, cudaMemcpyHostToDevice, ctx->stream));
+   if (b200pa_pcg_solve(f, dinv_dev, f->w1.as<double>(), f->w2.as<double>(), rel_tol, abs_tol, max_iter, res, norms_host)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(x_host, f->w2.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+extern "C" int b200pa_form_set_comm(b200pa_form f, b200pa_comm c)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   f->comm = c;
+   return 0;
+}

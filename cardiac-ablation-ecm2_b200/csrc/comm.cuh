@@ -1,0 +1,14 @@
+// Shared-dof exchange + scalar all-reduce between the ranks of a partitioned mesh (one rank
+// per GPU), NCCL over NVLink.  ≙ DeviceConformingProlongationOperator (fem/pfespace.cpp:5259-5532)
+// and InnerProduct(comm,...) (linalg/vector.hpp:773-779).  See comm.cu for the design.
+#pragma once
+#include "common.cuh"
+
+namespace b200pa
+{
+const unsigned char *comm_owner_mask(b200pa_comm c);
+// y[shared dofs] <- sum over all sharing ranks (ascending rank order, identical on every rank)
+int comm_exchange_sum(b200pa_comm c, double *yL_dev, const int *done);
+int comm_exchange_owner(b200pa_comm c, double *xL_dev);
+int comm_allreduce_sum_dev(b200pa_comm c, double *vals_dev, int n);
+} // namespace b200pa

@@ -1,0 +1,77 @@
+// One (D1D,Q1D) instantiation set of the element kernel.  Compiled six times:
+//   nvcc ... -DB200PA_D=3 -DB200PA_Q=4 -c elem_inst.cu -o elem_3_4.o
+#include "elem_launch.cuh"
+#include "pa_element_kernel.cuh"
+
+#ifndef B200PA_D
+#error "compile with -DB200PA_D=<D1D> -DB200PA_Q=<Q1D>"
+#endif
+
+namespace b200pa
+{
+
+namespace
+{
+constexpr int D = B200PA_D, Q = B200PA_Q;
+
+template <bool DIFF, bool MASS, int INMODE, int OUTMODE, int QOP>
+int run(const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   using L = ElemLayout<D, Q>;
+   auto kern = pa_element_kernel<D, Q, DIFF, MASS, INMODE, OUTMODE, QOP>;
+   static int blocks_per_sm = 0; // per instantiation
+   if (blocks_per_sm == 0)
+   {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES);
+      if (e != cudaSuccess) { return (int)e; }
+      int n = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, L::NT, L::SMEM_BYTES);
+      if (e != cudaSuccess) { return (int)e; }
+      blocks_per_sm = n > 0 ? n : 1;
+   }
+   ElemParams<D, Q> P;
+   for (int i = 0; i < Q * D; ++i) { P.bg.B[i] = a.B[i]; P.bg.G[i] = a.G ? a.G[i] : 0.0; }
+   P.NE = a.NE;
+   P.x = a.x; P.gmap = a.gmap; P.y = a.y; P.slot = a.slot;
+   P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.J = a.J;
+   P.f = a.f; P.detJ = a.detJ; P.W = a.W; P.nf = a.nf; P.done = a.done;
+   P.ca = a.ca; P.cb = a.cb; P.cT0 = a.cT0; P.s = a.s;
+   if (a.NE <= 0) { return 0; }
+   const int nbatch = (a.NE + L::NEB - 1) / L::NEB;
+   const int grid = nbatch < num_sms * blocks_per_sm ? nbatch : num_sms * blocks_per_sm;
+   kern<<<grid, L::NT, L::SMEM_BYTES, stream>>>(P);
+   return (int)cudaGetLastError();
+}
+
+template <int INMODE, int OUTMODE>
+int run_apply(const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   if (a.pa_diff && a.pa_mass) { return run<true, true, INMODE, OUTMODE, QOP_APPLY>(a, num_sms, stream); }
+   if (a.pa_diff) { return run<true, false, INMODE, OUTMODE, QOP_APPLY>(a, num_sms, stream); }
+   if (a.pa_mass) { return run<false, true, INMODE, OUTMODE, QOP_APPLY>(a, num_sms, stream); }
+   return (int)cudaErrorInvalidValue;
+}
+} // namespace
+
+#define B200PA_CAT3(a, b, c) a##b##_##c
+#define B200PA_NAME(D_, Q_) B200PA_CAT3(launch_element_, D_, Q_)
+
+int B200PA_NAME(B200PA_D, B200PA_Q)(int variant, const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   switch (variant)
+   {
+      case EV_APPLY_E: return run_apply<IN_E, OUT_E_ADD>(a, num_sms, stream);
+      case EV_APPLY_L2S: return run_apply<IN_GATHER, OUT_SLOT>(a, num_sms, stream);
+      case EV_VALUES_E: return run<false, false, IN_E, OUT_NONE, QOP_VALUES>(a, num_sms, stream);
+      case EV_VALUES_L: return run<false, false, IN_GATHER, OUT_NONE, QOP_VALUES>(a, num_sms, stream);
+      case EV_PHYSGRAD_E: return run<false, false, IN_E, OUT_NONE, QOP_PHYSGRAD>(a, num_sms, stream);
+      case EV_PHYSGRAD_L: return run<false, false, IN_GATHER, OUT_NONE, QOP_PHYSGRAD>(a, num_sms, stream);
+      case EV_LF_E: return run<false, false, IN_NONE, OUT_E_ADD, QOP_LF>(a, num_sms, stream);
+      case EV_LF_S: return run<false, false, IN_NONE, OUT_SLOT, QOP_LF>(a, num_sms, stream);
+      case EV_COEFF_L: return run<false, false, IN_GATHER, OUT_NONE, QOP_COEFF>(a, num_sms, stream);
+      case EV_JOULE_L: return run<false, false, IN_GATHER, OUT_NONE, QOP_JOULE>(a, num_sms, stream);
+      default: return (int)cudaErrorInvalidValue;
+   }
+}
+
+} // namespace b200pa

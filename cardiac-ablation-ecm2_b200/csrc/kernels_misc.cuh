@@ -1,0 +1,470 @@
+// Streaming kernels around the element kernel: restriction, set-up, diagonal, BLAS-1, Jacobi,
+// deterministic reductions.  All FP64, all HBM-bound; thread = one output entry, coalesced index
+// streams, grid-stride loops sized from the SM count.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200pa
+{
+
+// ------------------------------------------------------------------ reductions
+// Deterministic: fixed shuffle tree per block, block partials summed in a fixed order by the
+// last block to finish (ticket counter).  ≙ general/reducers.hpp:451-592 without the host join.
+__device__ __forceinline__ double block_sum(double v)
+{
+   __shared__ double ws[32];
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); }
+   if (lane == 0) { ws[w] = v; }
+   __syncthreads();
+   if (w == 0)
+   {
+      v = lane < nw ? ws[lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); }
+   }
+   return v; // valid in thread 0
+}
+
+__device__ __forceinline__ void grid_sum(double v, double *partials, unsigned int *ticket, double *out)
+{
+   const double bs = block_sum(v);
+   __shared__ bool last;
+   if (threadIdx.x == 0)
+   {
+      partials[blockIdx.x] = bs;
+      __threadfence();
+      const unsigned int t = atomicInc(ticket, gridDim.x - 1); // wraps back to 0: self-resetting
+      last = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (last)
+   {
+      __threadfence();
+      double s = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { s += ((volatile double *)partials)[i]; }
+      s = block_sum(s);
+      if (threadIdx.x == 0) { *out = s; }
+   }
+}
+
+__global__ void k_dot(long long n, const double *__restrict__ a, const double *__restrict__ b,
+                      double *partials, unsigned int *ticket, double *out)
+{
+   double s = 0.0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      s = fma(a[i], b[i], s);
+   }
+   grid_sum(s, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ restriction
+// fem/restriction.cpp:109-129
+__global__ void k_restrict_mult(long long n, const int *__restrict__ gmap, const double *__restrict__ x,
+                                double *__restrict__ y)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const int g = gmap[i];
+      y[i] = g >= 0 ? x[g] : -x[-1 - g];
+   }
+}
+
+// fem/restriction.cpp:152-186, 196-221 — CSR, one thread per L-dof, ascending element order
+__global__ void k_restrict_mult_transpose(int ndofs, const int *__restrict__ offsets, const int *__restrict__ indices,
+                                          const double *__restrict__ xE, double *__restrict__ y, int abs)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ndofs; i += gridDim.x * blockDim.x)
+   {
+      double v = 0.0;
+      const int j1 = offsets[i + 1];
+      for (int j = offsets[i]; j < j1; ++j)
+      {
+         const int s = indices[j];
+         const int k = s >= 0 ? s : -1 - s;
+         const double t = xE[k];
+         v += (abs || s >= 0) ? t : -t;
+      }
+      y[i] = v;
+   }
+}
+
+// The same sum over the SLOT layout written by the element kernel (y_S[j], j = CSR position):
+// a contiguous segmented reduction — no index stream, no scattered reads.  Optional fused
+// ConstrainedOperator fix-up (linalg/operator.cpp:615-640: y[ess] = x[ess]) and d.z partial.
+template <bool CONSTR, bool DOT, bool ABS>
+__global__ void k_segment_sum(int ndofs, const int *__restrict__ offsets, const double *__restrict__ yS,
+                              double *__restrict__ y, const unsigned char *__restrict__ ess_mask,
+                              const double *__restrict__ x, const unsigned char *__restrict__ own_mask,
+                              double *partials, unsigned int *ticket, double *dot_out, const int *done_flag)
+{
+   if (done_flag && *done_flag) { return; }
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ndofs; i += gridDim.x * blockDim.x)
+   {
+      double v = 0.0;
+      const int j1 = offsets[i + 1];
+      for (int j = offsets[i]; j < j1; ++j) { v += ABS ? fabs(yS[j]) : yS[j]; }
+      if (CONSTR && ess_mask[i]) { v = x[i]; }
+      y[i] = v;
+      if (DOT) { if (!own_mask || own_mask[i]) { acc = fma(x[i], v, acc); } }
+   }
+   if (DOT) { grid_sum(acc, partials, ticket, dot_out); }
+}
+
+// multi-GPU second pass after the shared-dof exchange: ConstrainedOperator fix-up and the
+// owned-dof partial of d.z
+__global__ void k_fixup_dot(int ndofs, double *__restrict__ y, const unsigned char *__restrict__ ess_mask,
+                            const double *__restrict__ x, const unsigned char *__restrict__ own_mask, int want_dot,
+                            double *partials, unsigned int *ticket, double *dot_out, const int *done_flag)
+{
+   if (done_flag && *done_flag) { return; }
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ndofs; i += gridDim.x * blockDim.x)
+   {
+      double v = y[i];
+      if (ess_mask && ess_mask[i]) { v = x[i]; y[i] = v; }
+      if (want_dot && (!own_mask || own_mask[i])) { acc = fma(x[i], v, acc); }
+   }
+   if (want_dot) { grid_sum(acc, partials, ticket, dot_out); }
+}
+
+// ----------------------------------------------------------------------- set-up
+// fem/integ/bilininteg_diffusion_kernels.cpp:243-367, scalar branch :349-362
+__global__ void k_diffusion_setup(long long NQ, long long NE, const double *__restrict__ W,
+                                  const double *__restrict__ J, const double *__restrict__ C, int const_c,
+                                  double *__restrict__ D)
+{
+   const long long n = NQ * NE;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const long long e = i / NQ, q = i - e * NQ;
+      const double *Je = J + e * 9 * NQ + q;
+      const double J11 = Je[0 * NQ], J21 = Je[1 * NQ], J31 = Je[2 * NQ];
+      const double J12 = Je[3 * NQ], J22 = Je[4 * NQ], J32 = Je[5 * NQ];
+      const double J13 = Je[6 * NQ], J23 = Je[7 * NQ], J33 = Je[8 * NQ];
+      const double detJ = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13);
+      const double c = const_c ? C[0] : C[i];
+      const double w = c * (W[q] / detJ);
+      const double A11 = (J22 * J33) - (J23 * J32), A12 = (J32 * J13) - (J12 * J33), A13 = (J12 * J23) - (J22 * J13);
+      const double A21 = (J31 * J23) - (J21 * J33), A22 = (J11 * J33) - (J13 * J31), A23 = (J21 * J13) - (J11 * J23);
+      const double A31 = (J21 * J32) - (J31 * J22), A32 = (J31 * J12) - (J11 * J32), A33 = (J11 * J22) - (J12 * J21);
+      double *De = D + e * 6 * NQ + q;
+      De[0 * NQ] = w * (A11 * A11 + A12 * A12 + A13 * A13);
+      De[1 * NQ] = w * (A11 * A21 + A12 * A22 + A13 * A23);
+      De[2 * NQ] = w * (A11 * A31 + A12 * A32 + A13 * A33);
+      De[3 * NQ] = w * (A21 * A21 + A22 * A22 + A23 * A23);
+      De[4 * NQ] = w * (A21 * A31 + A22 * A32 + A23 * A33);
+      De[5 * NQ] = w * (A31 * A31 + A32 * A32 + A33 * A33);
+   }
+}
+
+// fem/integ/bilininteg_mass_pa.cpp:62-78
+__global__ void k_mass_setup(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ detJ,
+                             const double *__restrict__ C, int const_c, double *__restrict__ v)
+{
+   const long long n = NQ * NE;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const long long q = i % NQ;
+      v[i] = W[q] * (const_c ? C[0] : C[i]) * detJ[i];
+   }
+}
+
+// mesh/mesh.cpp:15220-15273 for trilinear hexes: J(q) = sum_v X_v (x) grad N_v(xi_q); vertex
+// order of the reference hexahedron (mesh/mesh.cpp:3757-3765).  One thread per q-point.
+__global__ void k_geometry_trilinear(int Q1D, long long NE, const double *__restrict__ xi,
+                                     const double *__restrict__ vtx, const int *__restrict__ ev,
+                                     double *__restrict__ J, double *__restrict__ detJ)
+{
+   const long long NQ = (long long)Q1D * Q1D * Q1D, n = NQ * NE;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const long long e = i / NQ, q = i - e * NQ;
+      const int qx = q % Q1D, qy = (q / Q1D) % Q1D, qz = q / (Q1D * Q1D);
+      const double x = xi[qx], y = xi[qy], z = xi[qz];
+      const double bx[2] = {1.0 - x, x}, by[2] = {1.0 - y, y}, bz[2] = {1.0 - z, z};
+      const double gm[2] = {-1.0, 1.0};
+      // local vertex v -> (i,j,k) corner bits
+      const int ci[8] = {0, 1, 1, 0, 0, 1, 1, 0}, cj[8] = {0, 0, 1, 1, 0, 0, 1, 1}, ck[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+      double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // Jm[row + 3*col]
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+      {
+         const double *X = vtx + 3LL * ev[8 * e + v];
+         const double d0 = gm[ci[v]] * by[cj[v]] * bz[ck[v]];
+         const double d1 = bx[ci[v]] * gm[cj[v]] * bz[ck[v]];
+         const double d2 = bx[ci[v]] * by[cj[v]] * gm[ck[v]];
+#pragma unroll
+         for (int r = 0; r < 3; ++r)
+         {
+            Jm[r + 0] = fma(X[r], d0, Jm[r + 0]);
+            Jm[r + 3] = fma(X[r], d1, Jm[r + 3]);
+            Jm[r + 6] = fma(X[r], d2, Jm[r + 6]);
+         }
+      }
+      double *Je = J + e * 9 * NQ + q;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { Je[k * NQ] = Jm[k]; }
+      detJ[i] = Jm[0] * (Jm[4] * Jm[8] - Jm[5] * Jm[7]) - Jm[1] * (Jm[3] * Jm[8] - Jm[5] * Jm[6]) +
+                Jm[2] * (Jm[3] * Jm[7] - Jm[4] * Jm[6]);
+   }
+}
+
+// the "user forall over Q-points" of SURVEY §3.2/§3.3
+__global__ void k_coeff_eval(int kind, long long n, double a, double b, double T0, const double *__restrict__ T,
+                             const double *__restrict__ s, const double *__restrict__ g, double *__restrict__ out)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      if (kind == 0) { out[i] = a * (1.0 + b * (T[i] - T0)); }
+      else if (kind == 1) { out[i] = a; }
+      else
+      {
+         const double gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
+         out[i] = s[i] * (gx * gx + gy * gy + gz * gz) + a;
+      }
+   }
+}
+
+// --------------------------------------------------------------------- diagonal
+// fem/integ/bilininteg_diffusion_kernels.hpp:369-484 and bilininteg_mass_kernels.hpp:324-408:
+// dE[e,l] += sum_q grad(phi_l)^T D grad(phi_l) + v phi_l^2.  One thread per E-entry; B,G in smem.
+template <int D1, int Q1>
+__global__ void k_diag(long long NE, const double *__restrict__ Bg, const double *__restrict__ Gg,
+                       const double *__restrict__ pa_diff, const double *__restrict__ pa_mass,
+                       double *__restrict__ dE)
+{
+   __shared__ double sB[Q1 * D1], sG[Q1 * D1];
+   for (int i = threadIdx.x; i < Q1 * D1; i += blockDim.x) { sB[i] = Bg[i]; sG[i] = Gg[i]; }
+   __syncthreads();
+   constexpr int D3 = D1 * D1 * D1, Q3 = Q1 * Q1 * Q1;
+   const long long n = NE * D3;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const long long e = i / D3;
+      const int l = (int)(i - e * D3), dx = l % D1, dy = (l / D1) % D1, dz = l / (D1 * D1);
+      double acc = 0.0;
+      for (int qz = 0; qz < Q1; ++qz)
+      {
+         const double bz = sB[qz + Q1 * dz], gz = sG[qz + Q1 * dz];
+         for (int qy = 0; qy < Q1; ++qy)
+         {
+            const double by = sB[qy + Q1 * dy], gy = sG[qy + Q1 * dy];
+#pragma unroll
+            for (int qx = 0; qx < Q1; ++qx)
+            {
+               const double bx = sB[qx + Q1 * dx], gx = sG[qx + Q1 * dx];
+               const long long q = qx + Q1 * (qy + Q1 * qz);
+               if (pa_diff)
+               {
+                  const double *d = pa_diff + e * 6 * Q3 + q;
+                  const double X = gx * by * bz, Y = bx * gy * bz, Z = bx * by * gz;
+                  acc += X * (d[0] * X + d[Q3] * Y + d[2 * Q3] * Z) + Y * (d[Q3] * X + d[3 * Q3] * Y + d[4 * Q3] * Z) +
+                         Z * (d[2 * Q3] * X + d[4 * Q3] * Y + d[5 * Q3] * Z);
+               }
+               if (pa_mass)
+               {
+                  const double v = bx * by * bz;
+                  acc = fma(pa_mass[e * Q3 + q], v * v, acc);
+               }
+            }
+         }
+      }
+      dE[i] += acc;
+   }
+}
+
+// ------------------------------------------------------------------ BLAS-1 etc.
+__global__ void k_add(long long n, const double *__restrict__ v1, double alpha, const double *__restrict__ v2,
+                      double *__restrict__ v)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      v[i] = fma(alpha, v2[i], v1[i]);
+   }
+}
+
+// linalg/solvers.cpp:401-425
+__global__ void k_jacobi_setup(int n, const double *__restrict__ diag, double damping, double *__restrict__ dinv,
+                               int *zero_flag)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      const double d = diag[i];
+      if (d == 0.0) { *zero_flag = 1; }
+      dinv[i] = damping / d;
+   }
+}
+__global__ void k_set_indexed(int n, const int *__restrict__ idx, double val, double *__restrict__ v)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { v[idx[i]] = val; }
+}
+__global__ void k_copy_indexed(int n, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { dst[idx[i]] = src[idx[i]]; }
+}
+__global__ void k_mask_indexed(int n, const int *__restrict__ idx, unsigned char *__restrict__ mask)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { mask[idx[i]] = 1; }
+}
+// linalg/solvers.cpp:442-452
+__global__ void k_jacobi_mult(int n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ z)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { z[i] = dinv[i] * r[i]; }
+}
+__global__ void k_sub_inplace(int n, double *__restrict__ b, const double *__restrict__ z)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { b[i] -= z[i]; }
+}
+
+// ------------------------------------------------------------- CSR construction
+__global__ void k_iota(long long n, int *v)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { v[i] = (int)i; }
+}
+// offsets[i] = first position j with sorted_keys[j] >= i  (i in [0,ndofs])
+__global__ void k_offsets_from_sorted(int ndofs, long long n, const int *__restrict__ keys, int *__restrict__ offsets)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= ndofs; i += gridDim.x * blockDim.x)
+   {
+      long long lo = 0, hi = n;
+      while (lo < hi)
+      {
+         const long long mid = (lo + hi) >> 1;
+         if (keys[mid] < i) { lo = mid + 1; } else { hi = mid; }
+      }
+      offsets[i] = (int)lo;
+   }
+}
+__global__ void k_invert_perm(long long n, const int *__restrict__ indices, int *__restrict__ slot)
+{
+   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) { slot[indices[j]] = (int)j; }
+}
+__global__ void k_check_nonneg(long long n, const int *__restrict__ v, int ndofs, int *flag)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      if (v[i] < 0 || v[i] >= ndofs) { *flag = 1; }
+   }
+}
+// constrained gather map: entries that point at an essential dof become -1 ("read zero"),
+// folding z = x; z[ess] = 0 (linalg/operator.cpp:603-609) into the gather
+__global__ void k_constrain_gmap(long long n, const int *__restrict__ gmap, const unsigned char *__restrict__ ess_mask,
+                                 int *__restrict__ out)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const int g = gmap[i];
+      out[i] = ess_mask[g] ? -1 : g;
+   }
+}
+
+// -------------------------------------------------------------------------- PCG
+// Device-resident scalar state of CGSolver::Mult (linalg/solvers.cpp:869-1050).
+struct PcgState
+{
+   double nom, nom0, den, betanom, r0, alpha, beta;
+   double dot_a, dot_b;       // raw reduction results (before the scalar step / all-reduce)
+   double rel_tol, abs_tol;
+   int iter;                  // the reference's loop variable i
+   int max_iter;
+   int done, converged, final_iter, nonfinite;
+};
+
+// r = b - Ax (Ax passed in r), z = dinv r, d = z, nom partial = d.r    (:875-892)
+__global__ void k_pcg_init(int n, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ r,
+                           double *__restrict__ d, const unsigned char *__restrict__ own_mask, double *partials,
+                           unsigned int *ticket, PcgState *st)
+{
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      const double ri = b[i] - r[i];
+      const double zi = dinv[i] * ri;
+      r[i] = ri;
+      d[i] = zi;
+      if (!own_mask || own_mask[i]) { acc = fma(zi, ri, acc); }
+   }
+   grid_sum(acc, partials, ticket, &st->dot_a);
+}
+
+// scalar step after nom0 = Dot(d, r)   (:892-919)
+__global__ void k_pcg_scalar_init(PcgState *st, double *norms)
+{
+   const double nom = st->dot_a;
+   st->nom = st->nom0 = nom;
+   norms[0] = nom;
+   st->iter = 1;
+   if (!isfinite(nom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
+   if (nom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
+   st->r0 = fmax(nom * st->rel_tol * st->rel_tol, st->abs_tol * st->abs_tol);
+   st->betanom = nom;
+   if (nom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = 0; }
+}
+
+// scalar step after den = Dot(d, z)   (:921-938 first time, :1010-1024 in the loop)
+__global__ void k_pcg_scalar_den(PcgState *st)
+{
+   if (st->done) { return; }
+   const double den = st->dot_b;
+   st->den = den;
+   if (!isfinite(den)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = st->iter - 1; return; }
+   if (den == 0.0)
+   {
+      // before the loop: final_iter = 0; inside: final_iter = i (already incremented)
+      st->done = 1; st->converged = 0; st->final_iter = (st->iter == 1) ? 0 : st->iter;
+      return;
+   }
+   st->alpha = st->nom / den;
+}
+
+// x += alpha d; r -= alpha z; z = dinv r; betanom partial = r.z   (:956-963)
+__global__ void k_pcg_update(int n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+                             const double *__restrict__ d, const double *__restrict__ dinv,
+                             const unsigned char *__restrict__ own_mask, double *partials, unsigned int *ticket,
+                             PcgState *st)
+{
+   if (st->done) { return; }
+   const double alpha = st->alpha;
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      x[i] = fma(alpha, d[i], x[i]);
+      const double ri = fma(-alpha, z[i], r[i]);
+      const double zi = dinv[i] * ri;
+      r[i] = ri;
+      z[i] = zi;
+      if (!own_mask || own_mask[i]) { acc = fma(ri, zi, acc); }
+   }
+   grid_sum(acc, partials, ticket, &st->dot_a);
+}
+
+// scalar step after betanom = Dot(r, z)   (:964-1002)
+__global__ void k_pcg_scalar_beta(PcgState *st, double *norms)
+{
+   if (st->done) { return; }
+   const double betanom = st->dot_a;
+   const int i = st->iter;
+   st->betanom = betanom;
+   norms[i] = betanom;
+   if (!isfinite(betanom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = i; return; }
+   if (betanom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = i; return; }
+   if (betanom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = i; return; }
+   if (i + 1 > st->max_iter) { st->done = 1; st->converged = 0; st->final_iter = st->max_iter; return; }
+   st->iter = i + 1;
+   st->beta = betanom / st->nom;
+   st->nom = betanom; // (:1026; alpha of the next pass uses it)
+}
+
+// d = z + beta d   (:1003)
+__global__ void k_pcg_direction(int n, const double *__restrict__ z, double *__restrict__ d, const PcgState *st)
+{
+   if (st->done) { return; }
+   const double beta = st->beta;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { d[i] = fma(beta, d[i], z[i]); }
+}
+
+} // namespace b200pa

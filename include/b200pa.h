@@ -1,0 +1,271 @@
+/*
+ * b200pa.h — C ABI of libb200pa.so: the B200 (sm_100a, FP64) partial-assembly hot path behind
+ * the Pennes-bioheat / electrostatic solves of an MFEM-based cardiac-ablation solver.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree, stock MFEM 4.9.1-dev).
+ * Plain pointers and sizes only; no C++ or torch types.  The reference-side bindings a
+ * maintainer adds (C++ subclasses of mfem::DiffusionIntegrator / MassIntegrator / Operator /
+ * Solver forwarding to these functions) are shown in INTEGRATION.md and implemented against a
+ * mirror of the MFEM interface in cardiac-ablation-ecm2_b200/host/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on error; b200pa_last_error() returns the
+ *     message for the calling thread (≙ MFEM_VERIFY/MFEM_ABORT, general/error.hpp:26-64).
+ *     There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *   - layouts are the reference's: L-vector f64[ndofs]; E-vector f64[D,D,D,NE],
+ *     x fastest (fem/restriction.cpp:116); q-data f64[Q,Q,Q,ncomp,NE]
+ *     (fem/integ/bilininteg_diffusion_kernels.hpp:1009); B,G column-major [Q,D]
+ *     (fem/fe/fe_base.cpp:2654-2655); J f64[Q,Q,Q,3,3,NE] with J(q,row,col,e)
+ *     (fem/integ/bilininteg_diffusion_kernels.cpp:254); indices int32.
+ *   - "dev" pointers are device pointers on the context's GPU; "any" pointers may be host or
+ *     device (detected with cudaPointerGetAttributes) and are copied if they are host memory.
+ *   - kernels are enqueued on the context's stream and are asynchronous unless stated.
+ *   - supported: 3-D hexahedra, H1 scalar (vdim 1) spaces, orders 1..6 with the reference's
+ *     default rules (D1D = p+1, Q1D = p+2) — (D1D,Q1D) in {(2,3),(3,4),(4,5),(5,6),(6,7),(7,8)};
+ *     anything else is rejected (the reference would fall back to an unspecialised kernel,
+ *     fem/kernel_dispatch.hpp:138-153).
+ */
+#ifndef B200PA_H
+#define B200PA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PA_VERSION 100
+
+typedef struct b200pa_ctx_s *b200pa_ctx;      /* one per GPU / host thread (≙ mfem::Device)      */
+typedef struct b200pa_space_s *b200pa_space;  /* ElementRestriction + DofToQuad + GeometricFactors */
+typedef struct b200pa_form_s *b200pa_form;    /* PABilinearFormExtension (+ ConstrainedOperator)  */
+typedef struct b200pa_comm_s *b200pa_comm;    /* shared-dof halo exchange + allreduce (NCCL)      */
+
+int b200pa_version(void);
+const char *b200pa_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long b200pa_launch_count(void);
+
+/* ------------------------------------------------------------------ context */
+/* stream: a cudaStream_t to enqueue on, or NULL to create an owned stream. */
+int b200pa_ctx_create(int device, void *stream, b200pa_ctx *out);
+int b200pa_ctx_destroy(b200pa_ctx ctx);
+int b200pa_ctx_sync(b200pa_ctx ctx);                       /* ≙ MFEM_STREAM_SYNC */
+void *b200pa_ctx_stream(b200pa_ctx ctx);
+/* synchronous copies on the context's stream (≙ Vector::HostRead / Vector::Write of a device vector) */
+int b200pa_ctx_upload(b200pa_ctx ctx, void *dst_dev, const void *src_host, size_t bytes);
+int b200pa_ctx_download(b200pa_ctx ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* ------------------------------------------------- level 1: kernel-level API */
+/* ElementRestriction::Mult, fem/restriction.cpp:109-129.  y[i] = ±x[gather_map[i]] */
+int b200pa_restrict_mult(b200pa_ctx ctx, int ne, int nd, const int *gather_map_dev,
+                         const double *x_dev, double *y_dev);
+/* ElementRestriction::MultTranspose / AbsMultTranspose, fem/restriction.cpp:152-186, 196-221.
+ * Atomic-free: one thread per L-dof, CSR (offsets, indices), ascending element order. */
+int b200pa_restrict_mult_transpose(b200pa_ctx ctx, int ndofs, const int *offsets_dev,
+                                   const int *indices_dev, const double *xE_dev, double *yL_dev,
+                                   int abs);
+/* internal::PADiffusionSetup3D, fem/integ/bilininteg_diffusion_kernels.cpp:243-367 (scalar
+ * coefficient branch :349-362).  nc = 1 (constant) or Q^3*NE.  D is [Q,Q,Q,6,NE]. */
+int b200pa_diffusion_setup(b200pa_ctx ctx, int q1d, int ne, const double *W_dev, const double *J_dev,
+                           const double *C_dev, long long nc, double *D_dev);
+/* MassIntegrator::AssemblePA inner kernel, fem/integ/bilininteg_mass_pa.cpp:62-78 */
+int b200pa_mass_setup(b200pa_ctx ctx, int nq, int ne, const double *W_dev, const double *detJ_dev,
+                      const double *C_dev, long long nc, double *v_dev);
+/* DiffusionIntegrator::ApplyKernelType (fem/bilininteg.hpp:2181-2185) →
+ * SmemPADiffusionApply3D, fem/integ/bilininteg_diffusion_kernels.hpp:989-1214:  yE += G^T D G xE */
+int b200pa_diffusion_apply(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                           const double *G_any, const double *D_dev, const double *xE_dev, double *yE_dev);
+/* MassIntegrator::ApplyKernelType (fem/bilininteg.hpp:2387-2389) → SmemPAMassApply3D,
+ * fem/integ/bilininteg_mass_kernels.hpp:1119-1144:  yE += B^T v B xE */
+int b200pa_mass_apply(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                      const double *v_dev, const double *xE_dev, double *yE_dev);
+/* DiagonalKernelType: SmemPADiffusionDiagonal3D (…diffusion_kernels.hpp:369-484) and
+ * SmemPAMassAssembleDiagonal3D (…mass_kernels.hpp:324-408):  dE += diag(element matrix) */
+int b200pa_diffusion_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                          const double *G_any, const double *D_dev, double *dE_dev);
+int b200pa_mass_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                     const double *v_dev, double *dE_dev);
+/* quadrature_interpolator::Values3D, fem/qinterp/eval.hpp:131-193 (vdim 1): yq[Q,Q,Q,NE] */
+int b200pa_qvalues(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                   const double *xE_dev, double *yq_dev);
+/* quadrature_interpolator::Derivatives3D<byVDIM,GRAD_PHYS>, fem/qinterp/grad.hpp:233-374:
+ * gq[3,Q,Q,Q,NE] = J^{-T} grad_ref */
+int b200pa_qphysgrad(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                     const double *G_any, const double *J_dev, const double *xE_dev, double *gq_dev);
+/* DLFEvalAssemble3D, fem/integ/lininteg_domain_kernels.hpp:164-298: bE += B^T (W f detJ);
+ * nf = 1 (constant) or Q^3*NE */
+int b200pa_domain_lf(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B_any,
+                     const double *detJ_dev, const double *W_dev, const double *f_dev, long long nf,
+                     double *bE_dev);
+/* Vector::operator*, linalg/vector.cpp:1079-1152 (+ general/reducers.hpp:532-592).
+ * Deterministic block-tree reduction; synchronous (returns the value on the host). */
+int b200pa_dot(b200pa_ctx ctx, long long n, const double *a_dev, const double *b_dev, double *result_host);
+/* add(v1, alpha, v2, v), linalg/vector.cpp:436-473:  v = v1 + alpha v2 */
+int b200pa_add(b200pa_ctx ctx, long long n, const double *v1_dev, double alpha, const double *v2_dev,
+               double *v_dev);
+/* OperatorJacobiSmoother::Setup / ::Mult, linalg/solvers.cpp:401-425, 427-453 */
+int b200pa_jacobi_setup(b200pa_ctx ctx, int n, const double *diag_dev, int n_ess, const int *ess_dev,
+                        double damping, double *dinv_dev);
+int b200pa_jacobi_mult(b200pa_ctx ctx, int n, const double *dinv_dev, const double *r_dev, double *z_dev);
+/* q-point coefficient evaluation (the "user forall over Q-points" of SURVEY §3.2/§3.3):
+ *   kind 0: out = a*(1 + b*(T - T0))                   k(T), sigma(T)
+ *   kind 1: out = a                                      constant fill (rho c/dt + perfusion)
+ *   kind 2: out = s*|g|^2 + a   (g = grad phi [3,..])   Joule source + perfusion source
+ *           (semantics of miniapps/electromagnetics/joule_solver.cpp:898-906) */
+int b200pa_coeff_eval(b200pa_ctx ctx, int kind, long long n, double a, double b, double T0,
+                      const double *T_dev, const double *s_dev, const double *g_dev, double *out_dev);
+
+/* -------------------------------------------- level 2: space / form / solver */
+/* ElementRestriction ctor (fem/restriction.cpp:26-107) + DofToQuad (fem/fe/fe_base.cpp:2619-2662).
+ * Copies gather_map (sign-encoded entries are rejected: H1 has none), builds the CSR
+ * (offsets, indices) in ascending element order and its inverse (slot of every E-entry). */
+int b200pa_space_create(b200pa_ctx ctx, int d1d, int q1d, int ne, int ndofs, const int *gather_map_any,
+                        const double *B_any, const double *G_any, b200pa_space *out);
+int b200pa_space_destroy(b200pa_space sp);
+/* GeometricFactors (mesh/mesh.hpp:3086-3130): J[Q^3,3,3,NE], detJ[Q^3,NE], rule weights W[Q^3].
+ * J/detJ are referenced if they are device pointers (caller keeps them alive), copied otherwise. */
+int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, const double *J_any,
+                              const double *detJ_any);
+/* GeometricFactors::Compute (mesh/mesh.cpp:15220-15273) for trilinear hexes, on the device:
+ * vertices f64[3*nv], elem_vertices int32[8*NE] in the reference's hex vertex order. */
+int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv,
+                                        const double *vertices_any, const int *elem_vertices_any);
+/* read-only accessors to the device arrays (for tests and for the host mirror) */
+const int *b200pa_space_offsets(b200pa_space sp);
+const int *b200pa_space_indices(b200pa_space sp);
+const int *b200pa_space_gather_map(b200pa_space sp);
+const double *b200pa_space_J(b200pa_space sp);
+const double *b200pa_space_detJ(b200pa_space sp);
+const double *b200pa_space_W(b200pa_space sp);
+
+/* q-point operators straight from an L-vector (the L->E gather is fused in, nothing E-sized or
+ * q-sized is staged in HBM beyond the output):
+ *   qvalues    ≙ QuadratureFunction::ProjectGridFunction (fem/qfunction.cpp:73-105)
+ *   qphysgrad  ≙ ElementRestriction::Mult + QuadratureInterpolator::PhysDerivatives
+ *                (fem/quadinterpolator.cpp:682-687), layout [3,Q,Q,Q,NE]
+ *   coeff_linear: out_q = a (1 + b (T_q - T0))              k(T), sigma(T) of SURVEY §3.2/§3.3
+ *   joule:        out_q = sigma_q |grad phi|_q^2 + add      (miniapps/electromagnetics/joule_solver.cpp:898-906)
+ *   domain_lf  ≙ LinearForm(DomainLFIntegrator(f_q)) with UseFastAssembly (fem/linearform.cpp:162-184,
+ *                fem/integ/lininteg_domain.cpp:22-59): b_L = R^T B^T (W f detJ); nf = 1 or Q^3*NE */
+int b200pa_space_qvalues(b200pa_space sp, const double *xL_dev, double *yq_dev);
+int b200pa_space_qphysgrad(b200pa_space sp, const double *xL_dev, double *gq_dev);
+int b200pa_space_coeff_linear(b200pa_space sp, double a, double b, double T0, const double *TL_dev, double *out_q_dev);
+int b200pa_space_joule(b200pa_space sp, const double *phiL_dev, const double *sigma_q_dev, double add, double *out_q_dev);
+int b200pa_space_domain_lf(b200pa_space sp, const double *f_dev, long long nf, double *bL_dev);
+
+/* PABilinearFormExtension (fem/bilinearform_ext.cpp:246-847): diffusion and/or mass on `sp`. */
+int b200pa_form_create(b200pa_space sp, b200pa_form *out);
+int b200pa_form_destroy(b200pa_form f);
+/* DiffusionIntegrator::AssemblePA (fem/integ/bilininteg_diffusion_pa.cpp:89-142) with a constant
+ * (nc = 1) or q-data (nc = Q^3*NE; ≙ QuadratureFunctionCoefficient, fem/coefficient.cpp:2059-2062)
+ * scalar coefficient.  C may be NULL to drop the integrator. */
+int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any, long long nc);
+/* MassIntegrator::AssemblePA (fem/integ/bilininteg_mass_pa.cpp:24-79) */
+int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, long long nc);
+/* use caller-provided pa_data (device) instead of assembling; NULL drops the integrator */
+int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev, const double *pa_mass_dev);
+const double *b200pa_form_pa_diff(b200pa_form f);
+const double *b200pa_form_pa_mass(b200pa_form f);
+/* ConstrainedOperator ctor (linalg/operator.cpp:511-526): essential true-dof list, DIAG_ONE */
+int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any);
+/* PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487-564): y = A x, L→L, unconstrained.
+ * One fused gather + sum-factorised contraction launch and one segmented E→L reduction. */
+int b200pa_form_mult(b200pa_form f, const double *x_dev, double *y_dev);
+/* ConstrainedOperator::Mult (linalg/operator.cpp:586-646, 710-714) */
+int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_dev);
+/* the same two with HOST vectors: copies x up, applies, copies y back, synchronises */
+int b200pa_form_mult_host(b200pa_form f, int constrained, const double *x_host, double *y_host);
+/* PABilinearFormExtension::AssembleDiagonal (fem/bilinearform_ext.cpp:370-454) */
+int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev);
+/* ConstrainedOperator::EliminateRHS (linalg/operator.cpp:559-584): b -= A w; b[ess] = x[ess] */
+int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, double *b_dev);
+
+/* CGSolver::Mult with OperatorJacobiSmoother (linalg/solvers.cpp:869-1050, 331-453), operator =
+ * ConstrainedOperator(f), iterative_mode = true.  Stopping test, iteration numbering,
+ * `converged`, `final_norm = sqrt((Br,r))` as the reference.  norms_host (may be NULL) receives
+ * (B r, r) for iterations 0..final_iter (size max_iter+1).  Synchronous.
+ * b, x: device pointers (b200pa_pcg_solve) or host pointers (b200pa_pcg_solve_host: copies
+ * b and x0 up, x back). */
+typedef struct
+{
+   int final_iter;
+   int converged;
+   double final_norm;
+   double initial_norm;
+} b200pa_pcg_result;
+int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const double *b_dev, double *x_dev,
+                     double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
+                     double *norms_host);
+int b200pa_pcg_solve_host(b200pa_form f, const double *dinv_dev, const double *b_host, double *x_host,
+                          double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
+                          double *norms_host);
+
+/* ------------------------------------------------------ multi-GPU (one rank per GPU) */
+/* Shared-dof exchange ≙ DeviceConformingProlongationOperator::{Mult,MultTranspose}
+ * (fem/pfespace.cpp:5259-5532; GroupCommunicator, general/communication.cpp:723-1120) and
+ * InnerProduct(comm,…) (linalg/vector.hpp:773-779), over NCCL instead of MPI.
+ * Vectors handed to a form with a comm attached are *consistent L-vectors*: every copy of a
+ * shared dof holds the same value; the owner (lowest sharing rank, owner_mask = 1) is the copy
+ * that dots count.  P^T followed by P collapses into one symmetric neighbour exchange whose
+ * per-dof summation order is ascending rank on every rank (bit-identical copies).
+ * nccl_id: the 128-byte ncclUniqueId created on rank 0 (b200pa_comm_unique_id) and broadcast
+ * by the host application (torch.distributed / MPI). */
+int b200pa_comm_unique_id(unsigned char id_out[128]);
+int b200pa_comm_create(b200pa_ctx ctx, const unsigned char nccl_id[128], int rank, int nranks, b200pa_comm *out);
+int b200pa_comm_destroy(b200pa_comm c);
+/* Neighbour tables (≙ GroupCommunicator::GetNeighborLDofTable, general/communication.hpp:294-298):
+ * nbr_rank strictly ascending; shared_ldofs[shared_offsets[k] .. shared_offsets[k+1]) = local
+ * L-dofs shared with neighbour k, in an order both sides agree on (ascending global dof id). */
+int b200pa_comm_set_tables(b200pa_comm c, int ndofs, int n_nbr, const int *nbr_rank,
+                           const int *shared_offsets, const int *shared_ldofs);
+/* the host-side table construction behind set_tables (no GPU needed; used by the CPU tests).
+ * sh_ldof[n_shared], sh_off[n_shared+1], sh_src[n_send+n_shared] (-1 = own value, else index
+ * into the concatenated receive buffer; ascending rank order), owner_mask[ndofs].  Pass NULL
+ * tables to query n_shared only. */
+int b200pa_comm_build_tables(int rank, int ndofs, int n_nbr, const int *nbr_rank, const int *shared_offsets,
+                             const int *shared_ldofs, int *n_shared_out, int *sh_ldof, int *sh_off, int *sh_src,
+                             unsigned char *owner_mask);
+const unsigned char *b200pa_comm_owner_mask(b200pa_comm c);   /* device pointer */
+int b200pa_form_set_comm(b200pa_form f, b200pa_comm c);
+/* (P P^T) y: every copy of a shared dof <- sum of all copies.  (P R) x: <- the owner's value. */
+int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev);
+int b200pa_comm_bcast(b200pa_comm c, double *xL_dev);
+int b200pa_comm_allreduce_sum(b200pa_comm c, double *vals_dev, int n);
+
+/* -------------------------------------------------- host-side problem builder (no GPU) */
+/* Mesh::MakeCartesian3D (mesh/mesh.cpp:3683-3790, 4627-4635; space-filling-curve element order,
+ * mesh/ncmesh.cpp:5435-5620) + H1 dof numbering (fem/fespace.cpp:3426-3533) + lexicographic
+ * E-ordering (fem/restriction.cpp:44-62) for an nx*ny*nz hex mesh, order p — reproduces the
+ * reference's gather_map exactly (tests/test_hexmesh.py).  All outputs are caller-allocated host
+ * arrays; pass NULL to skip one.
+ *   gather_map   int32[ne*(p+1)^3]        elem_vertices int32[8*ne]
+ *   vertices     f64[3*nv]  ((x,y,z) per vertex, sx,sy,sz box; `skew` != 0 applies
+ *                y += 0.2x, z += 0.3x as tests/unit/fem/test_pa_coeff.cpp:33-39)
+ *   elem_ijk     int32[3*ne] lattice position of every element (SFC order)
+ *   bdr_attr_of_dof  uint8[ndofs]: bit a-1 set if the dof lies on boundary attribute a (1..6)
+ */
+int b200pa_hex_sizes(int nx, int ny, int nz, int p, long long *ne, long long *nv, long long *ndofs);
+int b200pa_hex_build(int nx, int ny, int nz, int p, double sx, double sy, double sz, int skew,
+                     int *gather_map, int *elem_vertices, double *vertices, int *elem_ijk,
+                     unsigned char *bdr_attr_of_dof);
+/* the same for the [ox,ox+nx) x [oy,oy+ny) x [oz,oz+nz) sub-box of a GNX x GNY x GNZ global mesh
+ * (≙ Mesh::CartesianPartitioning + ParMesh, mesh/mesh.cpp:8966-9003, mesh/pmesh.cpp:106): local
+ * numbering as if the sub-box were a mesh of its own, vertex coordinates / boundary attributes /
+ * lattice coordinates (int32[3*ndofs], units of h/p) those of the global mesh */
+int b200pa_hex_build_part(int GNX, int GNY, int GNZ, int ox, int oy, int oz, int nx, int ny, int nz, int p,
+                          double sx, double sy, double sz, int skew, int *gather_map, int *elem_vertices,
+                          double *vertices, int *elem_ijk, unsigned char *bdr_attr_of_dof, int *lattice);
+/* lattice coordinates (ix,iy,iz in [0,p*n]) of every L-dof: int32[3*ndofs] */
+int b200pa_hex_dof_lattice(int nx, int ny, int nz, int p, int *lattice);
+/* DofToQuad in TENSOR mode for H1 (GLL nodes) at the Gauss-Legendre rule with q1d points
+ * (fem/fe/fe_base.cpp:2619-2662, fem/intrules.cpp): B,G f64[q1d*d1d] column-major, w1d f64[q1d],
+ * W f64[q1d^3] */
+int b200pa_basis(int p, int q1d, double *B, double *G, double *w1d, double *W, double *gll_nodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PA_H */

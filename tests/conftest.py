@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "cardiac-ablation-ecm2_b200"))
 
 GOLDEN = os.path.join(HERE, "golden")
 
@@ -31,3 +32,12 @@ def load_case(tag):
 @pytest.fixture(params=golden_cases())
 def case(request):
     return load_case(request.param)
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One b200pa context on cuda:0 for the whole GPU session (fails loudly without a GPU)."""
+    import b200pa
+    c = b200pa.Context(0)
+    yield c
+    c.close()

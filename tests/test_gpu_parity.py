@@ -1,0 +1,265 @@
+"""GPU parity (run on the B200 box: pytest -m gpu): every entry point of the C ABI against
+ (a) the golden fixtures = outputs of the unmodified reference, and
+ (b) the CPU oracle (oracle/pa_oracle.c) on the same inputs.
+Tolerances are the north star's: 1e-12 relative per operator apply, 1e-10 on the solution
+after a fixed number of PCG iterations, iteration counts to a tolerance within +-1."""
+import numpy as np
+import pytest
+
+import b200pa
+import orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_APPLY = 1e-12
+TOL_PCG = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    assert a.shape == b.shape
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def close(a, b, tol=TOL_APPLY):
+    e = relerr(a, b)
+    assert e <= tol, f"rel err {e:.3e} > {tol:.1e}"
+
+
+class Dev:
+    """a golden case uploaded to the GPU"""
+
+    def __init__(self, ctx, c):
+        self.c, self.ctx = c, ctx
+        self.D, self.Q, self.NE, self.nd = c["D1D"], c["Q1D"], c["NE"], c["ndofs"]
+        self._cache = {}
+
+    def __getitem__(self, k):
+        if k not in self._cache:
+            self._cache[k] = self.ctx.to_dev(self.c[k])
+        return self._cache[k]
+
+    def space(self, geometry="given"):
+        c = self.c
+        sp = b200pa.Space(self.ctx, self.D, self.Q, self.NE, self.nd, c["gather_map"], c["B"], c["G"])
+        if geometry == "given":
+            sp.set_geometry(c["W"], self["J"], self["detJ"])
+        elif geometry == "vertices":
+            sp.geometry_from_vertices(c["W"], c["vertices"], c["elem_vertices"])
+        return sp
+
+    def form(self, sp, diff=True, mass=True, ess=True, assemble=False):
+        f = b200pa.Form(sp)
+        if assemble:
+            f.assemble_diffusion(self.c["kq"] if diff else None)
+            f.assemble_mass(self.c["mq"] if mass else None)
+        else:
+            f.set_pa_data(self["pa_diff"] if diff else None, self["pa_mass"] if mass else None)
+        f.set_essential(self.c["ess"] if ess else None)
+        return f
+
+
+@pytest.fixture
+def dev(ctx, case):
+    return Dev(ctx, case)
+
+
+def test_restriction(ctx, dev):
+    c = dev.c
+    nd3 = dev.D ** 3
+    xE = ctx.restrict_mult(dev.NE, nd3, dev["gather_map"], dev["x"])
+    assert np.array_equal(ctx.to_host(xE), c["xE"])                      # pure data movement: bit-exact
+    y = ctx.restrict_mult_transpose(dev.nd, dev["offsets"], dev["indices"], dev["yE_diff"])
+    assert np.array_equal(ctx.to_host(y), c["y_diff"])                   # same summation order: bit-exact
+    ya = ctx.restrict_mult_transpose(dev.nd, dev["offsets"], dev["indices"], dev["dE_diff"], abs_=True)
+    close(ctx.to_host(ya), orc.restrict_mult_transpose(dev.nd, c["offsets"], c["indices"], c["dE_diff"], True), 0.0)
+
+
+def test_space_tables_match_reference(ctx, dev):
+    sp = dev.space(geometry=None)
+    assert np.array_equal(sp.offsets(), dev.c["offsets"])
+    assert np.array_equal(sp.indices(), dev.c["indices"])
+    sp.close()
+
+
+def test_setup(ctx, dev):
+    c = dev.c
+    D = ctx.diffusion_setup(dev.Q, dev.NE, dev["W"], dev["J"], dev["kq"])
+    close(ctx.to_host(D), c["pa_diff"])
+    close(ctx.to_host(D), orc.diffusion_setup(dev.Q, dev.NE, c["W"], c["J"], c["kq"]))
+    v = ctx.mass_setup(dev.Q, dev.NE, dev["W"], dev["detJ"], dev["mq"])
+    close(ctx.to_host(v), c["pa_mass"])
+
+
+def test_geometry_from_vertices(ctx, dev):
+    sp = dev.space(geometry="vertices")
+    close(sp.J(), dev.c["J"])
+    close(sp.detJ(), dev.c["detJ"])
+    sp.close()
+
+
+def test_apply_E(ctx, dev):
+    c = dev.c
+    n = dev.NE * dev.D ** 3
+    y = ctx.diffusion_apply(dev.NE, dev.D, dev.Q, c["B"], c["G"], dev["pa_diff"], dev["xE"], ctx.zeros(n))
+    close(ctx.to_host(y), c["yE_diff"])
+    y = ctx.mass_apply(dev.NE, dev.D, dev.Q, c["B"], dev["pa_mass"], dev["xE"], ctx.zeros(n))
+    close(ctx.to_host(y), c["yE_mass"])
+    # accumulate semantics (AddMultPA): y += ...
+    y = ctx.diffusion_apply(dev.NE, dev.D, dev.Q, c["B"], c["G"], dev["pa_diff"], dev["xE"], ctx.zeros(n))
+    y = ctx.mass_apply(dev.NE, dev.D, dev.Q, c["B"], dev["pa_mass"], dev["xE"], y)
+    close(ctx.to_host(y), c["yE"])
+    close(ctx.to_host(y), orc.mass_apply(dev.NE, dev.D, dev.Q, c["B"], c["pa_mass"], c["xE"],
+                                         orc.diffusion_apply(dev.NE, dev.D, dev.Q, c["B"], c["G"], c["pa_diff"], c["xE"])))
+
+
+def test_diag_E(ctx, dev):
+    c = dev.c
+    n = dev.NE * dev.D ** 3
+    d = ctx.diffusion_diag(dev.NE, dev.D, dev.Q, c["B"], c["G"], dev["pa_diff"], ctx.zeros(n))
+    close(ctx.to_host(d), c["dE_diff"])
+    d = ctx.mass_diag(dev.NE, dev.D, dev.Q, c["B"], dev["pa_mass"], ctx.zeros(n))
+    close(ctx.to_host(d), c["dE_mass"])
+
+
+@pytest.mark.parametrize("assemble", [False, True])
+def test_form_mult_and_diag(ctx, dev, assemble):
+    c = dev.c
+    sp = dev.space()
+    f = dev.form(sp, assemble=assemble)
+    close(ctx.to_host(f.mult(dev["x"])), c["y"])
+    close(ctx.to_host(f.assemble_diagonal()), c["diag"])
+    close(ctx.to_host(f.constrained_mult(dev["x"])), c["y_constrained"])
+    # host-buffer entry point
+    yh = np.zeros(dev.nd)
+    f.mult_host(np.ascontiguousarray(c["x"]), yh)
+    close(yh, c["y"])
+    # single-integrator forms
+    fd = dev.form(sp, diff=True, mass=False, assemble=assemble)
+    close(ctx.to_host(fd.mult(dev["x"])), c["y_diff"])
+    fm = dev.form(sp, diff=False, mass=True, assemble=assemble)
+    close(ctx.to_host(fm.mult(dev["x"])), c["y_mass"])
+    for h in (f, fd, fm):
+        h.close()
+    sp.close()
+
+
+def test_rhs_and_jacobi(ctx, dev):
+    c = dev.c
+    sp = dev.space()
+    f = dev.form(sp)
+    b = ctx.to_dev(c["b_L"])
+    f.eliminate_rhs(dev["x0_L"], b)
+    close(ctx.to_host(b), c["B_rhs"])
+    dinv = f.jacobi()
+    close(ctx.to_host(ctx.jacobi_mult(dinv, dev["x"])), c["jacobi_z"])
+    f.close()
+    sp.close()
+
+
+def test_blas1(ctx, dev):
+    c = dev.c
+    x, y = dev["x"], dev["y"]
+    d = ctx.dot(x, y)
+    ref = orc.dot(c["x"], c["y"])
+    assert abs(d - ref) <= 1e-13 * np.sum(np.abs(c["x"] * c["y"]))
+    assert d == ctx.dot(x, y)                                            # deterministic run to run
+    close(ctx.to_host(ctx.add(x, -0.37, y)), c["x"] - 0.37 * c["y"], 1e-15)
+
+
+def test_pcg(ctx, dev):
+    c = dev.c
+    sp = dev.space()
+    f = dev.form(sp)
+    dinv = f.jacobi()
+    kmax = len(c["pcg_norms"]) - 1
+    for k in (1, 2, kmax):
+        x = ctx.to_dev(c["X0"])
+        res, norms = f.pcg(dinv, dev["B_rhs"], x, 0.0, 0.0, k)
+        assert res.final_iter == k and not res.converged
+        close(ctx.to_host(x), c[f"X_pcg{k}"], TOL_PCG)
+    close(norms, c["pcg_norms"], 1e-9)
+    # to tolerance: iteration count within +-1 of the reference, same flags
+    x = ctx.to_dev(c["X0"])
+    res, norms = f.pcg(dinv, dev["B_rhs"], x, 1e-8, 0.0, 5000)
+    assert abs(res.final_iter - int(c["pcg_tol_iters"][0])) <= 1
+    assert bool(res.converged) == bool(c["pcg_tol_converged"][0])
+    if res.final_iter == int(c["pcg_tol_iters"][0]):
+        assert abs(res.final_norm - c["pcg_tol_final_norm"][0]) <= 1e-6 * c["pcg_tol_final_norm"][0]
+    close(ctx.to_host(x), c["X_pcg_tol"], 1e-7)   # both are 1e-8-converged iterates
+    # host-buffer entry point, same answer as the device one
+    xh = np.ascontiguousarray(c["X0"]).copy()
+    res2, _ = f.pcg(dinv, np.ascontiguousarray(c["B_rhs"]), xh, 0.0, 0.0, kmax, host=True)
+    assert res2.final_iter == kmax
+    close(xh, c[f"X_pcg{kmax}"], TOL_PCG)
+    # against the oracle with the same Jacobi
+    op = orc.Operator(dev.D, dev.Q, dev.NE, dev.nd, c["gather_map"], c["B"], c["G"], c["pa_diff"], c["pa_mass"], c["ess"])
+    xo, it, conv, fn, _ = op.pcg(op.jacobi_dinv(), c["B_rhs"], c["X0"], 0.0, 0.0, kmax)
+    close(xh, xo, TOL_PCG)
+    f.close()
+    sp.close()
+
+
+def test_pcg_edge_cases(ctx, dev):
+    c = dev.c
+    sp = dev.space()
+    f = dev.form(sp)
+    dinv = f.jacobi()
+    # already converged: x = exact-ish solution, huge tolerance -> 0 iterations, converged
+    x = ctx.to_dev(c["X_pcg_tol"])
+    res, norms = f.pcg(dinv, dev["B_rhs"], x, 0.5, 0.0, 50)
+    assert res.final_iter == 0 and res.converged and len(norms) == 1
+    # zero rhs and zero guess: (Br,r) = 0 <= r0 -> converged at iteration 0
+    z = ctx.zeros(dev.nd)
+    res, _ = f.pcg(dinv, ctx.zeros(dev.nd), z, 1e-12, 0.0, 10)
+    assert res.final_iter == 0 and res.converged and res.final_norm == 0.0
+    # max_iter smaller than needed: not converged, final_iter == max_iter
+    x = ctx.to_dev(c["X0"])
+    res, _ = f.pcg(dinv, dev["B_rhs"], x, 1e-14, 0.0, 3)
+    assert res.final_iter == 3 and not res.converged
+    f.close()
+    sp.close()
+
+
+def test_qpoint_ops(ctx, dev):
+    c = dev.c
+    close(ctx.to_host(ctx.qvalues(dev.NE, dev.D, dev.Q, c["B"], dev["xE"])), c["xq_values"])
+    close(ctx.to_host(ctx.qphysgrad(dev.NE, dev.D, dev.Q, c["B"], c["G"], dev["J"], dev["xE"])), c["xq_physgrad"])
+    n = dev.NE * dev.D ** 3
+    bE = ctx.domain_lf(dev.NE, dev.D, dev.Q, c["B"], dev["detJ"], dev["W"], dev["lf_fq"], ctx.zeros(n))
+    b = ctx.restrict_mult_transpose(dev.nd, dev["offsets"], dev["indices"], bE)
+    close(ctx.to_host(b), c["lf_b"])
+    # fused L-vector variants
+    sp = dev.space()
+    close(ctx.to_host(sp.qvalues(dev["x"])), c["xq_values"])
+    close(ctx.to_host(sp.qphysgrad(dev["x"])), c["xq_physgrad"])
+    close(ctx.to_host(sp.domain_lf(dev["lf_fq"])), c["lf_b"])
+    k = ctx.to_host(sp.coeff_linear(0.5, 0.02, 37.0, dev["x"]))
+    close(k, 0.5 * (1.0 + 0.02 * (c["xq_values"] - 37.0)), 1e-14)
+    g = c["xq_physgrad"].reshape(-1, 3)
+    s = ctx.to_dev(c["xq_values"])
+    j = ctx.to_host(sp.joule(dev["x"], s, 1.5))
+    close(j, c["xq_values"] * (g * g).sum(1) + 1.5)
+    # unfused coefficient kernel
+    cq = ctx.coeff_eval(2, dev.NE * dev.Q ** 3, 1.5, 0.0, 0.0, None, s, dev["xq_physgrad"])
+    close(ctx.to_host(cq), c["xq_values"] * (g * g).sum(1) + 1.5, 1e-14)
+    sp.close()
+
+
+def test_unsupported_rejected(ctx):
+    """no fallback kernel: (D1D,Q1D) outside the supported set is an error, not a slow path"""
+    gm = np.zeros(8, np.int32)
+    with pytest.raises(b200pa.B200paError, match="unsupported"):
+        b200pa.Space(ctx, 2, 2, 1, 8, gm, np.zeros(4), np.zeros(4))
+    with pytest.raises(b200pa.B200paError, match="unsupported"):
+        b200pa.Space(ctx, 9, 10, 1, 8, gm, np.zeros(90), np.zeros(90))
+    bad = np.array([0, 1, 2, 3, 4, 5, 6, -1], np.int32)
+    with pytest.raises(b200pa.B200paError, match="negative"):
+        b200pa.Space(ctx, 2, 3, 1, 8, bad, np.zeros(6), np.zeros(6))
+
+
+def test_empty_space(ctx):
+    """ragged/empty input: a rank that owns no elements"""
+    b = b200pa.basis(2)
+    sp = b200pa.Space(ctx, 3, 4, 0, 0, np.zeros(0, np.int32), b["B"], b["G"])
+    sp.close()
