@@ -41,11 +41,11 @@ b200pa_space_offsets b200pa_space_indices b200pa_space_gather_map b200pa_space_J
 b200pa_space_qvalues b200pa_space_qphysgrad b200pa_space_coeff_linear b200pa_space_joule b200pa_space_domain_lf
 b200pa_form_create b200pa_form_destroy b200pa_form_assemble_diffusion b200pa_form_assemble_mass
 b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_essential b200pa_form_mult
-b200pa_form_constrained_mult b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
+b200pa_form_constrained_mult b200pa_form_mult_phases b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
 b200pa_pcg_solve b200pa_pcg_solve_host
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
 b200pa_comm_owner_mask b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
-b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis
+b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
 """.split()
 
 
@@ -132,6 +132,13 @@ def basis(p, q1d=None):
     w1d, W, gll = np.empty(q1d), np.empty(q1d ** 3), np.empty(D)
     check(lib().b200pa_basis(p, q1d, _ptr(B), _ptr(G), _ptr(w1d), _ptr(W), _ptr(gll)))
     return {"B": B, "G": G, "w1d": w1d, "W": W, "gll": gll}
+
+
+def randomize(n, seed=1):
+    """Vector::Randomize(seed): the reference's test / benchmark input vector"""
+    out = np.empty(int(n))
+    check(lib().b200pa_randomize(int(seed), C.c_longlong(int(n)), _ptr(out)))
+    return out
 
 
 def essential_dofs(bdr_attr, attrs):
@@ -408,6 +415,10 @@ class Form:
     def mult(self, x, y=None):
         y = self.ctx.empty(self.sp.ndofs) if y is None else y
         check(lib().b200pa_form_mult(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def mult_phases(self, x, y, phases):
+        check(lib().b200pa_form_mult_phases(self.h, _ptr(x), _ptr(y), int(phases)))
         return y
 
     def constrained_mult(self, x, y=None):

@@ -815,7 +815,8 @@ extern "C" int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *es
 
 // y = A x (constrained: ConstrainedOperator::Mult, DIAG_ONE).  dot_out != NULL adds x.y (owned dofs)
 // into the segmented reduction's epilogue.  done: PCG early-exit flag.
-static int form_apply(b200pa_form f, const double *x, double *y, bool constrained, double *dot_out, const int *done)
+static int form_apply(b200pa_form f, const double *x, double *y, bool constrained, double *dot_out, const int *done,
+                      int phases = 3)
 {
    b200pa_space sp = f->sp;
    b200pa_ctx ctx = sp->ctx;
@@ -829,8 +830,8 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
    a.pa_diff = f->has_diff ? f->pa_diff.as<double>() : nullptr;
    a.pa_mass = f->has_mass ? f->pa_mass.as<double>() : nullptr;
    a.done = done;
-   if (run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
-   if (sp->ndofs == 0) { return 0; }
+   if ((phases & 1) && run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
+   if (sp->ndofs == 0 || !(phases & 2)) { return 0; }
    const int grid = grid1d(ctx, sp->ndofs);
    const int *off = sp->offsets.as<int>();
    const double *yS = sp->scratchE.as<double>();
@@ -878,6 +879,13 @@ extern "C" int b200pa_form_mult(b200pa_form f, const double *x_dev, double *y_de
    B200PA_REQUIRE(f && x_dev && y_dev, "form_mult: NULL argument");
    NEED_CTX(f->sp->ctx);
    return form_apply(f, x_dev, y_dev, false, nullptr, nullptr);
+}
+
+extern "C" int b200pa_form_mult_phases(b200pa_form f, const double *x_dev, double *y_dev, int phases)
+{
+   B200PA_REQUIRE(f && x_dev && y_dev, "form_mult_phases: NULL argument");
+   NEED_CTX(f->sp->ctx);
+   return form_apply(f, x_dev, y_dev, false, nullptr, nullptr, phases);
 }
 
 extern "C" int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_dev)

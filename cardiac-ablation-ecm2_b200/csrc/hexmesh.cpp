@@ -17,6 +17,7 @@
 // instead of carrying orientation tables around.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -358,6 +359,15 @@ extern "C" int b200pa_hex_dof_lattice(int nx, int ny, int nz, int p, int *lattic
 {
    if (!lattice) { return hfail("hex_dof_lattice: NULL output"); }
    return b200pa_hex_build_part(nx, ny, nz, 0, 0, 0, nx, ny, nz, p, 1, 1, 1, 0, nullptr, nullptr, nullptr, nullptr, nullptr, lattice);
+}
+
+extern "C" int b200pa_randomize(int seed, long long n, double *out)
+{
+   if (n < 0 || (n > 0 && !out)) { return hfail("randomize: bad arguments"); }
+   srand((unsigned)seed);
+   const double scale = 1.0 / ((double)RAND_MAX + 1.0);
+   for (long long i = 0; i < n; ++i) { out[i] = rand() * scale; }
+   return 0;
 }
 
 extern "C" int b200pa_basis(int p, int q1d, double *B, double *G, double *w1d, double *W, double *gll_nodes)

@@ -174,6 +174,9 @@ int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any);
 /* PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487-564): y = A x, L→L, unconstrained.
  * One fused gather + sum-factorised contraction launch and one segmented E→L reduction. */
 int b200pa_form_mult(b200pa_form f, const double *x_dev, double *y_dev);
+/* profiling hook for bench.py's per-kernel roofline: phases bit 0 = the fused gather + element
+ * kernel only (writes the E-sized scratch), bit 1 = the segmented E->L reduction only; 3 = mult */
+int b200pa_form_mult_phases(b200pa_form f, const double *x_dev, double *y_dev, int phases);
 /* ConstrainedOperator::Mult (linalg/operator.cpp:586-646, 710-714) */
 int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_dev);
 /* the same two with HOST vectors: copies x up, applies, copies y back, synchronises */
@@ -260,6 +263,9 @@ int b200pa_hex_build_part(int GNX, int GNY, int GNZ, int ox, int oy, int oz, int
                           double *vertices, int *elem_ijk, unsigned char *bdr_attr_of_dof, int *lattice);
 /* lattice coordinates (ix,iy,iz in [0,p*n]) of every L-dof: int32[3*ndofs] */
 int b200pa_hex_dof_lattice(int nx, int ny, int nz, int p, int *lattice);
+/* Vector::Randomize(seed) (linalg/vector.cpp:955-967, rand_real linalg/vector.hpp:61-80):
+ * srand(seed); out[i] = rand() / (RAND_MAX + 1.0) — the reference tests' and benchmarks' input */
+int b200pa_randomize(int seed, long long n, double *out_host);
 /* DofToQuad in TENSOR mode for H1 (GLL nodes) at the Gauss-Legendre rule with q1d points
  * (fem/fe/fe_base.cpp:2619-2662, fem/intrules.cpp): B,G f64[q1d*d1d] column-major, w1d f64[q1d],
  * W f64[q1d^3] */
