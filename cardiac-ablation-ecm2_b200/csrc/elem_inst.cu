@@ -2,6 +2,7 @@
 //   nvcc ... -DB200PA_D=3 -DB200PA_Q=4 -c elem_inst.cu -o elem_3_4.o
 #include "elem_launch.cuh"
 #include "pa_element_kernel.cuh"
+#include "pa_apply_kernel.cuh"
 
 #ifndef B200PA_D
 #error "compile with -DB200PA_D=<D1D> -DB200PA_Q=<Q1D>"
@@ -13,6 +14,17 @@ namespace b200pa
 namespace
 {
 constexpr int D = B200PA_D, Q = B200PA_Q;
+
+template <int DD, int QQ>
+void fill_params(ElemParams<DD, QQ> &P, const ElemArgs &a)
+{
+   for (int i = 0; i < QQ * DD; ++i) { P.bg.B[i] = a.B[i]; P.bg.G[i] = a.G ? a.G[i] : 0.0; }
+   P.NE = a.NE;
+   P.x = a.x; P.gmap = a.gmap; P.y = a.y; P.slot = a.slot;
+   P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.J = a.J;
+   P.f = a.f; P.detJ = a.detJ; P.W = a.W; P.nf = a.nf; P.done = a.done;
+   P.ca = a.ca; P.cb = a.cb; P.cT0 = a.cT0; P.s = a.s;
+}
 
 template <bool DIFF, bool MASS, int INMODE, int OUTMODE, int QOP>
 int run(const ElemArgs &a, int num_sms, cudaStream_t stream)
@@ -30,17 +42,45 @@ int run(const ElemArgs &a, int num_sms, cudaStream_t stream)
       blocks_per_sm = n > 0 ? n : 1;
    }
    ElemParams<D, Q> P;
-   for (int i = 0; i < Q * D; ++i) { P.bg.B[i] = a.B[i]; P.bg.G[i] = a.G ? a.G[i] : 0.0; }
-   P.NE = a.NE;
-   P.x = a.x; P.gmap = a.gmap; P.y = a.y; P.slot = a.slot;
-   P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.J = a.J;
-   P.f = a.f; P.detJ = a.detJ; P.W = a.W; P.nf = a.nf; P.done = a.done;
-   P.ca = a.ca; P.cb = a.cb; P.cT0 = a.cT0; P.s = a.s;
+   fill_params(P, a);
    if (a.NE <= 0) { return 0; }
    const int nbatch = (a.NE + L::NEB - 1) / L::NEB;
    const int grid = nbatch < num_sms * blocks_per_sm ? nbatch : num_sms * blocks_per_sm;
    kern<<<grid, L::NT, L::SMEM_BYTES, stream>>>(P);
    return (int)cudaGetLastError();
+}
+
+// the hot path: gather -> diffusion (+ mass) -> slot write (pa_apply_kernel.cuh)
+template <bool DIFF, bool MASS>
+int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   using C = ApplyCfg<D, Q>;
+   auto kern = pa_apply_kernel<D, Q, DIFF, MASS>;
+   static int blocks_per_sm = 0;
+   if (blocks_per_sm == 0)
+   {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+      if (e != cudaSuccess) { return (int)e; }
+      int n = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::NT, C::SMEM_BYTES);
+      if (e != cudaSuccess) { return (int)e; }
+      blocks_per_sm = n > 0 ? n : 1;
+   }
+   if (a.NE <= 0) { return 0; }
+   ElemParams<D, Q> P;
+   fill_params(P, a);
+   const int nbatch = (a.NE + C::NEB - 1) / C::NEB;
+   const int grid = nbatch < num_sms * blocks_per_sm ? nbatch : num_sms * blocks_per_sm;
+   kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(P);
+   return (int)cudaGetLastError();
+}
+
+int run_apply_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   if (a.pa_diff && a.pa_mass) { return run_fused<true, true>(a, num_sms, stream); }
+   if (a.pa_diff) { return run_fused<true, false>(a, num_sms, stream); }
+   if (a.pa_mass) { return run_fused<false, true>(a, num_sms, stream); }
+   return (int)cudaErrorInvalidValue;
 }
 
 template <int INMODE, int OUTMODE>
@@ -61,7 +101,7 @@ int B200PA_NAME(B200PA_D, B200PA_Q)(int variant, const ElemArgs &a, int num_sms,
    switch (variant)
    {
       case EV_APPLY_E: return run_apply<IN_E, OUT_E_ADD>(a, num_sms, stream);
-      case EV_APPLY_L2S: return run_apply<IN_GATHER, OUT_SLOT>(a, num_sms, stream);
+      case EV_APPLY_L2S: return run_apply_fused(a, num_sms, stream);
       case EV_VALUES_E: return run<false, false, IN_E, OUT_NONE, QOP_VALUES>(a, num_sms, stream);
       case EV_VALUES_L: return run<false, false, IN_GATHER, OUT_NONE, QOP_VALUES>(a, num_sms, stream);
       case EV_PHYSGRAD_E: return run<false, false, IN_E, OUT_NONE, QOP_PHYSGRAD>(a, num_sms, stream);

@@ -206,9 +206,10 @@ def test_pcg_edge_cases(ctx, dev):
     sp = dev.space()
     f = dev.form(sp)
     dinv = f.jacobi()
-    # already converged: x = exact-ish solution, huge tolerance -> 0 iterations, converged
+    # already converged: x = 1e-8-converged solution, absolute tolerance above its residual
+    # -> (Br,r) <= r0 at iteration 0 (linalg/solvers.cpp:919-927)
     x = ctx.to_dev(c["X_pcg_tol"])
-    res, norms = f.pcg(dinv, dev["B_rhs"], x, 0.5, 0.0, 50)
+    res, norms = f.pcg(dinv, dev["B_rhs"], x, 0.0, 1.0, 50)
     assert res.final_iter == 0 and res.converged and len(norms) == 1
     # zero rhs and zero guess: (Br,r) = 0 <= r0 -> converged at iteration 0
     z = ctx.zeros(dev.nd)
