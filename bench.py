@@ -24,7 +24,6 @@ sys.path.insert(0, os.path.join(ROOT, "cardiac-ablation-ecm2_b200"))
 
 METRIC = "GDOF/s of FP64 PA diffusion+mass apply"
 PHYS = dict(dt=0.5, rc=3.6e6, wbcb=4.0e4, Ta=37.0, k0=0.5, ak=0.02, s0=0.3, as_=0.015, V=30.0)
-GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
 def algorithmic_bytes_per_dof(p, ncomp=7):
@@ -160,41 +159,6 @@ def reference_arm(args):
     return 0
 
 
-def shared_tables(lattice, lo, hi, grid, rc):
-    """neighbour tables of a box partition: dofs on the closed-box intersections, ordered by global
-    lattice key so both sides agree (≙ GroupCommunicator neighbour tables)"""
-    import numpy as np
-    lat = lattice.reshape(-1, 3).astype(np.int64)
-    PX, PY, PZ = grid
-    big = int(lat.max()) + 2
-    key = (lat[:, 2] * big + lat[:, 1]) * big + lat[:, 0]
-    nbrs = []
-    for dz in (-1, 0, 1):
-        for dy in (-1, 0, 1):
-            for dx in (-1, 0, 1):
-                if dx == dy == dz == 0:
-                    continue
-                q = (rc[0] + dx, rc[1] + dy, rc[2] + dz)
-                if not (0 <= q[0] < PX and 0 <= q[1] < PY and 0 <= q[2] < PZ):
-                    continue
-                m = np.ones(len(lat), bool)
-                for a, d in enumerate((dx, dy, dz)):
-                    if d == 1:
-                        m &= lat[:, a] == hi[a]
-                    elif d == -1:
-                        m &= lat[:, a] == lo[a]
-                idx = np.nonzero(m)[0]
-                idx = idx[np.argsort(key[idx], kind="stable")]
-                nbrs.append((q[0] + PX * (q[1] + PY * q[2]), idx.astype(np.int32)))
-    nbrs.sort(key=lambda t: t[0])
-    ranks = np.array([t[0] for t in nbrs], np.int32)
-    offs = np.zeros(len(nbrs) + 1, np.int32)
-    for i, t in enumerate(nbrs):
-        offs[i + 1] = offs[i] + len(t[1])
-    ldofs = np.concatenate([t[1] for t in nbrs]) if nbrs else np.zeros(0, np.int32)
-    return ranks, offs, ldofs
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU")
+    ap.add_argument("--ops", default="both", choices=["both", "diff"], help="diffusion+mass (headline) or diffusion only (configs[3] sweep)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip PCG / implicit-step extras (profiling runs)")
     args = ap.parse_args()
@@ -225,16 +190,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     p, n, K, W = args.order, args.n, args.steps, args.warmup
-    grid = GRIDS.get(world)
+    from b200pa import partition
+    grid = partition.GRIDS.get(world)
     if grid is None:
         raise SystemExit(f"unsupported world size {world}")
-    rc = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
     GN = (n * grid[0], n * grid[1], n * grid[2])
-    off = (n * rc[0], n * rc[1], n * rc[2])
 
     # ---- problem set-up (host builder -> device handles); not timed
     t_setup = time.perf_counter()
-    m = b200pa.hex_build(n, n, n, p, part=(*GN, *off), want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
+    m = partition.build_part(GN, grid, rank, p, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
     bas = b200pa.basis(p)
     ctx = b200pa.Context(local)
     nd, ne = m["ndofs"], m["ne"]
@@ -250,16 +214,15 @@ def main():
     mq = ctx.coeff_eval(1, nq, PHYS["rc"] / PHYS["dt"] + PHYS["wbcb"], 0.0, 0.0)
     form = b200pa.Form(sp)
     form.assemble_diffusion(kq)
-    form.assemble_mass(mq)
+    if args.ops == "both":
+        form.assemble_mass(mq)
     form.set_essential(None)
     comm = None
     if world > 1:
         ids = [b200pa.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         comm = b200pa.Comm(ctx, ids[0], rank, world)
-        lo = [off[a] * p for a in range(3)]
-        hi = [(off[a] + n) * p for a in range(3)]
-        comm.set_tables(nd, *shared_tables(m["lattice"], lo, hi, grid, rc))
+        comm.set_tables(nd, *partition.shared_tables(m, grid, p))
         form.set_comm(comm)
     global_dofs = (GN[0] * p + 1) * (GN[1] * p + 1) * (GN[2] * p + 1)
     xh = b200pa.randomize(nd, 1) if world == 1 else np.random.default_rng(1).random(nd)
@@ -315,7 +278,7 @@ def main():
     Ke = max(3, min(K, 20))
     ms_e2e = timed(lambda: form.mult_host(xp, yp), Ke)
 
-    bytes_total, bytes_elem = algorithmic_bytes_per_dof(p)
+    bytes_total, bytes_elem = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6)
     peak, peak_src = measured_peak_hbm()
     t_elem = ms_elem / K * 1e-3
     achieved = bytes_elem * nd / t_elem / 1e9
@@ -326,7 +289,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"configs[1]: Pennes bioheat operator k(T) diffusion + (rho c/dt + perfusion) mass, PA apply L->L, "
                                f"hex {GN[0]}x{GN[1]}x{GN[2]} (N={n}^3 per GPU), order {p}, {global_dofs} dofs",
-                   "order": p, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
+                   "order": p, "ops": args.ops, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
                    "partition": "x".join(map(str, grid)),
                    "l2": f"q-data + index streams = {bytes_total * nd / 1e9:.2f} GB per step >> 126 MB L2, no flush needed"},
         "e2e": {"value": global_dofs * Ke / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * nd,
@@ -358,7 +321,8 @@ def main():
         def implicit_step():
             k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0, out=kq)
             form.assemble_diffusion(k2)
-            form.assemble_mass(mq)
+            if args.ops == "both":
+                form.assemble_mass(mq)
             d2 = form.jacobi()
             T1.copy_(T0)
             return form.pcg(d2, rhs, T1, 1e-8, 0.0, 500, want_norms=False)[0]

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200pa.so")
+LIB_PATH = os.environ.get("B200PA_LIB") or os.path.join(os.path.dirname(_HERE), "libb200pa.so")  # env: tuning builds
 _lib = None
 
 c_dp = C.POINTER(C.c_double)

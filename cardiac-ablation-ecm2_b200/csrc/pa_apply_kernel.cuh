@@ -36,9 +36,16 @@ struct ApplyCfg
 {
    static constexpr int D2 = D * D, D3 = D * D * D, Q2 = Q * Q, Q3 = Q * Q * Q;
    // elements per batch: one q-point column per thread
+#ifdef B200PA_TUNE_NEB   // tuning builds only (tools/tune.sh)
+   static constexpr int NEB = B200PA_TUNE_NEB;
+   static constexpr int MINB = B200PA_TUNE_MINB;
+   static constexpr bool QPF = B200PA_TUNE_QPF;
+#else
    static constexpr int NEB = (D == 2) ? 14 : (D == 3) ? 8 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
-   static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int MINB = (D <= 4) ? 4 : (D == 5 ? 3 : 2); // resident CTAs per SM the register budget is tuned for
+   static constexpr bool QPF = true;                             // q-data prefetched one batch ahead (registers)
+#endif
+   static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int NIO = (NEB * D3 + NT - 1) / NT;          // gather / scatter items per thread
    static constexpr int SXS = D2 | 1;                            // slab stride of sXin / sXout
    // sE strides: see tools/smem_strides.py (searches the conflict-free pads per order)
@@ -119,7 +126,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    if (batch < nbatch)
    {
       load_gidx(batch);
-      load_qdata(batch);
+      if (C::QPF) { load_qdata(batch); }
       load_x();
    }
    for (; batch < nbatch; batch += gridDim.x)
@@ -194,6 +201,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // -------------------------------- phase B: column, q-point op, column^T
+      if (!C::QPF) { load_qdata(batch); }
       if (actB)
       {
          double *s = sE + eB * ES + cB;
@@ -250,7 +258,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // prefetch for the next batch: q-data column and gathered x (indices arrived during phase A)
       if (next < nbatch)
       {
-         load_qdata(next);
+         if (C::QPF) { load_qdata(next); }
          load_x();
       }
       __syncthreads();
