@@ -31,7 +31,7 @@ class PcgResult(C.Structure):
 # every symbol include/b200pa.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = """
 b200pa_version b200pa_last_error b200pa_launch_count
-b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download
+b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset
 b200pa_restrict_mult b200pa_restrict_mult_transpose b200pa_diffusion_setup b200pa_mass_setup
 b200pa_diffusion_apply b200pa_mass_apply b200pa_diffusion_diag b200pa_mass_diag b200pa_qvalues
 b200pa_qphysgrad b200pa_domain_lf b200pa_dot b200pa_add b200pa_jacobi_setup b200pa_jacobi_mult

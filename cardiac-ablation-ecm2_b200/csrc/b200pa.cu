@@ -203,6 +203,29 @@ extern "C" int b200pa_ctx_sync(b200pa_ctx c)
    return 0;
 }
 extern "C" void *b200pa_ctx_stream(b200pa_ctx c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int b200pa_malloc(b200pa_ctx c, size_t bytes, void **out)
+{
+   B200PA_REQUIRE(c && out, "malloc: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   B200PA_CK(cudaMalloc(out, bytes ? bytes : 8));
+   return 0;
+}
+extern "C" int b200pa_free(b200pa_ctx c, void *p)
+{
+   B200PA_REQUIRE(c, "free: ctx is NULL");
+   if (!p) { return 0; }
+   B200PA_CK(cudaSetDevice(c->device));
+   B200PA_CK(cudaStreamSynchronize(c->stream));
+   B200PA_CK(cudaFree(p));
+   return 0;
+}
+extern "C" int b200pa_memset(b200pa_ctx c, void *p, int value, size_t bytes)
+{
+   B200PA_REQUIRE(c && (p || !bytes), "memset: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   if (bytes) { B200PA_CK(cudaMemsetAsync(p, value, bytes, c->stream)); }
+   return 0;
+}
 extern "C" int b200pa_ctx_upload(b200pa_ctx c, void *dst_dev, const void *src_host, size_t bytes)
 {
    B200PA_REQUIRE(c && (bytes == 0 || (dst_dev && src_host)), "ctx_upload: NULL argument");

@@ -1,0 +1,316 @@
+// mfem_b200pa.hpp — the reference-side binding: MFEM classes whose PA virtuals run on a B200 through
+// the C ABI of libb200pa.so (include/b200pa.h).  Header-only; include it from an MFEM application
+// (a CPU build of MFEM is enough: the host library never sees a device pointer) and link -lb200pa.
+//
+//   drop-in level 1  b200::DiffusionIntegrator / b200::MassIntegrator
+//        subclasses of mfem::DiffusionIntegrator / mfem::MassIntegrator that override
+//        AssemblePA / AddMultPA / AddMultTransposePA / AssembleDiagonalPA (fem/bilininteg.hpp:52-97).
+//        Hand them to an ordinary BilinearForm with AssemblyLevel::PARTIAL; MFEM's own
+//        PABilinearFormExtension (fem/bilinearform_ext.cpp:332-564) keeps orchestrating gather,
+//        integrator calls and scatter, E-vectors cross PCIe per call.  Bit-for-tolerance, not fast.
+//   drop-in level 2  b200::PAOperator (an mfem::Operator) + b200::PCGSolver (an mfem::Solver)
+//        the whole L->L apply (ElementRestriction::Mult, both AddMultPA, MultTranspose) as one fused
+//        launch pair, ConstrainedOperator semantics, OperatorJacobiSmoother and CGSolver::Mult
+//        (linalg/solvers.cpp:869-1050) resident on the GPU; vectors cross PCIe once per solve.
+//
+// Error convention: a nonzero status from the C ABI becomes mfem::mfem_error(b200pa_last_error()),
+// i.e. MFEM_ABORT semantics (general/error.hpp:26-64).  Unsupported spaces (non-hex, vdim > 1,
+// orders > 6, non-default rules, matrix coefficients) abort: there is no CPU fallback.
+#ifndef MFEM_B200PA_HPP
+#define MFEM_B200PA_HPP
+
+#include "mfem.hpp"
+
+#include "../../include/b200pa.h"
+
+namespace b200
+{
+
+inline void Check(int rc)
+{
+   if (rc) { mfem::mfem_error(b200pa_last_error()); }
+}
+
+/// One context per process and GPU (≙ mfem::Device for this path).
+inline b200pa_ctx Ctx(int device = 0)
+{
+   static b200pa_ctx ctx = nullptr;
+   if (!ctx) { Check(b200pa_ctx_create(device, nullptr, &ctx)); }
+   return ctx;
+}
+
+/// RAII device buffer owned by the library side.
+class DeviceBuffer
+{
+   void *p = nullptr;
+   size_t bytes = 0;
+public:
+   DeviceBuffer() = default;
+   DeviceBuffer(const DeviceBuffer &) = delete;
+   DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+   ~DeviceBuffer() { if (p) { b200pa_free(Ctx(), p); } }
+   void Resize(size_t n)
+   {
+      if (n <= bytes && p) { return; }
+      if (p) { Check(b200pa_free(Ctx(), p)); p = nullptr; }
+      Check(b200pa_malloc(Ctx(), n, &p));
+      bytes = n;
+   }
+   void Upload(const void *src, size_t n) { Resize(n); Check(b200pa_ctx_upload(Ctx(), p, src, n)); }
+   void Download(void *dst, size_t n) const { Check(b200pa_ctx_download(Ctx(), dst, p, n)); }
+   double *D() const { return static_cast<double *>(p); }
+   int *I() const { return static_cast<int *>(p); }
+};
+
+namespace internal
+{
+/// The quadrature rule, tensor maps and q-data a PA integrator of the reference sets up.
+struct PASetup
+{
+   int ne = 0, d1d = 0, q1d = 0, nq = 0;
+   const mfem::IntegrationRule *ir = nullptr;
+   const mfem::DofToQuad *maps = nullptr;
+   void Init(const mfem::FiniteElementSpace &fes, const mfem::IntegrationRule *rule)
+   {
+      mfem::Mesh *mesh = fes.GetMesh();
+      MFEM_VERIFY(mesh->Dimension() == 3 && mesh->GetNumGeometries(3) == 1 &&
+                  mesh->GetElementBaseGeometry(0) == mfem::Geometry::CUBE,
+                  "b200pa: 3-D hexahedral meshes only");
+      MFEM_VERIFY(fes.GetVDim() == 1 && !fes.IsVariableOrder() && fes.Conforming(), "b200pa: scalar conforming H1 spaces only");
+      const mfem::FiniteElement &el = *fes.GetTypicalFE();
+      ir = rule;
+      maps = &el.GetDofToQuad(*ir, mfem::DofToQuad::TENSOR);
+      ne = fes.GetNE(); d1d = maps->ndof; q1d = maps->nqpt; nq = ir->GetNPoints();
+   }
+};
+} // namespace internal
+
+/// (Q grad u, grad v), scalar Q: mfem::DiffusionIntegrator with its PA virtuals on the GPU.
+class DiffusionIntegrator : public mfem::DiffusionIntegrator
+{
+   internal::PASetup s;
+   DeviceBuffer d_pa;
+   mutable DeviceBuffer d_x, d_y;
+public:
+   using mfem::DiffusionIntegrator::DiffusionIntegrator;
+
+   /// ≙ DiffusionIntegrator::AssemblePA, fem/integ/bilininteg_diffusion_pa.cpp:89-142
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      MFEM_VERIFY(!VQ && !MQ, "b200pa: scalar diffusion coefficients only");
+      const mfem::FiniteElement &el = *fes.GetTypicalFE();
+      s.Init(fes, IntRule ? IntRule : &GetRule(el, el));
+      mfem::Mesh *mesh = fes.GetMesh();
+      const mfem::GeometricFactors *geom = mesh->GetGeometricFactors(*s.ir, mfem::GeometricFactors::JACOBIANS);
+      mfem::QuadratureSpace qs(*mesh, *s.ir);
+      mfem::CoefficientVector coeff(qs, mfem::CoefficientStorage::COMPRESSED);
+      if (Q) { coeff.Project(*Q); } else { coeff.SetConstant(1.0); }
+      DeviceBuffer dW, dJ, dC;
+      dW.Upload(s.ir->GetWeights().HostRead(), sizeof(double) * s.nq);
+      dJ.Upload(geom->J.HostRead(), sizeof(double) * geom->J.Size());
+      dC.Upload(coeff.HostRead(), sizeof(double) * coeff.Size());
+      d_pa.Resize(sizeof(double) * 6 * (size_t)s.nq * s.ne);
+      Check(b200pa_diffusion_setup(Ctx(), s.q1d, s.ne, dW.D(), dJ.D(), dC.D(), coeff.Size(), d_pa.D()));
+      Check(b200pa_ctx_sync(Ctx()));
+   }
+
+   /// ≙ DiffusionIntegrator::AddMultPA, fem/integ/bilininteg_diffusion_pa.cpp:40-74 (y += A_E x)
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      const size_t b = sizeof(double) * x.Size();
+      d_x.Upload(x.HostRead(), b);
+      d_y.Upload(y.HostRead(), b);
+      Check(b200pa_diffusion_apply(Ctx(), s.ne, s.d1d, s.q1d, s.maps->B.HostRead(), s.maps->G.HostRead(), d_pa.D(), d_x.D(), d_y.D()));
+      d_y.Download(y.HostReadWrite(), b);
+   }
+   void AddMultTransposePA(const mfem::Vector &x, mfem::Vector &y) const override { AddMultPA(x, y); } // symmetric
+
+   /// ≙ DiffusionIntegrator::AssembleDiagonalPA, fem/integ/bilininteg_diffusion_pa.cpp:22-37
+   void AssembleDiagonalPA(mfem::Vector &diag) override
+   {
+      const size_t b = sizeof(double) * diag.Size();
+      d_y.Upload(diag.HostRead(), b);
+      Check(b200pa_diffusion_diag(Ctx(), s.ne, s.d1d, s.q1d, s.maps->B.HostRead(), s.maps->G.HostRead(), d_pa.D(), d_y.D()));
+      d_y.Download(diag.HostReadWrite(), b);
+   }
+   const double *DevicePAData() const { return d_pa.D(); }
+};
+
+/// (Q u, v): mfem::MassIntegrator with its PA virtuals on the GPU.
+class MassIntegrator : public mfem::MassIntegrator
+{
+   internal::PASetup s;
+   DeviceBuffer d_pa;
+   mutable DeviceBuffer d_x, d_y;
+public:
+   using mfem::MassIntegrator::MassIntegrator;
+
+   /// ≙ MassIntegrator::AssemblePA, fem/integ/bilininteg_mass_pa.cpp:24-79
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      const mfem::FiniteElement &el = *fes.GetTypicalFE();
+      mfem::Mesh *mesh = fes.GetMesh();
+      mfem::ElementTransformation *T0 = mesh->GetTypicalElementTransformation();
+      s.Init(fes, IntRule ? IntRule : &GetRule(el, el, *T0));
+      MFEM_VERIFY(el.GetMapType() == mfem::FiniteElement::VALUE, "b200pa: VALUE map type only");
+      const mfem::GeometricFactors *geom = mesh->GetGeometricFactors(*s.ir, mfem::GeometricFactors::DETERMINANTS);
+      mfem::QuadratureSpace qs(*mesh, *s.ir);
+      mfem::CoefficientVector coeff(Q, qs, mfem::CoefficientStorage::COMPRESSED);
+      DeviceBuffer dW, dD, dC;
+      dW.Upload(s.ir->GetWeights().HostRead(), sizeof(double) * s.nq);
+      dD.Upload(geom->detJ.HostRead(), sizeof(double) * geom->detJ.Size());
+      dC.Upload(coeff.HostRead(), sizeof(double) * coeff.Size());
+      d_pa.Resize(sizeof(double) * (size_t)s.nq * s.ne);
+      Check(b200pa_mass_setup(Ctx(), s.nq, s.ne, dW.D(), dD.D(), dC.D(), coeff.Size(), d_pa.D()));
+      Check(b200pa_ctx_sync(Ctx()));
+   }
+
+   /// ≙ MassIntegrator::AddMultPA, fem/integ/bilininteg_mass_pa.cpp:140-169
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      const size_t b = sizeof(double) * x.Size();
+      d_x.Upload(x.HostRead(), b);
+      d_y.Upload(y.HostRead(), b);
+      Check(b200pa_mass_apply(Ctx(), s.ne, s.d1d, s.q1d, s.maps->B.HostRead(), d_pa.D(), d_x.D(), d_y.D()));
+      d_y.Download(y.HostReadWrite(), b);
+   }
+   void AddMultTransposePA(const mfem::Vector &x, mfem::Vector &y) const override { AddMultPA(x, y); }
+
+   /// ≙ MassIntegrator::AssembleDiagonalPA, fem/integ/bilininteg_mass_pa.cpp:127-138
+   void AssembleDiagonalPA(mfem::Vector &diag) override
+   {
+      const size_t b = sizeof(double) * diag.Size();
+      d_y.Upload(diag.HostRead(), b);
+      Check(b200pa_mass_diag(Ctx(), s.ne, s.d1d, s.q1d, s.maps->B.HostRead(), d_pa.D(), d_y.D()));
+      d_y.Download(diag.HostReadWrite(), b);
+   }
+};
+
+/// The fused operator: PABilinearFormExtension::Mult + ConstrainedOperator for a form made of a
+/// DiffusionIntegrator and/or a MassIntegrator with scalar coefficients (either may be null).
+class PAOperator : public mfem::Operator
+{
+   const mfem::FiniteElementSpace &fes;
+   b200pa_space sp = nullptr;
+   b200pa_form form = nullptr;
+   mfem::Array<int> ess;
+   const mfem::IntegrationRule *ir = nullptr;
+   friend class PCGSolver;
+
+   void Project(mfem::Coefficient *c, std::vector<double> &out)
+   {
+      mfem::QuadratureSpace qs(*fes.GetMesh(), *ir);
+      mfem::CoefficientVector cv(c, qs, mfem::CoefficientStorage::COMPRESSED);
+      out.assign(cv.HostRead(), cv.HostRead() + cv.Size());
+   }
+public:
+   PAOperator(const mfem::FiniteElementSpace &fes_, mfem::Coefficient *kdiff, mfem::Coefficient *cmass,
+              const mfem::Array<int> &ess_tdof_list)
+      : mfem::Operator(fes_.GetVSize()), fes(fes_)
+   {
+      const mfem::FiniteElement &el = *fes.GetTypicalFE();
+      internal::PASetup s;
+      ir = &mfem::DiffusionIntegrator::GetRule(el, el);
+      s.Init(fes, ir);
+      // ElementRestriction tables (fem/restriction.cpp:26-107) and tensor maps (fem/fe/fe_base.cpp:2619-2662)
+      const mfem::ElementRestriction *R = dynamic_cast<const mfem::ElementRestriction *>(
+                                             fes.GetElementRestriction(mfem::ElementDofOrdering::LEXICOGRAPHIC));
+      MFEM_VERIFY(R, "b200pa: ElementRestriction expected");
+      Check(b200pa_space_create(Ctx(), s.d1d, s.q1d, s.ne, fes.GetNDofs(), R->GatherMap().HostRead(), s.maps->B.HostRead(),
+                                s.maps->G.HostRead(), &sp));
+      const mfem::GeometricFactors *geom = fes.GetMesh()->GetGeometricFactors(
+                                              *ir, mfem::GeometricFactors::JACOBIANS | mfem::GeometricFactors::DETERMINANTS);
+      Check(b200pa_space_set_geometry(sp, ir->GetWeights().HostRead(), geom->J.HostRead(), geom->detJ.HostRead()));
+      Check(b200pa_form_create(sp, &form));
+      std::vector<double> q;
+      if (kdiff) { Project(kdiff, q); Check(b200pa_form_assemble_diffusion(form, q.data(), (long long)q.size())); }
+      if (cmass) { Project(cmass, q); Check(b200pa_form_assemble_mass(form, q.data(), (long long)q.size())); }
+      ess_tdof_list.Copy(ess);
+      Check(b200pa_form_set_essential(form, ess.Size(), ess.HostRead()));
+   }
+   ~PAOperator() { b200pa_form_destroy(form); b200pa_space_destroy(sp); }
+
+   /// ≙ ConstrainedOperator::Mult (linalg/operator.cpp:710-714) of the PA form, host vectors
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      Check(b200pa_form_mult_host(form, 1, x.HostRead(), y.HostWrite()));
+   }
+   /// ≙ PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487-564): unconstrained A x
+   void MultUnconstrained(const mfem::Vector &x, mfem::Vector &y) const
+   {
+      Check(b200pa_form_mult_host(form, 0, x.HostRead(), y.HostWrite()));
+   }
+   /// ≙ PABilinearFormExtension::AssembleDiagonal (fem/bilinearform_ext.cpp:370-454)
+   void AssembleDiagonal(mfem::Vector &diag) const override
+   {
+      DeviceBuffer d;
+      d.Resize(sizeof(double) * height);
+      Check(b200pa_form_assemble_diagonal(form, d.D()));
+      d.Download(diag.HostWrite(), sizeof(double) * height);
+   }
+   /// ≙ ConstrainedOperator::EliminateRHS (linalg/operator.cpp:559-584)
+   void EliminateRHS(const mfem::Vector &x, mfem::Vector &b) const
+   {
+      DeviceBuffer dx, db;
+      dx.Upload(x.HostRead(), sizeof(double) * height);
+      db.Upload(b.HostRead(), sizeof(double) * height);
+      Check(b200pa_form_eliminate_rhs(form, dx.D(), db.D()));
+      db.Download(b.HostReadWrite(), sizeof(double) * height);
+   }
+   const mfem::Array<int> &GetEssentialTrueDofs() const { return ess; }
+};
+
+/// CGSolver + OperatorJacobiSmoother on the GPU (linalg/solvers.cpp:331-453, 869-1050); same
+/// setters / getters and the same meaning of iterative_mode, GetNumIterations, GetConverged,
+/// GetFinalNorm as mfem::CGSolver.
+class PCGSolver : public mfem::Solver
+{
+   const PAOperator *op = nullptr;
+   DeviceBuffer dinv;
+   double rel_tol = 0.0, abs_tol = 0.0, damping = 1.0;
+   int max_iter = 10, print_level = -1;
+   mutable b200pa_pcg_result res{};
+   mutable std::vector<double> norms;
+public:
+   PCGSolver() : mfem::Solver(0, true) {}
+   void SetRelTol(double t) { rel_tol = t; }
+   void SetAbsTol(double t) { abs_tol = t; }
+   void SetMaxIter(int n) { max_iter = n; }
+   void SetPrintLevel(int l) { print_level = l; }
+   /// SetOperator + SetPreconditioner(OperatorJacobiSmoother(a, ess, damping)) in one
+   void SetOperator(const mfem::Operator &o) override
+   {
+      op = dynamic_cast<const PAOperator *>(&o);
+      MFEM_VERIFY(op, "b200::PCGSolver works on a b200::PAOperator");
+      height = width = op->Height();
+      DeviceBuffer diag;
+      diag.Resize(sizeof(double) * height);
+      dinv.Resize(sizeof(double) * height);
+      Check(b200pa_form_assemble_diagonal(op->form, diag.D()));
+      DeviceBuffer dess;
+      dess.Upload(op->ess.HostRead(), sizeof(int) * std::max(op->ess.Size(), 1));
+      Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), op->ess.Size(), dess.I(), damping, dinv.D()));
+   }
+   void Mult(const mfem::Vector &b, mfem::Vector &x) const override
+   {
+      if (!iterative_mode) { x = 0.0; }
+      norms.assign(max_iter + 2, 0.0);
+      Check(b200pa_pcg_solve_host(op->form, dinv.D(), b.HostRead(), x.HostReadWrite(), rel_tol, abs_tol, max_iter, &res, norms.data()));
+      if (print_level >= 1)
+      {
+         for (int i = 0; i <= res.final_iter; i++)
+         {
+            mfem::out << "   Iteration : " << std::setw(3) << i << "  (B r, r) = " << norms[i] << '\n';
+         }
+      }
+   }
+   int GetNumIterations() const { return res.final_iter; }
+   bool GetConverged() const { return res.converged != 0; }
+   double GetFinalNorm() const { return res.final_norm; }
+   double GetInitialNorm() const { return res.initial_norm; }
+   const std::vector<double> &GetResidualHistory() const { return norms; }
+};
+
+} // namespace b200
+
+#endif

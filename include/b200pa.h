@@ -54,6 +54,11 @@ int b200pa_ctx_create(int device, void *stream, b200pa_ctx *out);
 int b200pa_ctx_destroy(b200pa_ctx ctx);
 int b200pa_ctx_sync(b200pa_ctx ctx);                       /* ≙ MFEM_STREAM_SYNC */
 void *b200pa_ctx_stream(b200pa_ctx ctx);
+/* device memory for callers that have no CUDA runtime of their own (a CPU build of the host
+ * library): ≙ Memory<T>::New with MemoryType::DEVICE (general/mem_manager.hpp) */
+int b200pa_malloc(b200pa_ctx ctx, size_t bytes, void **out_dev);
+int b200pa_free(b200pa_ctx ctx, void *dev);
+int b200pa_memset(b200pa_ctx ctx, void *dev, int value, size_t bytes);
 /* synchronous copies on the context's stream (≙ Vector::HostRead / Vector::Write of a device vector) */
 int b200pa_ctx_upload(b200pa_ctx ctx, void *dst_dev, const void *src_host, size_t bytes);
 int b200pa_ctx_download(b200pa_ctx ctx, void *dst_host, const void *src_dev, size_t bytes);

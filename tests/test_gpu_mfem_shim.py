@@ -1,0 +1,44 @@
+"""GPU: the UNMODIFIED reference (stock MFEM, CPU build) driving the B200 through the drop-in binding
+cardiac-ablation-ecm2_b200/host/mfem_b200pa.hpp, compared in-process with the reference's own CPU
+partial-assembly path (oracle/shim_check.cpp -> oracle/_ref/shim_check, built in the build container
+by `make -C oracle ref`; it travels to the GPU box with the snapshot)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref", "shim_check")
+
+
+def run(args, timeout=900):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/shim_check not built (needs the reference tree: make -C oracle ref)")
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    out = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout, env=env)
+    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return recs
+
+
+@pytest.mark.parametrize("p,dims", [(1, (5, 4, 3)), (2, (6, 5, 4)), (3, (4, 3, 3)), (4, (3, 3, 2)), (5, (2, 3, 2)), (6, (2, 2, 2))])
+def test_mfem_drop_in(p, dims):
+    recs = run(["apply", p, *dims])
+    assert len(recs) == 2
+    for r in recs:
+        assert r["ok"]
+        assert max(r["integrator_level"].values()) <= 1e-12
+        f = r["fused"]
+        assert max(f["apply"], f["diag"], f["constrained"], f["rhs"]) <= 1e-12 and f["pcg10"] <= 1e-10
+        assert abs(f["iters_ref"] - f["iters_gpu"]) <= 1
+
+
+def test_ex1_config0():
+    """BASELINE configs[0]: ex1 -pa -o 3, inline-hex with 3 refinements (912,673 dofs): the reference
+    needs 197 Jacobi-PCG iterations; the drop-in must agree within +-1."""
+    r = run(["ex1", 3, 3, "omp"][:3])[0]
+    assert r["ok"] and r["ndofs"] == 912673
+    assert abs(r["iters_ref"] - 197) <= 1 and abs(r["iters_gpu"] - r["iters_ref"]) <= 1
