@@ -288,7 +288,8 @@ public:
       dinv.Resize(sizeof(double) * height);
       Check(b200pa_form_assemble_diagonal(op->form, diag.D()));
       DeviceBuffer dess;
-      dess.Upload(op->ess.HostRead(), sizeof(int) * std::max(op->ess.Size(), 1));
+      dess.Resize(sizeof(int) * std::max(op->ess.Size(), 1));
+      if (op->ess.Size()) { dess.Upload(op->ess.HostRead(), sizeof(int) * op->ess.Size()); }
       Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), op->ess.Size(), dess.I(), damping, dinv.D()));
    }
    void Mult(const mfem::Vector &b, mfem::Vector &x) const override
