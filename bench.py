@@ -90,6 +90,15 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(p, n, ops):
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu capture of this workload"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[f"p{p}_n{n}_{ops}"]["pa_apply_kernel"]
+    except Exception:
+        return None
+
+
 def ref_driver_path():
     p = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     return p if os.path.exists(p) else None
@@ -297,7 +306,8 @@ def main():
                 "api": "b200pa_form_mult_host (pinned host x -> H2D -> apply -> D2H -> pinned host y)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "pa_element_kernel (gather + diffusion + mass + slot scatter)",
+                     "traffic": measured_traffic(p, n, args.ops), "algorithmic_bytes": bytes_elem * nd,
+                     "kernel": "pa_apply_kernel (gather + diffusion + mass + slot-order write)",
                      "bytes_per_dof": bytes_elem, "ms_per_launch": ms_elem / K, "peak_source": peak_src},
         "roofline_apply": {"achieved": bytes_total * nd / (ms_total / K * 1e-3) / 1e9, "frac": bytes_total * nd / (ms_total / K * 1e-3) / 1e9 / peak,
                            "bytes_per_dof": bytes_total, "ms_element_kernel": ms_elem / K, "ms_segment_sum": ms_seg / K},
