@@ -6,10 +6,12 @@
 // Second design, driven by the first ncu capture (profiles/r1a_*): the slab/column kernel moved the
 // right bytes (DRAM traffic = algorithmic bytes) but kept only ~21 KB per SM in flight - HBM latency
 // bound at 39 % of peak with 25 % occupancy.  Changes:
-//   * small batches (NEB elements, NEB*Q^2 = one q-point column per thread) so that every thread's
-//     q-data (7Q doubles) is one register-resident prefetch: the loads for batch b+1 are issued right
-//     after batch b's columns are done and fly during the whole of phases C/out/in/A
-//     (>= 4 CTAs/SM x 128 threads x 224 B = 114 KB per SM in flight, Little's law needs ~45 KB);
+//   * small batches (NEB elements, NEB*Q^2 = one q-point column per thread) whose q-data is ONE
+//     contiguous range of each q-data array, fetched one batch ahead: thread 0 issues two TMA bulk
+//     copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) right after batch b's columns are
+//     done, and the copy flies during the whole of phases C/out/in/A of the next batch
+//     (3-4 CTAs/SM x 29-36 KB = 100-140 KB per SM in flight, Little's law needs ~45 KB); no register
+//     is tied up by the prefetch (the register-resident variant, QPF && !TMA, spilled for p >= 3);
 //   * the gather is prefetched the same way (indices one batch ahead, x values half a batch ahead);
 //   * fine-grained tasks - (slab,qy) rows instead of whole slabs - so the small batch still fills
 //     the CTA in the x/y contractions, and all B/G operands except one row per task stay
@@ -40,10 +42,13 @@ struct ApplyCfg
    static constexpr int NEB = B200PA_TUNE_NEB;
    static constexpr int MINB = B200PA_TUNE_MINB;
    static constexpr bool QPF = B200PA_TUNE_QPF;
+   static constexpr bool TMA = B200PA_TUNE_TMA;
 #else
-   static constexpr int NEB = (D == 2) ? 14 : (D == 3) ? 8 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
-   static constexpr int MINB = (D <= 4) ? 4 : (D == 5 ? 3 : 2); // resident CTAs per SM the register budget is tuned for
-   static constexpr bool QPF = true;                             // q-data prefetched one batch ahead (registers)
+   // tuned on B200 with tools/tune.sh + tools/tune_run.sh (profiles/r1c_tuning.txt)
+   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 8 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
+   static constexpr int MINB = (D == 2) ? 3 : (D == 3) ? 4 : (D <= 6) ? 3 : 2; // resident CTAs/SM the register budget allows
+   static constexpr bool QPF = true;  // q-data of batch b+1 is fetched while batch b is still being contracted ...
+   static constexpr bool TMA = true;  // ... by TMA bulk copies into shared memory (false: into registers, 7Q doubles/thread)
 #endif
    static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int NIO = (NEB * D3 + NT - 1) / NT;          // gather / scatter items per thread
@@ -53,8 +58,41 @@ struct ApplyCfg
    static constexpr int ES = (D == 3) ? 185 : (3 * D * SQ + ((3 * D * SQ) % 2 == 0 ? 1 : 0));
    static constexpr int SX_DOUBLES = NEB * D * SXS;
    static constexpr int SE_DOUBLES = NEB * ES;
-   static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * D);
+   // TMA mode: one batch of q-data staged in shared memory, global layout kept ([e][6][Q^3] and [e][Q^3]);
+   // +2 doubles of slack each for the 16-byte alignment of the bulk copies
+   static constexpr int SQD_DOUBLES = TMA ? (NEB * 6 * Q3 + 2) : 0;
+   static constexpr int SQM_DOUBLES = TMA ? (((NEB * Q3 + 2) + 1) & ~1) : 0;
+   static constexpr int WORK_DOUBLES = ((2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * D) + 1) & ~1;
+   static constexpr size_t SMEM_BYTES = sizeof(double) * (WORK_DOUBLES + SQD_DOUBLES + SQM_DOUBLES);
 };
+
+// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
 
 template <int D, int Q, bool DIFF, bool MASS>
 __global__ void __launch_bounds__(ApplyCfg<D, Q>::NT, ApplyCfg<D, Q>::MINB)
@@ -71,6 +109,9 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    double *sE = sXout + C::SX_DOUBLES;
    double *sBt = sE + C::SE_DOUBLES; // sBt[qy*D + dy] = B(qy,dy): the one runtime-indexed row of phase A
    double *sGt = sBt + Q * D;
+   double *sQd = smem + C::WORK_DOUBLES;      // TMA mode: this batch's diffusion q-data (16-byte aligned)
+   double *sQm = sQd + C::SQD_DOUBLES;        //           and mass q-data
+   __shared__ unsigned long long qbar;        // TMA mode: "q-data of the current batch has landed"
    const int tid = threadIdx.x;
    if (P.done && *P.done) { return; }
    const int nbatch = (P.NE + NEB - 1) / NEB;
@@ -122,11 +163,50 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       for (int r = 0; r < NIO; ++r) { xg[r] = gi[r] >= 0 ? P.x[gi[r]] : 0.0; }
    };
 
+   // TMA mode: two bulk copies per batch (the batch's elements are contiguous in both q-data arrays).
+   // The mass array's element stride (Q^3 doubles) is odd for odd Q, so its copy starts at the
+   // 16-byte boundary below the batch and `mshift` (0 or 1 doubles) finds the data again.
+   int mshift = 0;
+   auto tma_issue = [&](int b)
+   {
+      const long long e0 = (long long)b * NEB;
+      const int nel = (int)(P.NE - e0 < NEB ? P.NE - e0 : NEB);
+      unsigned bytes_d = 0, bytes_m = 0;
+      const double *src_m = nullptr;
+      if (DIFF) { bytes_d = (unsigned)(nel * 6 * Q3 * sizeof(double)); }
+      if (MASS)
+      {
+         const double *src = P.pa_mass + e0 * Q3;
+         const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
+         src_m = src - sh;
+         int nd = sh + nel * Q3;
+         if (nd & 1)
+         {
+            // 16-byte granularity: take one double more, except at the very end of the array, where the
+            // last double is fetched with a plain load instead (never read past the caller's buffer)
+            if (e0 + nel < P.NE) { nd += 1; }
+            else { nd -= 1; sQm[nd] = __ldg(src_m + nd); }
+         }
+         bytes_m = (unsigned)(nd * sizeof(double));
+      }
+      mbar_expect_tx(&qbar, bytes_d + bytes_m);
+      if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
+      if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
+   };
+   auto mass_shift = [&](int b) { return (int)(((unsigned long long)(P.pa_mass + (long long)b * NEB * Q3) >> 3) & 1ull); };
+   unsigned qphase = 0;
+   if (C::TMA)
+   {
+      if (tid == 0) { mbar_init(&qbar, 1); }
+      __syncthreads();
+   }
+
    int batch = blockIdx.x;
    if (batch < nbatch)
    {
       load_gidx(batch);
-      if (C::QPF) { load_qdata(batch); }
+      if (C::TMA) { if (tid == 0) { tma_issue(batch); } }
+      else if (C::QPF) { load_qdata(batch); }
       load_x();
    }
    for (; batch < nbatch; batch += gridDim.x)
@@ -201,7 +281,15 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // -------------------------------- phase B: column, q-point op, column^T
-      if (!C::QPF) { load_qdata(batch); }
+      if (!C::QPF && !C::TMA) { load_qdata(batch); }
+      if (C::TMA)
+      {
+         mbar_wait(&qbar, qphase);
+         qphase ^= 1u;
+         if (MASS) { mshift = mass_shift(batch); }
+      }
+      const double *qd = sQd + (eB * 6) * Q3 + cB;         // TMA mode: this thread's column in the staged q-data
+      const double *qm = sQm + mshift + eB * Q3 + cB;
       if (actB)
       {
          double *s = sE + eB * ES + cB;
@@ -231,11 +319,18 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             double hX = 0.0, hY = 0.0, hZ = 0.0, hM = 0.0;
             if (DIFF)
             {
-               hX = O[qz][0] * gX + O[qz][1] * gY + O[qz][2] * gZ;
-               hY = O[qz][1] * gX + O[qz][3] * gY + O[qz][4] * gZ;
-               hZ = O[qz][2] * gX + O[qz][4] * gY + O[qz][5] * gZ;
+               double o0, o1, o2, o3, o4, o5;
+               if (C::TMA)
+               {
+                  const double *d = qd + qz * Q2;
+                  o0 = d[0]; o1 = d[Q3]; o2 = d[2 * Q3]; o3 = d[3 * Q3]; o4 = d[4 * Q3]; o5 = d[5 * Q3];
+               }
+               else { o0 = O[qz][0]; o1 = O[qz][1]; o2 = O[qz][2]; o3 = O[qz][3]; o4 = O[qz][4]; o5 = O[qz][5]; }
+               hX = o0 * gX + o1 * gY + o2 * gZ;
+               hY = o1 * gX + o3 * gY + o4 * gZ;
+               hZ = o2 * gX + o4 * gY + o5 * gZ;
             }
-            if (MASS) { hM = Mq[qz] * val; }
+            if (MASS) { hM = (C::TMA ? qm[qz * Q2] : Mq[qz]) * val; }
             B200PA_UNROLL
             for (int dz = 0; dz < D; ++dz)
             {
@@ -258,10 +353,13 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // prefetch for the next batch: q-data column and gathered x (indices arrived during phase A)
       if (next < nbatch)
       {
-         if (C::QPF) { load_qdata(next); }
+         if (C::QPF && !C::TMA) { load_qdata(next); }
          load_x();
       }
       __syncthreads();
+      // every thread is done reading the staged q-data: refill the buffer with the next batch; the copy
+      // flies during phases C1/C2, stage-out, stage-in and phase A of the next batch
+      if (C::TMA && next < nbatch && tid == 0) { tma_issue(next); }
 
       // ----------------------------------------------- phase C1: (slab, qy) rows, x^T
       for (int task = tid; task < NEB * D * Q; task += NT)
