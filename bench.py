@@ -122,6 +122,23 @@ def run_reference_cpu(p, n, reps, warm):
     raise RuntimeError("ref_driver failed: " + out.stderr[-400:])
 
 
+def run_reference_bioheat(p, n, iters):
+    """the reference's own composition of the coupled RF + bioheat step (oracle/ref_driver.cpp `bioheat`)"""
+    drv = ref_driver_path()
+    if drv is None:
+        return None
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close")
+    out = subprocess.run([drv, "time_bioheat", str(p), str(n), str(iters), "omp"], env=env, capture_output=True, text=True,
+                         timeout=1500)
+    for line in out.stdout.splitlines():
+        if line.startswith("{"):
+            r = json.loads(line)
+            r["cores"] = cores
+            return r
+    raise RuntimeError("ref_driver time_bioheat failed: " + out.stderr[-400:])
+
+
 def oracle_port_cpu(p, n):
     """fallback CPU baseline when oracle/_ref did not travel: the C restatement on a bounded sample"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -343,6 +360,20 @@ def main():
         line["bioheat_step"] = {"ms": ms_step, "pcg_iters": res[0].final_iter, "converged": bool(res[0].converged),
                                 "what": "k(T) q-data + PA setup + Jacobi diagonal + PCG to rel 1e-8"}
 
+        # the whole RF-ablation coupled step (electrostatics + Joule + bioheat), fixed 20 + 20 PCG iterations
+        from b200pa.bioheat import CoupledStep
+        cs = CoupledStep(ctx, sp, m, GN, comm=comm)
+        cs.step(T0, 2, 2)
+        out = [None]
+        ms_rf = timed(lambda: out.__setitem__(0, cs.step(T0, 20, 20)), 1)
+        o = out[0]
+        line["rf_step"] = {"ms": ms_rf, "pcg_iters": [20, 20], "what": "sigma(T),k(T) q-data + 2 PA set-ups + 2 Jacobi diagonals + "
+                           "EliminateRHS + 20 PCG its (phi) + Joule q-data + RHS + 20 PCG its (T)"}
+        if world == 1:
+            line["rf_step"].update(phi_norm=float(np.sqrt(ctx.dot(o["phi"], o["phi"]))), T1_norm=float(np.sqrt(ctx.dot(o["T1"], o["T1"]))),
+                                   src_sum=float(o["src"].sum().item()))
+        cs.close()
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on the host cores
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -355,6 +386,15 @@ def main():
                 # full-size parity: same mesh, same numbering, same x = Randomize(1), same operator
                 line["parity_vs_reference_cpu"] = {"ref_y_norm": r["y_norm"], "gpu_y_norm": float(np.sqrt(ynorm2)),
                                                    "rel_diff": abs(np.sqrt(ynorm2) - r["y_norm"]) / r["y_norm"]}
+                if "rf_step" in line and args.ops == "both":
+                    rb = run_reference_bioheat(p, n, 20)
+                    t_ref = sum(rb[k] for k in ("t_coef", "t_asm_e", "t_cg_e", "t_joule", "t_asm_t", "t_rhs", "t_cg_t"))
+                    g = line["rf_step"]
+                    line["rf_step"]["reference_cpu"] = {
+                        "ms": t_ref * 1e3, "cores": rb["cores"], "phi_norm": rb["phi_norm"], "T1_norm": rb["T1_norm"], "src_sum": rb["src_sum"],
+                        "rel_diff": {"phi_norm": abs(g["phi_norm"] - rb["phi_norm"]) / rb["phi_norm"],
+                                     "T1_norm": abs(g["T1_norm"] - rb["T1_norm"]) / rb["T1_norm"],
+                                     "src_sum": abs(g["src_sum"] - rb["src_sum"]) / abs(rb["src_sum"])}}
             else:
                 r = oracle_port_cpu(p, min(n, 40))
                 line["cpu_baseline"] = {"value": r["ndofs"] / r["t_apply_mean"] / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",

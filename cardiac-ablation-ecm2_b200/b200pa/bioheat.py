@@ -1,0 +1,70 @@
+"""The RF-ablation coupled step of SURVEY.md §3.2/§3.3 composed from the C-ABI entry points
+(host-side driver; the reference composes the same step from its PA API, see oracle/ref_driver.cpp
+`bioheat` which is what tests and bench compare against).
+
+  (1) electrostatics  div sigma(T) grad phi = 0, phi = V on z=0, 0 on z=1      -> PCG + Jacobi
+  (2) Joule source    q = sigma |grad phi|^2 + w_b rho_b c_b T_a               -> q-point kernel
+  (3) bioheat         (rho c/dt + w_b rho_b c_b) M T1 + K(k(T0)) T1 = (rho c/dt) M T0 + b(q)   -> PCG + Jacobi
+"""
+import numpy as np
+
+from . import Form, essential_dofs
+
+PHYS = dict(dt=0.5, rc=3.6e6, wbcb=4.0e4, Ta=37.0, k0=0.5, ak=0.02, s0=0.3, as_=0.015, V=30.0)
+
+
+def initial_temperature(lattice, gll, p, GN):
+    """GridFunction::ProjectCoefficient of 37 + 20 exp(-40 r^2): nodal values at the GLL points"""
+    lat = lattice.reshape(-1, 3)
+    xyz = (lat // p + gll[lat % p]) / np.asarray(GN, dtype=np.float64)
+    return 37.0 + 20.0 * np.exp(-40.0 * ((xyz - 0.5) ** 2).sum(1))
+
+
+class CoupledStep:
+    """Keeps the three forms and the q-data buffers alive across time steps (device resident)."""
+
+    def __init__(self, ctx, sp, mesh, GN, P=PHYS, comm=None):
+        self.ctx, self.sp, self.m, self.P, self.comm = ctx, sp, mesh, P, comm
+        nq = sp.ne * sp.nq
+        self.nq = nq
+        self.kq, self.sq, self.src = ctx.empty(nq), ctx.empty(nq), ctx.empty(nq)
+        self.mq = ctx.coeff_eval(1, nq, P["rc"] / P["dt"] + P["wbcb"], 0.0, 0.0)
+        self.ess = essential_dofs(mesh["bdr_attr"], [1, 6])
+        lat = mesh["lattice"].reshape(-1, 3)
+        self.phi_bc = np.zeros(mesh["ndofs"])
+        self.phi_bc[self.ess] = P["V"] * (1.0 - lat[self.ess, 2] / (mesh["p"] * GN[2]))
+        self.fe, self.ft, self.fm = Form(sp), Form(sp), Form(sp)
+        self.fe.set_essential(self.ess)
+        self.ft.set_essential(None)
+        self.fm.assemble_mass(np.array([P["rc"] / P["dt"]]))
+        self.fm.set_essential(None)
+        for f in (self.fe, self.ft, self.fm):
+            if comm is not None:
+                f.set_comm(comm)
+
+    def step(self, T0, iters_e, iters_t, rel_tol=0.0):
+        ctx, sp, P = self.ctx, self.sp, self.P
+        sp.coeff_linear(P["k0"], P["ak"], 37.0, T0, out=self.kq)
+        sp.coeff_linear(P["s0"], P["as_"], 37.0, T0, out=self.sq)
+        # (1)
+        self.fe.assemble_diffusion(self.sq)
+        phi = ctx.to_dev(self.phi_bc)
+        Be = ctx.zeros(self.m["ndofs"])
+        self.fe.eliminate_rhs(phi, Be)
+        res_e, _ = self.fe.pcg(self.fe.jacobi(), Be, phi, rel_tol, 0.0, iters_e, want_norms=False)
+        # (2)
+        sp.joule(phi, self.sq, P["wbcb"] * P["Ta"], out=self.src)
+        # (3)
+        self.ft.assemble_diffusion(self.kq)
+        self.ft.assemble_mass(self.mq)
+        rhs = sp.domain_lf(self.src)
+        if self.comm is not None:
+            self.comm.exchange_sum(rhs)
+        rhs = ctx.add(rhs, 1.0, self.fm.mult(T0))
+        T1 = T0.clone()
+        res_t, _ = self.ft.pcg(self.ft.jacobi(), rhs, T1, rel_tol, 0.0, iters_t, want_norms=False)
+        return dict(phi=phi, Be=Be, src=self.src, rhs=rhs, T1=T1, res_e=res_e, res_t=res_t)
+
+    def close(self):
+        for f in (self.fe, self.ft, self.fm):
+            f.close()

@@ -95,7 +95,12 @@ template <int D1, int Q1>
 static void launch_diag(b200pa_ctx ctx, long long ne, const double *B, const double *G, const double *pd,
                         const double *pm, double *dE)
 {
-   k_diag<D1, Q1><<<grid1d(ctx, ne * D1 * D1 * D1, 128), 128, 0, ctx->stream>>>(ne, B, G, pd, pm, dE);
+   // elements per CTA so that the two staging tensors stay under the 48 KB static shared-memory limit
+   constexpr int PER_E = 7 * (Q1 * Q1 * D1 + Q1 * D1 * D1) * 8;
+   constexpr int NEB = (40 * 1024 / PER_E) < 1 ? 1 : ((40 * 1024 / PER_E) > 8 ? 8 : (40 * 1024 / PER_E));
+   const long long nbatch = (ne + NEB - 1) / NEB;
+   const long long cap = (long long)ctx->num_sms * 8;
+   k_diag_sf<D1, Q1, NEB><<<(int)(nbatch < cap ? nbatch : cap), 128, 0, ctx->stream>>>(ne, B, G, pd, pm, dE);
 }
 
 static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *Bdev, const double *Gdev,

@@ -277,6 +277,103 @@ __global__ void k_diag(long long NE, const double *__restrict__ Bg, const double
    }
 }
 
+// Sum-factorised diagonal (what the reference's SmemPADiffusionDiagonal3D / SmemPAMassAssembleDiagonal3D
+// do, fem/integ/bilininteg_diffusion_kernels.hpp:369-484, bilininteg_mass_kernels.hpp:324-408):
+//   dE[dx,dy,dz] += sum_f w_f sum_q D_f(q) Mx_f(qx,dx) My_f(qy,dy) Mz_f(qz,dz)
+// with the seven fields f = D00, D01, D02, D11, D12, D22, mass; per direction the 1-D factor is
+// GG, BG or BB (G in the directions i and j of D_ij, B elsewhere); w = 2 for the off-diagonal D_ij.
+// Three contraction passes through shared memory instead of a Q^3 loop per E-entry (14x fewer FMAs at p=2).
+template <int D1, int Q1, int NEB>
+__global__ void __launch_bounds__(128)
+k_diag_sf(long long NE, const double *__restrict__ Bg, const double *__restrict__ Gg, const double *__restrict__ pa_diff,
+          const double *__restrict__ pa_mass, double *__restrict__ dE)
+{
+   constexpr int D3 = D1 * D1 * D1, Q2 = Q1 * Q1, Q3 = Q1 * Q1 * Q1, NF = 7;
+   constexpr int T1E = NF * Q2 * D1, T2E = NF * Q1 * D1 * D1;
+   __shared__ double sM[3][Q1 * D1]; // 0: BB, 1: BG, 2: GG
+   __shared__ double sT1[NEB * T1E];
+   __shared__ double sT2[NEB * T2E];
+   for (int i = threadIdx.x; i < Q1 * D1; i += blockDim.x)
+   {
+      const double b = Bg[i], g = Gg[i];
+      sM[0][i] = b * b; sM[1][i] = b * g; sM[2][i] = g * g;
+   }
+   __syncthreads();
+   // factor type of field f in direction a: number of indices of D_ij equal to a
+   auto mtype = [](int f, int a) -> int
+   {
+      const int fi[7] = {0, 0, 0, 1, 1, 2, -1}, fj[7] = {0, 1, 2, 1, 2, 2, -1};
+      return (fi[f] == a) + (fj[f] == a);
+   };
+   const long long nbatch = (NE + NEB - 1) / NEB;
+   for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x)
+   {
+      const long long e0 = batch * NEB;
+      const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
+      // pass 1: contract qx.  task = (e, f, qz, qy): one contiguous row of Q1 q-data values
+      for (int t = threadIdx.x; t < nel * NF * Q2; t += blockDim.x)
+      {
+         const int e = t / (NF * Q2), r = t - e * NF * Q2, f = r / Q2, row = r - f * Q2;
+         const double *src = f < 6 ? (pa_diff ? pa_diff + ((e0 + e) * 6 + f) * Q3 + row * Q1 : nullptr)
+                                   : (pa_mass ? pa_mass + (e0 + e) * Q3 + row * Q1 : nullptr);
+         const double *M = sM[mtype(f, 0)];
+         double out[D1];
+#pragma unroll
+         for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
+         if (src)
+         {
+#pragma unroll
+            for (int q = 0; q < Q1; ++q)
+            {
+               const double v = src[q];
+#pragma unroll
+               for (int d = 0; d < D1; ++d) { out[d] = fma(M[q + Q1 * d], v, out[d]); }
+            }
+         }
+#pragma unroll
+         for (int d = 0; d < D1; ++d) { sT1[e * T1E + (f * Q2 + row) * D1 + d] = out[d]; }
+      }
+      __syncthreads();
+      // pass 2: contract qy.  task = (e, f, qz, dx)
+      for (int t = threadIdx.x; t < nel * NF * Q1 * D1; t += blockDim.x)
+      {
+         const int e = t / (NF * Q1 * D1), r = t - e * NF * Q1 * D1, f = r / (Q1 * D1), r2 = r - f * Q1 * D1, qz = r2 / D1, dx = r2 - qz * D1;
+         const double *M = sM[mtype(f, 1)];
+         double out[D1];
+#pragma unroll
+         for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
+#pragma unroll
+         for (int qy = 0; qy < Q1; ++qy)
+         {
+            const double v = sT1[e * T1E + (f * Q2 + qz * Q1 + qy) * D1 + dx];
+#pragma unroll
+            for (int d = 0; d < D1; ++d) { out[d] = fma(M[qy + Q1 * d], v, out[d]); }
+         }
+#pragma unroll
+         for (int dy = 0; dy < D1; ++dy) { sT2[e * T2E + ((f * Q1 + qz) * D1 + dy) * D1 + dx] = out[dy]; }
+      }
+      __syncthreads();
+      // pass 3: contract qz and sum the fields.  task = (e, dz, dy, dx)
+      for (int t = threadIdx.x; t < nel * D3; t += blockDim.x)
+      {
+         const int e = t / D3, l = t - e * D3, dz = l / (D1 * D1), k = l - dz * D1 * D1;
+         double acc = 0.0;
+#pragma unroll
+         for (int f = 0; f < NF; ++f)
+         {
+            const double w = (f == 1 || f == 2 || f == 4) ? 2.0 : 1.0;
+            const double *M = sM[mtype(f, 2)];
+            double a = 0.0;
+#pragma unroll
+            for (int qz = 0; qz < Q1; ++qz) { a = fma(M[qz + Q1 * dz], sT2[e * T2E + (f * Q1 + qz) * D1 * D1 + k], a); }
+            acc = fma(w, a, acc);
+         }
+         dE[(e0 + e) * D3 + l] += acc;
+      }
+      __syncthreads();
+   }
+}
+
 // ------------------------------------------------------------------ BLAS-1 etc.
 __global__ void k_add(long long n, const double *__restrict__ v1, double alpha, const double *__restrict__ v2,
                       double *__restrict__ v)

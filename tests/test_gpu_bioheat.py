@@ -33,40 +33,14 @@ def build(ctx, p, n):
 
 
 def coupled_step(ctx, m, b, sp, T0, iters, rel_tol=0.0):
-    nq = sp.ne * sp.nq
-    kq = sp.coeff_linear(P["k0"], P["ak"], 37.0, T0)
-    sq = sp.coeff_linear(P["s0"], P["as_"], 37.0, T0)
-    mq = ctx.coeff_eval(1, nq, P["rc"] / P["dt"] + P["wbcb"], 0.0, 0.0)
-    # (1) electrostatics: div sigma(T) grad phi = 0, phi = V on z=0, 0 on z=1
-    ess = b200pa.essential_dofs(m["bdr_attr"], [1, 6])
-    lat = m["lattice"].reshape(-1, 3)
-    phi0 = np.zeros(m["ndofs"])
-    zc = lat[ess, 2] / (m["p"] * round(m["ne"] ** (1 / 3)))
-    phi0[ess] = P["V"] * (1.0 - zc)
-    fe = b200pa.Form(sp)
-    fe.assemble_diffusion(sq)
-    fe.set_essential(ess)
-    phi = ctx.to_dev(phi0)
-    Be = ctx.zeros(m["ndofs"])
-    fe.eliminate_rhs(phi, Be)
-    res_e, _ = fe.pcg(fe.jacobi(), Be, phi, rel_tol, 0.0, iters)
-    # (2) Joule source
-    src = sp.joule(phi, sq, P["wbcb"] * P["Ta"])
-    # (3) bioheat backward Euler
-    ft = b200pa.Form(sp)
-    ft.assemble_diffusion(kq)
-    ft.assemble_mass(mq)
-    ft.set_essential(None)
-    fm = b200pa.Form(sp)
-    fm.assemble_mass(np.array([P["rc"] / P["dt"]]))
-    rhs = sp.domain_lf(src)
-    rhs = ctx.add(rhs, 1.0, fm.mult(T0))
-    T1 = T0.clone()
-    res_t, _ = ft.pcg(ft.jacobi(), rhs, T1, rel_tol, 0.0, iters)
-    out = dict(kq=kq, sq=sq, mq=mq, ess=ess, phi0=phi0, Be=Be, phi=phi, src=src, rhs=rhs, T1=T1, res_e=res_e, res_t=res_t,
-               fe=fe, ft=ft)
-    fm.close()
-    return out
+    """the product-side driver (b200pa/bioheat.py), plus the intermediate q-data the test inspects"""
+    from b200pa.bioheat import CoupledStep
+    n = round(m["ne"] ** (1 / 3))
+    cs = CoupledStep(ctx, sp, m, (n, n, n))
+    o = cs.step(T0, iters, iters, rel_tol)
+    o.update(kq=cs.kq, sq=cs.sq, mq=cs.mq, ess=cs.ess, phi0=cs.phi_bc, fe=cs.fe, ft=cs.ft)
+    cs.fm.close()
+    return o
 
 
 def test_coupled_step_matches_reference(ctx):
