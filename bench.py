@@ -192,7 +192,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", type=int, default=2)
-    ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU")
+    ap.add_argument("--elems", "--n", dest="n", type=int, default=100, help="elements per direction per GPU")
     ap.add_argument("--ops", default="both", choices=["both", "diff"], help="diffusion+mass (headline) or diffusion only (configs[3] sweep)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip PCG / implicit-step extras (profiling runs)")

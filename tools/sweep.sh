@@ -4,6 +4,6 @@
 for ops in both diff; do
   for pn in "1 200" "2 100" "3 67" "4 50" "5 40" "6 34" "2 200" "3 134" "1 100" "2 50"; do
     set -- $pn
-    timeout 600 python bench.py --order $1 --n $2 --ops $ops --steps 20 --warmup 3 --no-cpu --no-extras 2>/dev/null
+    timeout 600 python bench.py --order $1 --elems $2 --ops $ops --steps 20 --warmup 3 --no-cpu --no-extras 2>/dev/null
   done
 done
