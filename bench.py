@@ -201,6 +201,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner ("NCCL version ...", printed to stdout
+    # when NCCL_DEBUG=VERSION/INFO is set in the environment) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist
