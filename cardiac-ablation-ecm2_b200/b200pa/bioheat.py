@@ -1,6 +1,6 @@
 """The RF-ablation coupled step of SURVEY.md §3.2/§3.3 composed from the C-ABI entry points
-(host-side driver; the reference composes the same step from its PA API, see oracle/ref_driver.cpp
-`bioheat` which is what tests and bench compare against).
+(host-side driver; the reference composes the same step from its own PA API - the tests and the bench
+compare against that composition run by the unmodified reference).
 
   (1) electrostatics  div sigma(T) grad phi = 0, phi = V on z=0, 0 on z=1      -> PCG + Jacobi
   (2) Joule source    q = sigma |grad phi|^2 + w_b rho_b c_b T_a               -> q-point kernel

@@ -92,30 +92,42 @@ static int run_element(b200pa_ctx ctx, int d1d, int q1d, int variant, const Elem
 }
 
 template <int D1, int Q1>
-static void launch_diag(b200pa_ctx ctx, long long ne, const double *B, const double *G, const double *pd,
-                        const double *pm, double *dE)
+static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const double *pd, const double *pm,
+                        double *dE)
 {
-   // elements per CTA so that the two staging tensors stay under the 48 KB static shared-memory limit
-   constexpr int PER_E = 7 * (Q1 * Q1 * D1 + Q1 * D1 * D1) * 8;
-   constexpr int NEB = (40 * 1024 / PER_E) < 1 ? 1 : ((40 * 1024 / PER_E) > 8 ? 8 : (40 * 1024 / PER_E));
+   // elements per CTA: q-data staging + the two contraction tensors within ~72 KB (3 CTAs per SM)
+   constexpr int PER_E = (7 * Q1 * Q1 * Q1 + 7 * (Q1 * Q1 * D1 + Q1 * D1 * D1)) * 8;
+   constexpr int NEB = (72 * 1024 / PER_E) < 1 ? 1 : ((72 * 1024 / PER_E) > 8 ? 8 : (72 * 1024 / PER_E));
+   using C = DiagSfCfg<D1, Q1, NEB>;
+   auto kern = k_diag_sf<D1, Q1, NEB>;
+   static bool attr_set = false;
+   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES); attr_set = true; }
+   DiagParams<D1, Q1> P;
+   for (int i = 0; i < Q1 * D1; ++i)
+   {
+      P.M[0][i] = hB[i] * hB[i]; P.M[1][i] = hB[i] * hG[i]; P.M[2][i] = hG[i] * hG[i];
+   }
+   P.NE = ne; P.pa_diff = pd; P.pa_mass = pm; P.dE = dE;
    const long long nbatch = (ne + NEB - 1) / NEB;
-   const long long cap = (long long)ctx->num_sms * 8;
-   k_diag_sf<D1, Q1, NEB><<<(int)(nbatch < cap ? nbatch : cap), 128, 0, ctx->stream>>>(ne, B, G, pd, pm, dE);
+   const long long cap = (long long)ctx->num_sms * 3;
+   kern<<<(int)(nbatch < cap ? nbatch : cap), 128, C::SMEM_BYTES, ctx->stream>>>(P);
 }
 
-static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *Bdev, const double *Gdev,
+// hB, hG: HOST copies of the 1-D basis tables
+static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *hB, const double *hG,
                     const double *pd, const double *pm, double *dE)
 {
    B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
    if (ne <= 0) { return 0; }
+   B200PA_REQUIRE(((((unsigned long long)pd) | ((unsigned long long)pm)) & 15ull) == 0, "pa_data must be 16-byte aligned (TMA bulk copies)");
    switch (d1d)
    {
-      case 2: launch_diag<2, 3>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
-      case 3: launch_diag<3, 4>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
-      case 4: launch_diag<4, 5>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
-      case 5: launch_diag<5, 6>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
-      case 6: launch_diag<6, 7>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
-      case 7: launch_diag<7, 8>(ctx, ne, Bdev, Gdev, pd, pm, dE); break;
+      case 2: launch_diag<2, 3>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 3: launch_diag<3, 4>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 4: launch_diag<4, 5>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 5: launch_diag<5, 6>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 6: launch_diag<6, 7>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 7: launch_diag<7, 8>(ctx, ne, hB, hG, pd, pm, dE); break;
    }
    B200PA_LAUNCHED();
    return 0;
@@ -134,6 +146,10 @@ struct b200pa_space_s
    DevBuf dB, dG;
    DevBuf gmap, offsets, indices, slot;
    DevBuf W, J, detJ;
+   // trilinear geometry kept as vertices (b200pa_space_geometry_from_vertices): J is then never stored
+   // unless somebody asks for it (b200pa_space_J); set-up and q-point kernels rebuild it on the fly
+   DevBuf vtx, ev, dxi;
+   std::vector<double> hxi;
    DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
 };
 
@@ -340,15 +356,9 @@ static int diag_common(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B
 {
    NEED_CTX(ctx);
    B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
-   DevBuf bB, bG;
-   const void *dB = nullptr, *dG = nullptr;
-   std::vector<double> zero((size_t)d1d * q1d, 0.0);
-   int rc = to_device(ctx, B, sizeof(double) * d1d * q1d, bB, &dB);
-   if (!rc) { rc = to_device(ctx, G ? G : zero.data(), sizeof(double) * d1d * q1d, bG, &dG); }
-   if (!rc) { rc = run_diag(ctx, d1d, q1d, ne, (const double *)dB, (const double *)dG, pd, pm, dE); }
-   if (!rc && (bB.owned || bG.owned)) { cudaStreamSynchronize(ctx->stream); }
-   bB.release(); bG.release();
-   return rc;
+   HostBG h;
+   if (h.get(ctx, d1d, q1d, B, G)) { return 1; }
+   return run_diag(ctx, d1d, q1d, ne, h.B.data(), h.G.data(), pd, pm, dE);
 }
 
 extern "C" int b200pa_diffusion_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G,
@@ -551,7 +561,7 @@ extern "C" int b200pa_space_destroy(b200pa_space sp)
    if (!sp) { return 0; }
    cudaSetDevice(sp->ctx->device);
    cudaStreamSynchronize(sp->ctx->stream);
-   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->scratchE})
+   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->scratchE})
    {
       b->release();
    }
@@ -582,7 +592,11 @@ extern "C" int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, c
       B200PA_CK(cudaMemcpyAsync(sp->W.p, w.data(), q3 * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
       B200PA_CK(cudaStreamSynchronize(sp->ctx->stream));
    }
-   if (J_any) { if (borrow_or_copy(sp->ctx, J_any, 9 * (size_t)sp->nQ, sp->J)) { return 1; } }
+   if (J_any)
+   {
+      if (borrow_or_copy(sp->ctx, J_any, 9 * (size_t)sp->nQ, sp->J)) { return 1; }
+      sp->vtx.release(); sp->ev.release(); sp->hxi.clear(); // the host's Jacobians win over a trilinear rebuild
+   }
    if (detJ_any) { if (borrow_or_copy(sp->ctx, detJ_any, (size_t)sp->nQ, sp->detJ)) { return 1; } }
    return 0;
 }
@@ -613,38 +627,56 @@ extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double
    NEED_CTX(sp->ctx);
    b200pa_ctx ctx = sp->ctx;
    if (b200pa_space_set_geometry(sp, W_any, nullptr, nullptr)) { return 1; }
-   DevBuf bv, bev, bxi;
-   const void *dv = nullptr, *dev = nullptr;
-   int rc = to_device(ctx, vertices_any, sizeof(double) * 3 * (size_t)nv, bv, &dv);
-   if (!rc && !is_device_ptr(elem_vertices_any))
-   {
-      rc = alloc(bev, sizeof(int) * 8 * (size_t)std::max(sp->ne, 1));
-      if (!rc) { cudaMemcpyAsync(bev.p, elem_vertices_any, sizeof(int) * 8 * (size_t)sp->ne, cudaMemcpyHostToDevice, ctx->stream); dev = bev.p; }
-   }
-   else { dev = elem_vertices_any; }
-   double xi[16];
-   gauss_legendre_01(sp->q1d, xi);
-   if (!rc) { rc = alloc(bxi, sizeof(double) * 16); }
-   if (!rc) { cudaMemcpyAsync(bxi.p, xi, sizeof(double) * sp->q1d, cudaMemcpyHostToDevice, ctx->stream); }
    sp->J.release(); sp->detJ.release();
-   if (!rc) { rc = alloc(sp->J, sizeof(double) * 9 * (size_t)std::max<long long>(sp->nQ, 1)); }
-   if (!rc) { rc = alloc(sp->detJ, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1)); }
-   if (!rc && sp->ne > 0)
+   if (alloc(sp->vtx, sizeof(double) * 3 * (size_t)std::max(nv, 1)) || alloc(sp->ev, sizeof(int) * 8 * (size_t)std::max(sp->ne, 1)) ||
+       alloc(sp->dxi, sizeof(double) * 16) || alloc(sp->detJ, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1)))
    {
-      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, bxi.as<double>(), (const double *)dv,
-                                                                       (const int *)dev, sp->J.as<double>(), sp->detJ.as<double>());
-      g_launches++;
-      if (cudaGetLastError() != cudaSuccess) { rc = fail("geometry kernel launch failed"); }
+      return 1;
    }
-   cudaStreamSynchronize(ctx->stream);
-   bv.release(); bev.release(); bxi.release();
-   return rc;
+   B200PA_CK(cudaMemcpyAsync(sp->vtx.p, vertices_any, sizeof(double) * 3 * (size_t)nv,
+                             is_device_ptr(vertices_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+   if (sp->ne > 0)
+   {
+      B200PA_CK(cudaMemcpyAsync(sp->ev.p, elem_vertices_any, sizeof(int) * 8 * (size_t)sp->ne,
+                                is_device_ptr(elem_vertices_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+   }
+   sp->hxi.assign(16, 0.0);
+   gauss_legendre_01(sp->q1d, sp->hxi.data());
+   B200PA_CK(cudaMemcpyAsync(sp->dxi.p, sp->hxi.data(), sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+   if (sp->ne > 0)
+   {
+      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, sp->dxi.as<double>(), sp->vtx.as<double>(),
+                                                                       sp->ev.as<int>(), nullptr, sp->detJ.as<double>());
+      B200PA_LAUNCHED();
+   }
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+// Jacobians on demand (accessor / callers that want the reference's J array)
+static int ensure_J(b200pa_space sp)
+{
+   if (sp->J.p) { return 0; }
+   B200PA_REQUIRE(sp->vtx.p, "space has no geometry (call b200pa_space_set_geometry or b200pa_space_geometry_from_vertices)");
+   b200pa_ctx ctx = sp->ctx;
+   if (alloc(sp->J, sizeof(double) * 9 * (size_t)std::max<long long>(sp->nQ, 1))) { return 1; }
+   if (sp->ne > 0)
+   {
+      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, sp->dxi.as<double>(), sp->vtx.as<double>(),
+                                                                       sp->ev.as<int>(), sp->J.as<double>(), nullptr);
+      B200PA_LAUNCHED();
+   }
+   return 0;
 }
 
 extern "C" const int *b200pa_space_offsets(b200pa_space sp) { return sp ? sp->offsets.as<int>() : nullptr; }
 extern "C" const int *b200pa_space_indices(b200pa_space sp) { return sp ? sp->indices.as<int>() : nullptr; }
 extern "C" const int *b200pa_space_gather_map(b200pa_space sp) { return sp ? sp->gmap.as<int>() : nullptr; }
-extern "C" const double *b200pa_space_J(b200pa_space sp) { return sp ? sp->J.as<double>() : nullptr; }
+extern "C" const double *b200pa_space_J(b200pa_space sp)
+{
+   if (!sp || cudaSetDevice(sp->ctx->device) != cudaSuccess || ensure_J(sp)) { return nullptr; }
+   return sp->J.as<double>();
+}
 extern "C" const double *b200pa_space_detJ(b200pa_space sp) { return sp ? sp->detJ.as<double>() : nullptr; }
 extern "C" const double *b200pa_space_W(b200pa_space sp) { return sp ? sp->W.as<double>() : nullptr; }
 
@@ -658,6 +690,13 @@ static ElemArgs space_args(b200pa_space sp)
    ElemArgs a;
    a.B = sp->hB.data(); a.G = sp->hG.data(); a.NE = sp->ne;
    return a;
+}
+
+// stored Jacobians if the space has them, else the vertices they are rebuilt from
+static void geometry_args(b200pa_space sp, ElemArgs &a)
+{
+   if (sp->J.p) { a.J = sp->J.as<double>(); }
+   else { a.vtx = sp->vtx.as<double>(); a.ev = sp->ev.as<int>(); a.xi = sp->hxi.data(); }
 }
 
 // ---- q-point operators straight from an L-vector (gather fused in)
@@ -674,9 +713,10 @@ extern "C" int b200pa_space_qphysgrad(b200pa_space sp, const double *xL_dev, dou
 {
    B200PA_REQUIRE(sp, "space is NULL");
    NEED_CTX(sp->ctx);
-   B200PA_REQUIRE(sp->J.p, "space has no geometry (call b200pa_space_set_geometry)");
+   B200PA_REQUIRE(sp->J.p || sp->vtx.p, "space has no geometry (call b200pa_space_set_geometry)");
    ElemArgs a = space_args(sp);
-   a.x = xL_dev; a.gmap = sp->gmap.as<int>(); a.y = gq_dev; a.J = sp->J.as<double>();
+   a.x = xL_dev; a.gmap = sp->gmap.as<int>(); a.y = gq_dev;
+   geometry_args(sp, a);
    return run_element(sp->ctx, sp->d1d, sp->q1d, EV_PHYSGRAD_L, a);
 }
 
@@ -694,9 +734,10 @@ extern "C" int b200pa_space_joule(b200pa_space sp, const double *phiL_dev, const
 {
    B200PA_REQUIRE(sp, "space is NULL");
    NEED_CTX(sp->ctx);
-   B200PA_REQUIRE(sp->J.p, "space has no geometry (call b200pa_space_set_geometry)");
+   B200PA_REQUIRE(sp->J.p || sp->vtx.p, "space has no geometry (call b200pa_space_set_geometry)");
    ElemArgs a = space_args(sp);
-   a.x = phiL_dev; a.gmap = sp->gmap.as<int>(); a.y = out_q_dev; a.J = sp->J.as<double>(); a.s = sigma_q_dev; a.ca = add;
+   a.x = phiL_dev; a.gmap = sp->gmap.as<int>(); a.y = out_q_dev; a.s = sigma_q_dev; a.ca = add;
+   geometry_args(sp, a);
    return run_element(sp->ctx, sp->d1d, sp->q1d, EV_JOULE_L, a);
 }
 
@@ -753,14 +794,25 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
    b200pa_space sp = f->sp;
    NEED_CTX(sp->ctx);
    if (!C_any) { f->pa_diff.release(); f->has_diff = false; return 0; }
-   B200PA_REQUIRE(sp->J.p && sp->W.p, "assemble_diffusion: space has no geometry");
+   B200PA_REQUIRE((sp->J.p || sp->vtx.p) && sp->W.p, "assemble_diffusion: space has no geometry");
    B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_diffusion: coefficient must have 1 or Q^3*NE entries");
    DevBuf cb;
    const void *dC = nullptr;
    if (to_device(sp->ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
    if (!f->pa_diff.owned) { f->pa_diff.release(); }
    int rc = alloc(f->pa_diff, sizeof(double) * 6 * (size_t)std::max<long long>(sp->nQ, 1));
-   if (!rc) { rc = b200pa_diffusion_setup(sp->ctx, sp->q1d, sp->ne, sp->W.as<double>(), sp->J.as<double>(), (const double *)dC, nc, f->pa_diff.as<double>()); }
+   if (!rc && sp->J.p)
+   {
+      rc = b200pa_diffusion_setup(sp->ctx, sp->q1d, sp->ne, sp->W.as<double>(), sp->J.as<double>(), (const double *)dC, nc, f->pa_diff.as<double>());
+   }
+   else if (!rc && sp->ne > 0)
+   {
+      k_diffusion_setup_trilinear<<<grid1d(sp->ctx, sp->nQ), 256, 0, sp->ctx->stream>>>(sp->q1d, sp->ne, sp->W.as<double>(), sp->dxi.as<double>(),
+                                                                                      sp->vtx.as<double>(), sp->ev.as<int>(), (const double *)dC,
+                                                                                      nc == 1, f->pa_diff.as<double>());
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("diffusion set-up kernel launch failed"); }
+   }
    if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
    f->has_diff = (rc == 0);
    return rc;
@@ -844,7 +896,7 @@ extern "C" int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *es
 // y = A x (constrained: ConstrainedOperator::Mult, DIAG_ONE).  dot_out != NULL adds x.y (owned dofs)
 // into the segmented reduction's epilogue.  done: PCG early-exit flag.
 static int form_apply(b200pa_form f, const double *x, double *y, bool constrained, double *dot_out, const int *done,
-                      int phases = 3)
+                      int phases = 3, PcgState *st_epilogue = nullptr)
 {
    b200pa_space sp = f->sp;
    b200pa_ctx ctx = sp->ctx;
@@ -882,7 +934,7 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
    if (constrained && dot_out)
    {
       k_segment_sum<true, true, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, own, ctx->d_partials,
-                                                                    ctx->d_ticket, dot_out, done);
+                                                                    ctx->d_ticket, dot_out, done, st_epilogue);
    }
    else if (constrained)
    {
@@ -952,7 +1004,7 @@ extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
    B200PA_REQUIRE(f->has_diff || f->has_mass, "form has no assembled integrator");
    // fem/bilinearform_ext.cpp:401-423: localY = 0; every integrator adds; AbsMultTranspose
    B200PA_CK(cudaMemsetAsync(sp->scratchE.p, 0, sizeof(double) * (size_t)sp->nE, ctx->stream));
-   if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->dB.as<double>(), sp->dG.as<double>(),
+   if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->hB.data(), sp->hG.data(),
                 f->has_diff ? f->pa_diff.as<double>() : nullptr, f->has_mass ? f->pa_mass.as<double>() : nullptr,
                 sp->scratchE.as<double>()))
    {
@@ -1026,18 +1078,31 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    B200PA_CK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
    B200PA_CK(cudaMemsetAsync(norms, 0, sizeof(double) * ((size_t)max_iter + 2), s));
 
+   // Single GPU: the scalar steps (alpha, beta, stopping test) run as the epilogue of the reduction that
+   // produces their input - 4 launches per iteration.  Multi-GPU: an all-reduce sits between the two, so
+   // they are 1-thread kernels after it.
+   const bool fused_scalars = (f->comm == nullptr);
+   double *ep_norms = fused_scalars ? norms : nullptr;
+   PcgState *ep_st = fused_scalars ? st : nullptr;
+
    // r = b - A x; z = B r; d = z; nom = (d, r)                              (solvers.cpp:875-895)
    if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
-   k_pcg_init<<<grid, 256, 0, s>>>(n, b_dev, dinv_dev, r, d, own, ctx->d_partials, ctx->d_ticket, st);
+   k_pcg_init<<<grid, 256, 0, s>>>(n, b_dev, dinv_dev, r, d, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
    B200PA_LAUNCHED();
-   if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
-   k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms);
-   B200PA_LAUNCHED();
+   if (!fused_scalars)
+   {
+      if (comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
+      k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms);
+      B200PA_LAUNCHED();
+   }
    // z = A d; den = (z, d)                                                   (:921-938)
-   if (form_apply(f, d, z, true, &st->dot_b, &st->done)) { return 1; }
-   if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
-   k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
-   B200PA_LAUNCHED();
+   if (form_apply(f, d, z, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+   if (!fused_scalars)
+   {
+      if (comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
+      k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
+      B200PA_LAUNCHED();
+   }
 
    // the loop (:952-1027).  Scalars stay on the device; the host only polls `done` every few
    // iterations (kernels after convergence return immediately on the flag).
@@ -1046,17 +1111,23 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    const int poll = 8;
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
-      k_pcg_update<<<grid, 256, 0, s>>>(n, x_dev, r, z, d, dinv_dev, own, ctx->d_partials, ctx->d_ticket, st);
+      k_pcg_update<<<grid, 256, 0, s>>>(n, x_dev, r, z, d, dinv_dev, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
       B200PA_LAUNCHED();
-      if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
-      k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms);
-      B200PA_LAUNCHED();
+      if (!fused_scalars)
+      {
+         if (comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
+         k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms);
+         B200PA_LAUNCHED();
+      }
       k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st);
       B200PA_LAUNCHED();
-      if (form_apply(f, d, z, true, &st->dot_b, &st->done)) { return 1; }
-      if (f->comm && comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
-      k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
-      B200PA_LAUNCHED();
+      if (form_apply(f, d, z, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+      if (!fused_scalars)
+      {
+         if (comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
+         k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
+         B200PA_LAUNCHED();
+      }
       if (it % poll == 0)
       {
          B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));

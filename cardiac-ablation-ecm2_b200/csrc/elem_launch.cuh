@@ -37,6 +37,9 @@ struct ElemArgs
    const int *done = nullptr;
    double ca = 0.0, cb = 0.0, cT0 = 0.0;    // EV_COEFF_L / EV_JOULE_L parameters
    const double *s = nullptr;               // EV_JOULE_L: sigma_q
+   const double *vtx = nullptr;             // J == nullptr: trilinear geometry from vertices
+   const int *ev = nullptr;
+   const double *xi = nullptr;              // HOST pointer, Q values
 };
 
 // returns cudaError_t as int; `num_sms` sizes the persistent grid

@@ -4,6 +4,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "geometry.cuh"
+#include "tma.cuh"
+
 namespace b200pa
 {
 
@@ -27,7 +30,9 @@ __device__ __forceinline__ double block_sum(double v)
    return v; // valid in thread 0
 }
 
-__device__ __forceinline__ void grid_sum(double v, double *partials, unsigned int *ticket, double *out)
+// returns true in thread 0 of the last block to finish, after *out has been written: the place to run a
+// scalar epilogue without another launch
+__device__ __forceinline__ bool grid_sum(double v, double *partials, unsigned int *ticket, double *out)
 {
    const double bs = block_sum(v);
    __shared__ bool last;
@@ -45,8 +50,9 @@ __device__ __forceinline__ void grid_sum(double v, double *partials, unsigned in
       double s = 0.0;
       for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { s += ((volatile double *)partials)[i]; }
       s = block_sum(s);
-      if (threadIdx.x == 0) { *out = s; }
+      if (threadIdx.x == 0) { *out = s; return true; }
    }
+   return false;
 }
 
 __global__ void k_dot(long long n, const double *__restrict__ a, const double *__restrict__ b,
@@ -59,6 +65,68 @@ __global__ void k_dot(long long n, const double *__restrict__ a, const double *_
    }
    grid_sum(s, partials, ticket, out);
 }
+
+// Device-resident scalar state of CGSolver::Mult (linalg/solvers.cpp:869-1050).
+struct PcgState
+{
+   double nom, nom0, den, betanom, r0, alpha, beta;
+   double dot_a, dot_b;       // raw reduction results (before the scalar step / all-reduce)
+   double rel_tol, abs_tol;
+   int iter;                  // the reference's loop variable i
+   int max_iter;
+   int done, converged, final_iter, nonfinite;
+};
+
+
+// the scalar steps of the loop; run either as the epilogue of the reduction that produced their input
+// (single GPU) or as 1-thread kernels after the all-reduce (multi-GPU)
+__device__ __forceinline__ void pcg_scalar_init(PcgState *st, double *norms)
+{
+   const double nom = st->dot_a;
+   st->nom = st->nom0 = nom;
+   norms[0] = nom;
+   st->iter = 1;
+   if (!isfinite(nom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
+   if (nom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
+   st->r0 = fmax(nom * st->rel_tol * st->rel_tol, st->abs_tol * st->abs_tol);
+   st->betanom = nom;
+   if (nom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = 0; }
+}
+
+__device__ __forceinline__ void pcg_scalar_den(PcgState *st)
+{
+   if (st->done) { return; }
+   const double den = st->dot_b;
+   st->den = den;
+   if (!isfinite(den)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = st->iter - 1; return; }
+   if (den == 0.0)
+   {
+      // before the loop: final_iter = 0; inside: final_iter = i (already incremented)
+      st->done = 1; st->converged = 0; st->final_iter = (st->iter == 1) ? 0 : st->iter;
+      return;
+   }
+   st->alpha = st->nom / den;
+}
+
+__device__ __forceinline__ void pcg_scalar_beta(PcgState *st, double *norms)
+{
+   if (st->done) { return; }
+   const double betanom = st->dot_a;
+   const int i = st->iter;
+   st->betanom = betanom;
+   norms[i] = betanom;
+   if (!isfinite(betanom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = i; return; }
+   if (betanom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = i; return; }
+   if (betanom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = i; return; }
+   if (i + 1 > st->max_iter) { st->done = 1; st->converged = 0; st->final_iter = st->max_iter; return; }
+   st->iter = i + 1;
+   st->beta = betanom / st->nom;
+   st->nom = betanom; // (:1026; alpha of the next pass uses it)
+}
+
+__global__ void k_pcg_scalar_init(PcgState *st, double *norms) { pcg_scalar_init(st, norms); }
+__global__ void k_pcg_scalar_den(PcgState *st) { pcg_scalar_den(st); }
+__global__ void k_pcg_scalar_beta(PcgState *st, double *norms) { pcg_scalar_beta(st, norms); }
 
 // ------------------------------------------------------------------ restriction
 // fem/restriction.cpp:109-129
@@ -98,7 +166,8 @@ template <bool CONSTR, bool DOT, bool ABS>
 __global__ void k_segment_sum(int ndofs, const int *__restrict__ offsets, const double *__restrict__ yS,
                               double *__restrict__ y, const unsigned char *__restrict__ ess_mask,
                               const double *__restrict__ x, const unsigned char *__restrict__ own_mask,
-                              double *partials, unsigned int *ticket, double *dot_out, const int *done_flag)
+                              double *partials, unsigned int *ticket, double *dot_out, const int *done_flag,
+                              PcgState *st_epilogue = nullptr)
 {
    if (done_flag && *done_flag) { return; }
    double acc = 0.0;
@@ -111,7 +180,11 @@ __global__ void k_segment_sum(int ndofs, const int *__restrict__ offsets, const 
       y[i] = v;
       if (DOT) { if (!own_mask || own_mask[i]) { acc = fma(x[i], v, acc); } }
    }
-   if (DOT) { grid_sum(acc, partials, ticket, dot_out); }
+   if (DOT)
+   {
+      // den = (d, A d) is complete: alpha / termination logic right here (linalg/solvers.cpp:1010-1024)
+      if (grid_sum(acc, partials, ticket, dot_out) && st_epilogue) { pcg_scalar_den(st_epilogue); }
+   }
 }
 
 // multi-GPU second pass after the shared-dof exchange: ConstrainedOperator fix-up and the
@@ -173,8 +246,7 @@ __global__ void k_mass_setup(long long NQ, long long NE, const double *__restric
    }
 }
 
-// mesh/mesh.cpp:15220-15273 for trilinear hexes: J(q) = sum_v X_v (x) grad N_v(xi_q); vertex
-// order of the reference hexahedron (mesh/mesh.cpp:3757-3765).  One thread per q-point.
+// One thread per q-point; J and/or detJ may be null (only what is asked for is stored).
 __global__ void k_geometry_trilinear(int Q1D, long long NE, const double *__restrict__ xi,
                                      const double *__restrict__ vtx, const int *__restrict__ ev,
                                      double *__restrict__ J, double *__restrict__ detJ)
@@ -184,32 +256,49 @@ __global__ void k_geometry_trilinear(int Q1D, long long NE, const double *__rest
    {
       const long long e = i / NQ, q = i - e * NQ;
       const int qx = q % Q1D, qy = (q / Q1D) % Q1D, qz = q / (Q1D * Q1D);
-      const double x = xi[qx], y = xi[qy], z = xi[qz];
-      const double bx[2] = {1.0 - x, x}, by[2] = {1.0 - y, y}, bz[2] = {1.0 - z, z};
-      const double gm[2] = {-1.0, 1.0};
-      // local vertex v -> (i,j,k) corner bits
-      const int ci[8] = {0, 1, 1, 0, 0, 1, 1, 0}, cj[8] = {0, 0, 1, 1, 0, 0, 1, 1}, ck[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-      double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // Jm[row + 3*col]
-#pragma unroll
-      for (int v = 0; v < 8; ++v)
+      double Jm[9];
+      trilinear_jacobian(vtx, ev + 8 * e, xi[qx], xi[qy], xi[qz], Jm);
+      if (J)
       {
-         const double *X = vtx + 3LL * ev[8 * e + v];
-         const double d0 = gm[ci[v]] * by[cj[v]] * bz[ck[v]];
-         const double d1 = bx[ci[v]] * gm[cj[v]] * bz[ck[v]];
-         const double d2 = bx[ci[v]] * by[cj[v]] * gm[ck[v]];
+         double *Je = J + e * 9 * NQ + q;
 #pragma unroll
-         for (int r = 0; r < 3; ++r)
-         {
-            Jm[r + 0] = fma(X[r], d0, Jm[r + 0]);
-            Jm[r + 3] = fma(X[r], d1, Jm[r + 3]);
-            Jm[r + 6] = fma(X[r], d2, Jm[r + 6]);
-         }
+         for (int k = 0; k < 9; ++k) { Je[k * NQ] = Jm[k]; }
       }
-      double *Je = J + e * 9 * NQ + q;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) { Je[k * NQ] = Jm[k]; }
-      detJ[i] = Jm[0] * (Jm[4] * Jm[8] - Jm[5] * Jm[7]) - Jm[1] * (Jm[3] * Jm[8] - Jm[5] * Jm[6]) +
-                Jm[2] * (Jm[3] * Jm[7] - Jm[4] * Jm[6]);
+      if (detJ)
+      {
+         detJ[i] = Jm[0] * (Jm[4] * Jm[8] - Jm[5] * Jm[7]) - Jm[1] * (Jm[3] * Jm[8] - Jm[5] * Jm[6]) +
+                   Jm[2] * (Jm[3] * Jm[7] - Jm[4] * Jm[6]);
+      }
+   }
+}
+
+// GeometricFactors::Compute + PADiffusionSetup3D in one pass for trilinear hexes: J never goes to HBM
+// (reads 8 vertices per element instead of 9 doubles per q-point: 56 instead of 128 B per q-point).
+__global__ void k_diffusion_setup_trilinear(int Q1D, long long NE, const double *__restrict__ W, const double *__restrict__ xi,
+                                            const double *__restrict__ vtx, const int *__restrict__ ev,
+                                            const double *__restrict__ C, int const_c, double *__restrict__ D)
+{
+   const long long NQ = (long long)Q1D * Q1D * Q1D, n = NQ * NE;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      const long long e = i / NQ, q = i - e * NQ;
+      const int qx = q % Q1D, qy = (q / Q1D) % Q1D, qz = q / (Q1D * Q1D);
+      double Jm[9];
+      trilinear_jacobian(vtx, ev + 8 * e, xi[qx], xi[qy], xi[qz], Jm);
+      const double J11 = Jm[0], J21 = Jm[1], J31 = Jm[2], J12 = Jm[3], J22 = Jm[4], J32 = Jm[5], J13 = Jm[6], J23 = Jm[7], J33 = Jm[8];
+      const double detJ = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13);
+      const double c = const_c ? C[0] : C[i];
+      const double w = c * (W[q] / detJ);
+      const double A11 = (J22 * J33) - (J23 * J32), A12 = (J32 * J13) - (J12 * J33), A13 = (J12 * J23) - (J22 * J13);
+      const double A21 = (J31 * J23) - (J21 * J33), A22 = (J11 * J33) - (J13 * J31), A23 = (J21 * J13) - (J11 * J23);
+      const double A31 = (J21 * J32) - (J31 * J22), A32 = (J31 * J12) - (J11 * J32), A33 = (J11 * J22) - (J12 * J21);
+      double *De = D + e * 6 * NQ + q;
+      De[0 * NQ] = w * (A11 * A11 + A12 * A12 + A13 * A13);
+      De[1 * NQ] = w * (A11 * A21 + A12 * A22 + A13 * A23);
+      De[2 * NQ] = w * (A11 * A31 + A12 * A32 + A13 * A33);
+      De[3 * NQ] = w * (A21 * A21 + A22 * A22 + A23 * A23);
+      De[4 * NQ] = w * (A21 * A31 + A22 * A32 + A23 * A33);
+      De[5 * NQ] = w * (A31 * A31 + A32 * A32 + A33 * A33);
    }
 }
 
@@ -230,53 +319,6 @@ __global__ void k_coeff_eval(int kind, long long n, double a, double b, double T
 }
 
 // --------------------------------------------------------------------- diagonal
-// fem/integ/bilininteg_diffusion_kernels.hpp:369-484 and bilininteg_mass_kernels.hpp:324-408:
-// dE[e,l] += sum_q grad(phi_l)^T D grad(phi_l) + v phi_l^2.  One thread per E-entry; B,G in smem.
-template <int D1, int Q1>
-__global__ void k_diag(long long NE, const double *__restrict__ Bg, const double *__restrict__ Gg,
-                       const double *__restrict__ pa_diff, const double *__restrict__ pa_mass,
-                       double *__restrict__ dE)
-{
-   __shared__ double sB[Q1 * D1], sG[Q1 * D1];
-   for (int i = threadIdx.x; i < Q1 * D1; i += blockDim.x) { sB[i] = Bg[i]; sG[i] = Gg[i]; }
-   __syncthreads();
-   constexpr int D3 = D1 * D1 * D1, Q3 = Q1 * Q1 * Q1;
-   const long long n = NE * D3;
-   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-   {
-      const long long e = i / D3;
-      const int l = (int)(i - e * D3), dx = l % D1, dy = (l / D1) % D1, dz = l / (D1 * D1);
-      double acc = 0.0;
-      for (int qz = 0; qz < Q1; ++qz)
-      {
-         const double bz = sB[qz + Q1 * dz], gz = sG[qz + Q1 * dz];
-         for (int qy = 0; qy < Q1; ++qy)
-         {
-            const double by = sB[qy + Q1 * dy], gy = sG[qy + Q1 * dy];
-#pragma unroll
-            for (int qx = 0; qx < Q1; ++qx)
-            {
-               const double bx = sB[qx + Q1 * dx], gx = sG[qx + Q1 * dx];
-               const long long q = qx + Q1 * (qy + Q1 * qz);
-               if (pa_diff)
-               {
-                  const double *d = pa_diff + e * 6 * Q3 + q;
-                  const double X = gx * by * bz, Y = bx * gy * bz, Z = bx * by * gz;
-                  acc += X * (d[0] * X + d[Q3] * Y + d[2 * Q3] * Z) + Y * (d[Q3] * X + d[3 * Q3] * Y + d[4 * Q3] * Z) +
-                         Z * (d[2 * Q3] * X + d[4 * Q3] * Y + d[5 * Q3] * Z);
-               }
-               if (pa_mass)
-               {
-                  const double v = bx * by * bz;
-                  acc = fma(pa_mass[e * Q3 + q], v * v, acc);
-               }
-            }
-         }
-      }
-      dE[i] += acc;
-   }
-}
-
 // Sum-factorised diagonal (what the reference's SmemPADiffusionDiagonal3D / SmemPAMassAssembleDiagonal3D
 // do, fem/integ/bilininteg_diffusion_kernels.hpp:369-484, bilininteg_mass_kernels.hpp:324-408):
 //   dE[dx,dy,dz] += sum_f w_f sum_q D_f(q) Mx_f(qx,dx) My_f(qy,dy) Mz_f(qz,dz)
@@ -284,94 +326,155 @@ __global__ void k_diag(long long NE, const double *__restrict__ Bg, const double
 // GG, BG or BB (G in the directions i and j of D_ij, B elsewhere); w = 2 for the off-diagonal D_ij.
 // Three contraction passes through shared memory instead of a Q^3 loop per E-entry (14x fewer FMAs at p=2).
 template <int D1, int Q1, int NEB>
-__global__ void __launch_bounds__(128)
-k_diag_sf(long long NE, const double *__restrict__ Bg, const double *__restrict__ Gg, const double *__restrict__ pa_diff,
-          const double *__restrict__ pa_mass, double *__restrict__ dE)
+struct DiagSfCfg
 {
-   constexpr int D3 = D1 * D1 * D1, Q2 = Q1 * Q1, Q3 = Q1 * Q1 * Q1, NF = 7;
-   constexpr int T1E = NF * Q2 * D1, T2E = NF * Q1 * D1 * D1;
-   __shared__ double sM[3][Q1 * D1]; // 0: BB, 1: BG, 2: GG
-   __shared__ double sT1[NEB * T1E];
-   __shared__ double sT2[NEB * T2E];
-   for (int i = threadIdx.x; i < Q1 * D1; i += blockDim.x)
-   {
-      const double b = Bg[i], g = Gg[i];
-      sM[0][i] = b * b; sM[1][i] = b * g; sM[2][i] = g * g;
-   }
+   static constexpr int Q2 = Q1 * Q1, Q3 = Q1 * Q1 * Q1, NF = 7;
+   static constexpr int T1E = NF * Q2 * D1, T2E = NF * Q1 * D1 * D1;
+   static constexpr int SQD = NEB * 6 * Q3 + 2, SQM = ((NEB * Q3 + 2) + 1) & ~1; // TMA staging (16-byte aligned, +slack)
+   static constexpr size_t SMEM_BYTES = sizeof(double) * (SQD + SQM + NEB * (T1E + T2E));
+};
+
+// kernel parameters: the three 1-D factor tables live in the constant bank, so that with the field loop
+// unrolled every coefficient is a compile-time-indexed DFMA operand
+template <int D1, int Q1>
+struct DiagParams
+{
+   double M[3][Q1 * D1]; // 0: B*B, 1: B*G, 2: G*G, column-major [Q,D]
+   long long NE;
+   const double *__restrict__ pa_diff;
+   const double *__restrict__ pa_mass;
+   double *__restrict__ dE;
+};
+
+template <int D1, int Q1, int NEB>
+__global__ void __launch_bounds__(128)
+k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
+{
+   using C = DiagSfCfg<D1, Q1, NEB>;
+   constexpr int D3 = D1 * D1 * D1, Q2 = C::Q2, Q3 = C::Q3, NF = C::NF, T1E = C::T1E, T2E = C::T2E;
+   extern __shared__ double dsm[];
+   double *sQd = dsm;                 // this batch's q-data, staged by TMA one batch ahead (as pa_apply_kernel)
+   double *sQm = sQd + C::SQD;
+   double *sT1 = sQm + C::SQM;
+   double *sT2 = sT1 + NEB * T1E;
+   __shared__ unsigned long long qbar;
+   const long long NE = P.NE;
+   const double *pa_diff = P.pa_diff, *pa_mass = P.pa_mass;
+   if (threadIdx.x == 0) { mbar_init(&qbar, 1); }
    __syncthreads();
-   // factor type of field f in direction a: number of indices of D_ij equal to a
-   auto mtype = [](int f, int a) -> int
+// factor type of field f = D00, D01, D02, D11, D12, D22, mass in direction a: how many of the two indices
+// of D_ij equal a (0: BB, 1: BG, 2: GG); f and a are compile-time wherever this is used
+#define B200PA_MTYPE(f, a) ((((a) == 0 ? 0x0016u : ((a) == 1 ? 0x0184u : 0x0910u)) >> (2 * (f))) & 3u)
+   auto issue = [&](long long b)
    {
-      const int fi[7] = {0, 0, 0, 1, 1, 2, -1}, fj[7] = {0, 1, 2, 1, 2, 2, -1};
-      return (fi[f] == a) + (fj[f] == a);
+      const long long e0 = b * NEB;
+      const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
+      unsigned bytes_d = 0, bytes_m = 0;
+      const double *src_m = nullptr;
+      if (pa_diff) { bytes_d = (unsigned)(nel * 6 * Q3 * sizeof(double)); }
+      if (pa_mass)
+      {
+         const double *src = pa_mass + e0 * Q3;
+         const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
+         src_m = src - sh;
+         int nd = sh + nel * Q3;
+         if (nd & 1)
+         {
+            if (e0 + nel < NE) { nd += 1; }
+            else { nd -= 1; sQm[nd] = __ldg(src_m + nd); }
+         }
+         bytes_m = (unsigned)(nd * sizeof(double));
+      }
+      mbar_expect_tx(&qbar, bytes_d + bytes_m);
+      if (pa_diff) { tma_bulk_g2s(sQd, pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
+      if (pa_mass) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
    };
    const long long nbatch = (NE + NEB - 1) / NEB;
+   unsigned phase = 0;
+   if ((long long)blockIdx.x < nbatch && threadIdx.x == 0) { issue(blockIdx.x); }
    for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x)
    {
       const long long e0 = batch * NEB;
       const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
-      // pass 1: contract qx.  task = (e, f, qz, qy): one contiguous row of Q1 q-data values
-      for (int t = threadIdx.x; t < nel * NF * Q2; t += blockDim.x)
+      mbar_wait(&qbar, phase);
+      phase ^= 1u;
+      const int msh = pa_mass ? (int)(((unsigned long long)(pa_mass + e0 * Q3) >> 3) & 1ull) : 0;
+      // pass 1: contract qx.  task = (e, qz, qy), all seven fields: one row of Q1 q-data values each
+      for (int t = threadIdx.x; t < nel * Q2; t += blockDim.x)
       {
-         const int e = t / (NF * Q2), r = t - e * NF * Q2, f = r / Q2, row = r - f * Q2;
-         const double *src = f < 6 ? (pa_diff ? pa_diff + ((e0 + e) * 6 + f) * Q3 + row * Q1 : nullptr)
-                                   : (pa_mass ? pa_mass + (e0 + e) * Q3 + row * Q1 : nullptr);
-         const double *M = sM[mtype(f, 0)];
-         double out[D1];
+         const int e = t / Q2, row = t - e * Q2;
 #pragma unroll
-         for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
-         if (src)
+         for (int f = 0; f < NF; ++f)
          {
+            const bool have = f < 6 ? pa_diff != nullptr : pa_mass != nullptr;
+            const double *src = f < 6 ? sQd + (e * 6 + f) * Q3 + row * Q1 : sQm + msh + e * Q3 + row * Q1;
+            double out[D1];
 #pragma unroll
-            for (int q = 0; q < Q1; ++q)
+            for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
+            if (have)
             {
-               const double v = src[q];
 #pragma unroll
-               for (int d = 0; d < D1; ++d) { out[d] = fma(M[q + Q1 * d], v, out[d]); }
+               for (int q = 0; q < Q1; ++q)
+               {
+                  const double v = src[q];
+#pragma unroll
+                  for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 0)][q + Q1 * d], v, out[d]); }
+               }
             }
-         }
 #pragma unroll
-         for (int d = 0; d < D1; ++d) { sT1[e * T1E + (f * Q2 + row) * D1 + d] = out[d]; }
+            for (int d = 0; d < D1; ++d) { sT1[e * T1E + (f * Q2 + row) * D1 + d] = out[d]; }
+         }
       }
       __syncthreads();
-      // pass 2: contract qy.  task = (e, f, qz, dx)
-      for (int t = threadIdx.x; t < nel * NF * Q1 * D1; t += blockDim.x)
+      // the staged q-data is consumed: fetch the next batch while passes 2 and 3 run
+      if (batch + gridDim.x < nbatch && threadIdx.x == 0) { issue(batch + gridDim.x); }
+      // pass 2: contract qy.  task = (e, qz, dx), all seven fields
+      for (int t = threadIdx.x; t < nel * Q1 * D1; t += blockDim.x)
       {
-         const int e = t / (NF * Q1 * D1), r = t - e * NF * Q1 * D1, f = r / (Q1 * D1), r2 = r - f * Q1 * D1, qz = r2 / D1, dx = r2 - qz * D1;
-         const double *M = sM[mtype(f, 1)];
-         double out[D1];
+         const int e = t / (Q1 * D1), r2 = t - e * Q1 * D1, qz = r2 / D1, dx = r2 - qz * D1;
 #pragma unroll
-         for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
-#pragma unroll
-         for (int qy = 0; qy < Q1; ++qy)
+         for (int f = 0; f < NF; ++f)
          {
-            const double v = sT1[e * T1E + (f * Q2 + qz * Q1 + qy) * D1 + dx];
+            double out[D1];
 #pragma unroll
-            for (int d = 0; d < D1; ++d) { out[d] = fma(M[qy + Q1 * d], v, out[d]); }
+            for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
+#pragma unroll
+            for (int qy = 0; qy < Q1; ++qy)
+            {
+               const double v = sT1[e * T1E + (f * Q2 + qz * Q1 + qy) * D1 + dx];
+#pragma unroll
+               for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 1)][qy + Q1 * d], v, out[d]); }
+            }
+#pragma unroll
+            for (int dy = 0; dy < D1; ++dy) { sT2[e * T2E + ((f * Q1 + qz) * D1 + dy) * D1 + dx] = out[dy]; }
          }
-#pragma unroll
-         for (int dy = 0; dy < D1; ++dy) { sT2[e * T2E + ((f * Q1 + qz) * D1 + dy) * D1 + dx] = out[dy]; }
       }
       __syncthreads();
-      // pass 3: contract qz and sum the fields.  task = (e, dz, dy, dx)
-      for (int t = threadIdx.x; t < nel * D3; t += blockDim.x)
+      // pass 3: contract qz and sum the fields.  task = (e, dy, dx): all dz at once
+      for (int t = threadIdx.x; t < nel * D1 * D1; t += blockDim.x)
       {
-         const int e = t / D3, l = t - e * D3, dz = l / (D1 * D1), k = l - dz * D1 * D1;
-         double acc = 0.0;
+         const int e = t / (D1 * D1), k = t - e * D1 * D1;
+         double acc[D1];
+#pragma unroll
+         for (int d = 0; d < D1; ++d) { acc[d] = 0.0; }
 #pragma unroll
          for (int f = 0; f < NF; ++f)
          {
             const double w = (f == 1 || f == 2 || f == 4) ? 2.0 : 1.0;
-            const double *M = sM[mtype(f, 2)];
-            double a = 0.0;
 #pragma unroll
-            for (int qz = 0; qz < Q1; ++qz) { a = fma(M[qz + Q1 * dz], sT2[e * T2E + (f * Q1 + qz) * D1 * D1 + k], a); }
-            acc = fma(w, a, acc);
+            for (int qz = 0; qz < Q1; ++qz)
+            {
+               const double v = w * sT2[e * T2E + (f * Q1 + qz) * D1 * D1 + k];
+#pragma unroll
+               for (int dz = 0; dz < D1; ++dz) { acc[dz] = fma(P.M[B200PA_MTYPE(f, 2)][qz + Q1 * dz], v, acc[dz]); }
+            }
          }
-         dE[(e0 + e) * D3 + l] += acc;
+#pragma unroll
+         for (int dz = 0; dz < D1; ++dz) { P.dE[(e0 + e) * D3 + dz * D1 * D1 + k] += acc[dz]; }
       }
       __syncthreads();
    }
+#undef B200PA_MTYPE
 }
 
 // ------------------------------------------------------------------ BLAS-1 etc.
@@ -460,21 +563,10 @@ __global__ void k_constrain_gmap(long long n, const int *__restrict__ gmap, cons
 }
 
 // -------------------------------------------------------------------------- PCG
-// Device-resident scalar state of CGSolver::Mult (linalg/solvers.cpp:869-1050).
-struct PcgState
-{
-   double nom, nom0, den, betanom, r0, alpha, beta;
-   double dot_a, dot_b;       // raw reduction results (before the scalar step / all-reduce)
-   double rel_tol, abs_tol;
-   int iter;                  // the reference's loop variable i
-   int max_iter;
-   int done, converged, final_iter, nonfinite;
-};
-
 // r = b - Ax (Ax passed in r), z = dinv r, d = z, nom partial = d.r    (:875-892)
 __global__ void k_pcg_init(int n, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ r,
                            double *__restrict__ d, const unsigned char *__restrict__ own_mask, double *partials,
-                           unsigned int *ticket, PcgState *st)
+                           unsigned int *ticket, PcgState *st, double *norms_epilogue)
 {
    double acc = 0.0;
    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -485,44 +577,18 @@ __global__ void k_pcg_init(int n, const double *__restrict__ b, const double *__
       d[i] = zi;
       if (!own_mask || own_mask[i]) { acc = fma(zi, ri, acc); }
    }
-   grid_sum(acc, partials, ticket, &st->dot_a);
+   if (grid_sum(acc, partials, ticket, &st->dot_a) && norms_epilogue) { pcg_scalar_init(st, norms_epilogue); }
 }
 
 // scalar step after nom0 = Dot(d, r)   (:892-919)
-__global__ void k_pcg_scalar_init(PcgState *st, double *norms)
-{
-   const double nom = st->dot_a;
-   st->nom = st->nom0 = nom;
-   norms[0] = nom;
-   st->iter = 1;
-   if (!isfinite(nom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
-   if (nom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
-   st->r0 = fmax(nom * st->rel_tol * st->rel_tol, st->abs_tol * st->abs_tol);
-   st->betanom = nom;
-   if (nom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = 0; }
-}
 
 // scalar step after den = Dot(d, z)   (:921-938 first time, :1010-1024 in the loop)
-__global__ void k_pcg_scalar_den(PcgState *st)
-{
-   if (st->done) { return; }
-   const double den = st->dot_b;
-   st->den = den;
-   if (!isfinite(den)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = st->iter - 1; return; }
-   if (den == 0.0)
-   {
-      // before the loop: final_iter = 0; inside: final_iter = i (already incremented)
-      st->done = 1; st->converged = 0; st->final_iter = (st->iter == 1) ? 0 : st->iter;
-      return;
-   }
-   st->alpha = st->nom / den;
-}
 
 // x += alpha d; r -= alpha z; z = dinv r; betanom partial = r.z   (:956-963)
 __global__ void k_pcg_update(int n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
                              const double *__restrict__ d, const double *__restrict__ dinv,
                              const unsigned char *__restrict__ own_mask, double *partials, unsigned int *ticket,
-                             PcgState *st)
+                             PcgState *st, double *norms_epilogue)
 {
    if (st->done) { return; }
    const double alpha = st->alpha;
@@ -536,25 +602,10 @@ __global__ void k_pcg_update(int n, double *__restrict__ x, double *__restrict__
       z[i] = zi;
       if (!own_mask || own_mask[i]) { acc = fma(ri, zi, acc); }
    }
-   grid_sum(acc, partials, ticket, &st->dot_a);
+   if (grid_sum(acc, partials, ticket, &st->dot_a) && norms_epilogue) { pcg_scalar_beta(st, norms_epilogue); }
 }
 
 // scalar step after betanom = Dot(r, z)   (:964-1002)
-__global__ void k_pcg_scalar_beta(PcgState *st, double *norms)
-{
-   if (st->done) { return; }
-   const double betanom = st->dot_a;
-   const int i = st->iter;
-   st->betanom = betanom;
-   norms[i] = betanom;
-   if (!isfinite(betanom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = i; return; }
-   if (betanom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = i; return; }
-   if (betanom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = i; return; }
-   if (i + 1 > st->max_iter) { st->done = 1; st->converged = 0; st->final_iter = st->max_iter; return; }
-   st->iter = i + 1;
-   st->beta = betanom / st->nom;
-   st->nom = betanom; // (:1026; alpha of the next pass uses it)
-}
 
 // d = z + beta d   (:1003)
 __global__ void k_pcg_direction(int n, const double *__restrict__ z, double *__restrict__ d, const PcgState *st)

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include "pa_element_kernel.cuh"
+#include "tma.cuh"
 
 namespace b200pa
 {
@@ -52,10 +53,12 @@ struct ApplyCfg
 #endif
    static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int NIO = (NEB * D3 + NT - 1) / NT;          // gather / scatter items per thread
-   static constexpr int SXS = D2 | 1;                            // slab stride of sXin / sXout
-   // sE strides: see tools/smem_strides.py (searches the conflict-free pads per order)
-   static constexpr int SQ = (D == 3) ? 19 : (Q2 | 1);
-   static constexpr int ES = (D == 3) ? 185 : (3 * D * SQ + ((3 * D * SQ) % 2 == 0 ? 1 : 0));
+   // shared-memory strides found by tools/smem_strides.py (fewest bank-conflict wavefronts over all phases;
+   // conflict-free at p=2): SXS = slab stride of sXin/sXout, SQ = slab stride and ES = element stride of sE
+   static constexpr int SXS = (D == 2) ? 6 : (D == 3) ? 9 : (D == 4) ? 20 : (D == 5) ? 25 : (D == 6) ? 38 : 55;
+   static constexpr int SQ = (D == 2) ? 11 : (D == 3) ? 19 : (D == 4) ? 25 : (D == 5) ? 37 : (D == 6) ? 49 : 71;
+   static constexpr int ES = (D == 2) ? 73 : (D == 3) ? 185 : (D == 4) ? 308 : (D == 5) ? 564 : (D == 6) ? 886 : 1505;
+   static_assert(SXS >= D2 && SQ >= Q2 && ES >= 3 * D * SQ, "strides too small");
    static constexpr int SX_DOUBLES = NEB * D * SXS;
    static constexpr int SE_DOUBLES = NEB * ES;
    // TMA mode: one batch of q-data staged in shared memory, global layout kept ([e][6][Q^3] and [e][Q^3]);
@@ -65,34 +68,6 @@ struct ApplyCfg
    static constexpr int WORK_DOUBLES = ((2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * D) + 1) & ~1;
    static constexpr size_t SMEM_BYTES = sizeof(double) * (WORK_DOUBLES + SQD_DOUBLES + SQM_DOUBLES);
 };
-
-// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-   asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@!p bra WAIT_%=;\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
-{
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                : "memory");
-}
 
 template <int D, int Q, bool DIFF, bool MASS>
 __global__ void __launch_bounds__(ApplyCfg<D, Q>::NT, ApplyCfg<D, Q>::MINB)

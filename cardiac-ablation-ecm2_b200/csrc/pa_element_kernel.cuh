@@ -24,6 +24,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "geometry.cuh"
+
 namespace b200pa
 {
 
@@ -57,6 +59,10 @@ struct ElemParams
    const int *done;                    // PCG early-exit flag (device) or null
    double ca, cb, cT0;                 // QOP_COEFF: a (1 + b (T - T0)); QOP_JOULE: s |grad|^2 + a
    const double *__restrict__ s;       // QOP_JOULE: sigma at q-points [Q^3,NE]
+   // QOP_PHYSGRAD / QOP_JOULE without stored Jacobians (J == null): trilinear geometry from the vertices
+   const double *__restrict__ vtx;     // [3,nv]
+   const int *__restrict__ ev;         // [8,NE]
+   double xi[Q];                       // 1-D Gauss-Legendre points
 };
 
 // launch shape per (D,Q): elements per CTA and threads per CTA
@@ -265,10 +271,20 @@ pa_element_kernel(const __grid_constant__ ElemParams<D, Q> P)
             else if (QOP == QOP_PHYSGRAD || QOP == QOP_JOULE)
             {
                // J^{-T} (gX,gY,gZ): adjugate / det, fem/qinterp/grad.hpp:340-352
-               const double *Je = P.J + eg * 9 * Q3 + q;
-               const double a0 = Je[0 * Q3], a1 = Je[1 * Q3], a2 = Je[2 * Q3];
-               const double a3 = Je[3 * Q3], a4 = Je[4 * Q3], a5 = Je[5 * Q3];
-               const double a6 = Je[6 * Q3], a7 = Je[7 * Q3], a8 = Je[8 * Q3];
+               double a0, a1, a2, a3, a4, a5, a6, a7, a8;
+               if (P.J)
+               {
+                  const double *Je = P.J + eg * 9 * Q3 + q;
+                  a0 = Je[0 * Q3]; a1 = Je[1 * Q3]; a2 = Je[2 * Q3];
+                  a3 = Je[3 * Q3]; a4 = Je[4 * Q3]; a5 = Je[5 * Q3];
+                  a6 = Je[6 * Q3]; a7 = Je[7 * Q3]; a8 = Je[8 * Q3];
+               }
+               else
+               {
+                  double Jm[9];
+                  trilinear_jacobian(P.vtx, P.ev + 8 * eg, P.xi[c % Q], P.xi[c / Q], P.xi[qz], Jm);
+                  a0 = Jm[0]; a1 = Jm[1]; a2 = Jm[2]; a3 = Jm[3]; a4 = Jm[4]; a5 = Jm[5]; a6 = Jm[6]; a7 = Jm[7]; a8 = Jm[8];
+               }
                const double i0 = a4 * a8 - a5 * a7, i1 = a2 * a7 - a1 * a8, i2 = a1 * a5 - a2 * a4;
                const double i3 = a5 * a6 - a3 * a8, i4 = a0 * a8 - a2 * a6, i5 = a2 * a3 - a0 * a5;
                const double i6 = a3 * a7 - a4 * a6, i7 = a1 * a6 - a0 * a7, i8 = a0 * a4 - a1 * a3;

@@ -1,0 +1,45 @@
+"""CPU: bench.py's reference arm (the one leg that may execute oracle/_ref) prints the contract's JSON line,
+and the algorithmic-bytes table of SURVEY.md §8(d) is what bench.py uses for the roofline."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_algorithmic_bytes_match_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    # diff+mass / diff-only bytes per dof for p = 1..6
+    expect = {1: (1596, 1380), 2: (495, 431), 3: (298, 261), 4: (225, 198), 5: (188, 166), 6: (165, 147)}
+    for p, (both, diff) in expect.items():
+        assert abs(bench.algorithmic_bytes_per_dof(p, 7)[0] - both) <= 1.0   # the survey rounds to whole bytes
+        assert abs(bench.algorithmic_bytes_per_dof(p, 6)[0] - diff) <= 1.0
+        tot, elem = bench.algorithmic_bytes_per_dof(p, 7)
+        assert elem == tot - 12
+
+
+def test_reference_arm_json_line():
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
+        pytest.skip("oracle/_ref/ref_driver not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--elems", "12", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GDOF/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("GDOF/s of FP64 PA diffusion+mass apply")
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["dtype"] == "f64"
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                         text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
