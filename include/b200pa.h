@@ -6,8 +6,9 @@
  * interface it replaces (paths relative to the reference tree, stock MFEM 4.9.1-dev).
  * Plain pointers and sizes only; no C++ or torch types.  The reference-side bindings a
  * maintainer adds (C++ subclasses of mfem::DiffusionIntegrator / MassIntegrator / Operator /
- * Solver forwarding to these functions) are shown in INTEGRATION.md and implemented against a
- * mirror of the MFEM interface in cardiac-ablation-ecm2_b200/host/.
+ * Solver forwarding to these functions) are shown in INTEGRATION.md and implemented in
+ * cardiac-ablation-ecm2_b200/host/mfem_b200pa.hpp (compiled against the unmodified reference by
+ * oracle/Makefile, checked on the GPU by tests/test_gpu_mfem_shim.py).
  *
  * Conventions
  *   - every function returns 0 on success, nonzero on error; b200pa_last_error() returns the
@@ -135,7 +136,9 @@ int b200pa_space_destroy(b200pa_space sp);
 int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, const double *J_any,
                               const double *detJ_any);
 /* GeometricFactors::Compute (mesh/mesh.cpp:15220-15273) for trilinear hexes, on the device:
- * vertices f64[3*nv], elem_vertices int32[8*NE] in the reference's hex vertex order. */
+ * vertices f64[3*nv], elem_vertices int32[8*NE] in the reference's hex vertex order.  The space
+ * keeps the vertices and detJ; J[Q^3,3,3,NE] is NOT stored (set-up and q-point kernels rebuild it
+ * per q-point) unless it is asked for through b200pa_space_J(). */
 int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv,
                                         const double *vertices_any, const int *elem_vertices_any);
 /* read-only accessors to the device arrays (for tests and for the host mirror) */
