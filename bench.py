@@ -321,6 +321,8 @@ def main():
                                f"hex {GN[0]}x{GN[1]}x{GN[2]} (N={n}^3 per GPU), order {p}, {global_dofs} dofs",
                    "order": p, "ops": args.ops, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
                    "partition": "x".join(map(str, grid)),
+                   "exchange": ("none" if comm is None else ("peer-memory stores + flags over NVLink (CUDA IPC)" if comm.p2p_enabled()
+                                                             else "NCCL send/recv + all-reduce")),
                    "l2": f"q-data + index streams = {bytes_total * nd / 1e9:.2f} GB per step >> 126 MB L2, no flush needed"},
         "e2e": {"value": global_dofs * Ke / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * nd,
                 "d2h_bytes_per_step": 8 * nd, "ms_per_step": ms_e2e / Ke,

@@ -44,7 +44,7 @@ b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_
 b200pa_form_constrained_mult b200pa_form_mult_phases b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
 b200pa_pcg_solve b200pa_pcg_solve_host
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
-b200pa_comm_owner_mask b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
+b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
 b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
 """.split()
 
@@ -449,6 +449,8 @@ class Form:
         fn = lib().b200pa_pcg_solve_host if host else lib().b200pa_pcg_solve
         check(fn(self.h, _ptr(dinv), _ptr(b), _ptr(x), C.c_double(rel_tol), C.c_double(abs_tol), int(max_iter),
                  C.byref(res), _ptr(norms) if want_norms else None))
+        if getattr(self, "_comm", None) is not None:
+            self._comm.check_p2p()
         return res, (norms[:res.final_iter + 1] if want_norms else None)
 
     def close(self):
@@ -472,10 +474,44 @@ class Comm:
         check(lib().b200pa_comm_unique_id(buf))
         return bytes(buf)
 
-    def set_tables(self, ndofs, nbr_rank, shared_offsets, shared_ldofs):
+    def set_tables(self, ndofs, nbr_rank, shared_offsets, shared_ldofs, p2p=None):
+        """neighbour tables; p2p=None enables the peer-memory path when torch.distributed is initialised
+        (B200PA_NO_P2P=1 keeps NCCL send/recv + all-reduce)"""
         nbr_rank, shared_offsets, shared_ldofs = _i32(nbr_rank), _i32(shared_offsets), _i32(shared_ldofs)
         check(lib().b200pa_comm_set_tables(self.h, ndofs, len(nbr_rank), _ptr(nbr_rank), _ptr(shared_offsets),
                                            _ptr(shared_ldofs)))
+        self._nbr_rank, self._offs = [int(v) for v in nbr_rank], [int(v) for v in shared_offsets]
+        if p2p is None:
+            p2p = os.environ.get("B200PA_NO_P2P", "0") != "1"
+        if p2p and self.nranks > 1:
+            self.enable_p2p()
+
+    def enable_p2p(self):
+        """map every rank's mailbox into every other rank (CUDA IPC) - collective over torch.distributed"""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or self.nranks > 8:
+            return False
+        hbuf = (C.c_ubyte * 64)()
+        check(lib().b200pa_comm_px_prepare(self.h, hbuf))
+        info = [None] * self.nranks
+        dist.all_gather_object(info, (bytes(hbuf), self._nbr_rank, self._offs))
+        handles = (C.c_ubyte * (64 * self.nranks)).from_buffer_copy(b"".join(i[0] for i in info))
+        n = len(self._nbr_rank)
+        roff, rns = (C.c_longlong * max(n, 1))(), (C.c_longlong * max(n, 1))()
+        for k, q in enumerate(self._nbr_rank):
+            qn, qo = info[q][1], info[q][2]
+            idx = qn.index(self.rank)
+            roff[k], rns[k] = qo[idx], qo[len(qn)]
+        check(lib().b200pa_comm_px_connect(self.h, handles, roff, rns))
+        dist.barrier()
+        return True
+
+    def p2p_enabled(self):
+        return bool(lib().b200pa_comm_px_enabled(self.h))
+
+    def check_p2p(self):
+        if lib().b200pa_comm_px_error(self.h):
+            raise B200paError("b200pa: a peer-memory wait timed out (a rank did not take part in the exchange / all-reduce)")
 
     def exchange_sum(self, y):
         check(lib().b200pa_comm_exchange_sum(self.h, _ptr(y)))

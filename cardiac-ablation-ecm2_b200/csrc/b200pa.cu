@@ -916,6 +916,31 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
    const int *off = sp->offsets.as<int>();
    const double *yS = sp->scratchE.as<double>();
    const unsigned char *em = f->ess_mask.as<unsigned char>();
+   if (f->comm && comm_px(f->comm))
+   {
+      // peer-memory path: non-shared dofs are finished by the segmented reduction (constraint + their part of the
+      // dot -> *dot_out); the exchange kernel finishes the shared ones (their part of the dot -> dot_out[1])
+      const unsigned char *shm = comm_shared_mask(f->comm);
+      if (constrained && dot_out)
+      {
+         k_segment_sum_mg<true, true><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, ctx->d_partials, ctx->d_ticket, dot_out, done);
+      }
+      else if (constrained)
+      {
+         k_segment_sum_mg<true, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, nullptr, nullptr, nullptr, done);
+      }
+      else if (dot_out)
+      {
+         k_segment_sum_mg<false, true><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, ctx->d_partials, ctx->d_ticket, dot_out, done);
+      }
+      else
+      {
+         k_segment_sum_mg<false, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, nullptr, nullptr, nullptr, done);
+      }
+      B200PA_LAUNCHED();
+      return comm_exchange_sum_apply(f->comm, y, done, (constrained || dot_out) ? x : nullptr, constrained ? em : nullptr,
+                                     dot_out ? dot_out + 1 : nullptr);
+   }
    if (f->comm)
    {
       // partial sums -> exchange over NVLink -> constrained fix-up + dot in a second pass
@@ -1089,20 +1114,25 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
    k_pcg_init<<<grid, 256, 0, s>>>(n, b_dev, dinv_dev, r, d, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
    B200PA_LAUNCHED();
-   if (!fused_scalars)
+   // multi-GPU: all-reduce + scalar step, one launch over peer memory or NCCL + a 1-thread kernel
+   auto reduce_step = [&](double *val, int step) -> int
    {
-      if (comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
-      k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms);
+      bool handled = false;
+      // peer path: d.Ad arrives in two local parts (non-shared dofs: dot_b, shared dofs: dot_b2)
+      const double *extra = (step == 3 && comm_px(f->comm)) ? &st->dot_b2 : nullptr;
+      if (comm_allreduce_scalar_step(f->comm, val, step, st, norms, &handled, extra)) { return 1; }
+      if (handled) { return 0; }
+      if (comm_allreduce_sum_dev(f->comm, val, 1)) { return 1; }
+      if (step == 1) { k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms); }
+      else if (step == 2) { k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms); }
+      else { k_pcg_scalar_den<<<1, 1, 0, s>>>(st); }
       B200PA_LAUNCHED();
-   }
+      return 0;
+   };
+   if (!fused_scalars && reduce_step(&st->dot_a, 1)) { return 1; }
    // z = A d; den = (z, d)                                                   (:921-938)
    if (form_apply(f, d, z, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
-   if (!fused_scalars)
-   {
-      if (comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
-      k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
-      B200PA_LAUNCHED();
-   }
+   if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
 
    // the loop (:952-1027).  Scalars stay on the device; the host only polls `done` every few
    // iterations (kernels after convergence return immediately on the flag).
@@ -1113,21 +1143,11 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    {
       k_pcg_update<<<grid, 256, 0, s>>>(n, x_dev, r, z, d, dinv_dev, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
       B200PA_LAUNCHED();
-      if (!fused_scalars)
-      {
-         if (comm_allreduce_sum_dev(f->comm, &st->dot_a, 1)) { return 1; }
-         k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms);
-         B200PA_LAUNCHED();
-      }
+      if (!fused_scalars && reduce_step(&st->dot_a, 2)) { return 1; }
       k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st);
       B200PA_LAUNCHED();
       if (form_apply(f, d, z, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
-      if (!fused_scalars)
-      {
-         if (comm_allreduce_sum_dev(f->comm, &st->dot_b, 1)) { return 1; }
-         k_pcg_scalar_den<<<1, 1, 0, s>>>(st);
-         B200PA_LAUNCHED();
-      }
+      if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
       if (it % poll == 0)
       {
          B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));

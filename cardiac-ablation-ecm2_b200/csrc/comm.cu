@@ -21,6 +21,8 @@
 #include <map>
 
 #include "comm.cuh"
+#include "pcg_state.cuh"
+#include "reduce.cuh"
 
 namespace
 {
@@ -108,6 +110,161 @@ __global__ void k_unpack(int ns, const int *__restrict__ sh_ldof, const int *__r
       y[l] = v;
    }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Peer-memory path (NVLink 5 / NVSwitch, one process per GPU, buffers mapped with CUDA IPC): the shared-dof
+// exchange and the scalar all-reduce are done by the kernels themselves with stores into the peers'
+// mailboxes and release/acquire flags - no NCCL call (and no NCCL launch latency) inside the PCG loop.
+//   mailbox of rank r (device memory of r, mapped by every peer):
+//     flags_x [nranks] u64   epoch of the last exchange whose data from rank s has landed in r
+//     flags_ar[nranks] u64   epoch of the last all-reduce contribution of rank s
+//     ar_slot [2][nranks][4] f64   all-reduce contributions, by epoch parity
+//     recv    [2][n_send(r)] f64   exchange data, by epoch parity, laid out like r's NCCL receive buffer
+// A rank cannot get two epochs ahead of a peer (it needs that peer's data of the current epoch to finish
+// it), so two parities suffice.  Spins are bounded: on time-out the kernel raises an error word the host
+// checks, instead of hanging the GPU.
+constexpr int PX_AR_MAX = 4;
+constexpr unsigned long long PX_SPIN_LIMIT = 1ull << 26;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p)
+{
+   double v;
+   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long epoch, int *err)
+{
+   for (unsigned long long it = 0; it < PX_SPIN_LIMIT; ++it)
+   {
+      if (ld_acquire_sys(flag) >= epoch) { return true; }
+      __nanosleep(64);
+   }
+   atomicExch(err, 1);
+   return false;
+}
+
+struct PxPeers
+{
+   double *recv[26];               // per neighbour: where this rank's block starts in the neighbour's recv area (parity 0)
+   long long parity_stride[26];    // n_send of the neighbour (doubles)
+   unsigned long long *flag[26];   // the neighbour's flags_x[my rank]
+   int off[27];                    // this rank's send offsets per neighbour
+   int nbr_rank[26];
+   int n_nbr;
+};
+
+// pack + send: y[shared ldofs] -> straight into the neighbours' mailboxes; the last block to finish
+// publishes the epoch to every neighbour
+__global__ void k_px_send(int n, const int *__restrict__ ldof, const unsigned char *__restrict__ nbr_of, const double *__restrict__ y,
+                          const __grid_constant__ PxPeers P, unsigned long long epoch, unsigned int *ticket, const int *done)
+{
+   if (done && *done) { return; }
+   const int par = (int)(epoch & 1ull);
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      const int k = nbr_of[i];
+      P.recv[k][par * P.parity_stride[k] + (i - P.off[k])] = y[ldof[i]];
+   }
+   __threadfence_system();
+   __shared__ bool last;
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+      last = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (last)
+   {
+      __threadfence_system();
+      if (threadIdx.x < P.n_nbr) { st_release_sys(P.flag[threadIdx.x], epoch); }
+   }
+}
+
+// wait for every neighbour's data of this epoch, then the ascending-rank sum (as k_unpack)
+// Optional epilogue for the operator apply (x != null): ConstrainedOperator fix-up of the shared dofs and their
+// owned part of the dot x.y, reduced deterministically into *dot_out.
+__global__ void k_px_recv(int ns, const int *__restrict__ sh_ldof, const int *__restrict__ sh_off, const int *__restrict__ sh_src,
+                          const double *recv, double *__restrict__ y, int owner_only, const unsigned long long *my_flags,
+                          const __grid_constant__ PxPeers P, unsigned long long epoch, int *err, const int *done,
+                          const double *__restrict__ x, const unsigned char *__restrict__ ess_mask,
+                          const unsigned char *__restrict__ own_mask, double *partials, unsigned int *ticket, double *dot_out)
+{
+   if (done && *done) { return; }
+   if (threadIdx.x < P.n_nbr) { spin_until(my_flags + P.nbr_rank[threadIdx.x], epoch, err); }
+   __syncthreads();
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x)
+   {
+      const int l = sh_ldof[i];
+      const double own = y[l];
+      const int j0 = sh_off[i], j1 = owner_only ? j0 + 1 : sh_off[i + 1];
+      double v = 0.0;
+      for (int j = j0; j < j1; ++j)
+      {
+         const int s = sh_src[j];
+         v += s < 0 ? own : ld_relaxed_sys_f64(recv + s);
+      }
+      if (x)
+      {
+         if (ess_mask && ess_mask[l]) { v = x[l]; }
+         if (dot_out && own_mask[l]) { acc = fma(x[l], v, acc); }
+      }
+      y[l] = v;
+   }
+   if (x && dot_out) { b200pa::grid_sum(acc, partials, ticket, dot_out); }
+}
+
+struct PxAll
+{
+   double *slot[8];                // rank t's ar_slot base
+   unsigned long long *flag[8];    // rank t's flags_ar
+   int nranks, rank;
+};
+
+// all-reduce (sum, n <= 4 doubles) by peer stores: every rank writes its contribution into everybody's slot,
+// waits for everybody's, and adds them in rank order -> bit-identical result on all ranks
+// epilogue: 0 none, 1/2/3 = the PCG scalar step that consumes the reduced value (init / beta / den)
+__global__ void k_px_allreduce(double *vals, int n, const __grid_constant__ PxAll P, const double *my_slots,
+                               const unsigned long long *my_flags, unsigned long long epoch, int *err, int epilogue,
+                               b200pa::PcgState *st, double *norms, const double *extra)
+{
+   if (epilogue >= 2 && st->done) { return; } // every rank holds the same scalars: all skip together
+   if (extra && threadIdx.x == 0) { vals[0] += extra[0]; } // second local partial (shared dofs) of the same dot
+   __syncthreads();
+   const int t = threadIdx.x, par = (int)(epoch & 1ull);
+   if (t < P.nranks)
+   {
+      double *dst = P.slot[t] + ((size_t)par * P.nranks + P.rank) * PX_AR_MAX;
+      for (int k = 0; k < n; ++k) { dst[k] = vals[k]; }
+      __threadfence_system();
+      st_release_sys(P.flag[t] + P.rank, epoch);
+      spin_until(my_flags + t, epoch, err);
+   }
+   __syncthreads();
+   if (t < n)
+   {
+      double s = 0.0;
+      for (int r = 0; r < P.nranks; ++r) { s += ld_relaxed_sys_f64(my_slots + ((size_t)par * P.nranks + r) * PX_AR_MAX + t); }
+      vals[t] = s;
+   }
+   if (epilogue && t == 0) // n == 1: thread 0 wrote vals[0] itself
+   {
+      if (epilogue == 1) { b200pa::pcg_scalar_init(st, norms); }
+      else if (epilogue == 2) { b200pa::pcg_scalar_beta(st, norms); }
+      else { b200pa::pcg_scalar_den(st); }
+   }
+}
 } // namespace
 
 struct b200pa_comm_s
@@ -118,6 +275,15 @@ struct b200pa_comm_s
    int ndofs = 0, n_nbr = 0, n_send = 0, n_shared = 0;
    std::vector<int> nbr_rank, nbr_off;
    b200pa::DevBuf send_ldof, sendbuf, recvbuf, sh_ldof, sh_off, sh_src, owner_mask;
+   // peer-memory path
+   bool px = false;
+   void *mailbox = nullptr;                  // cudaMalloc'ed (IPC-exportable)
+   size_t mb_flags_x = 0, mb_flags_ar = 0, mb_slots = 0, mb_recv = 0, mb_bytes = 0; // byte offsets
+   std::vector<void *> peer_mb;              // opened peer mailboxes (own entry = mailbox)
+   b200pa::DevBuf send_nbr, px_err, px_ticket, shared_mask;
+   PxPeers peers{};
+   PxAll all{};
+   unsigned long long epoch_x = 0, epoch_ar = 0;
 };
 
 using namespace b200pa;
@@ -152,6 +318,12 @@ extern "C" int b200pa_comm_destroy(b200pa_comm c)
    if (!c) { return 0; }
    cudaSetDevice(c->ctx->device);
    cudaStreamSynchronize(c->ctx->stream);
+   for (size_t r = 0; r < c->peer_mb.size(); ++r)
+   {
+      if (c->peer_mb[r] && (int)r != c->rank) { cudaIpcCloseMemHandle(c->peer_mb[r]); }
+   }
+   if (c->mailbox) { cudaFree(c->mailbox); }
+   c->send_nbr.release(); c->px_err.release(); c->px_ticket.release(); c->shared_mask.release();
    if (c->nccl) { g_nccl.CommDestroy(c->nccl); }
    for (DevBuf *b : {&c->send_ldof, &c->sendbuf, &c->recvbuf, &c->sh_ldof, &c->sh_off, &c->sh_src, &c->owner_mask}) { b->release(); }
    delete c;
@@ -257,6 +429,9 @@ extern "C" int b200pa_comm_set_tables(b200pa_comm c, int ndofs, int n_nbr, const
       return 1;
    }
    if (alloc(c->sendbuf, sizeof(double) * (size_t)std::max(n_send, 1)) || alloc(c->recvbuf, sizeof(double) * (size_t)std::max(n_send, 1))) { return 1; }
+   std::vector<unsigned char> shm(std::max(ndofs, 1), 0);
+   for (int i = 0; i < ns; ++i) { shm[sh_ldof[i]] = 1; }
+   if (up(c->shared_mask, shm.data(), (size_t)ndofs)) { return 1; }
    B200PA_CK(cudaStreamSynchronize(ctx->stream));
    return 0;
 }
@@ -265,13 +440,35 @@ namespace b200pa
 {
 const unsigned char *comm_owner_mask(b200pa_comm c) { return c->owner_mask.as<unsigned char>(); }
 
-static int exchange(b200pa_comm c, double *y, int owner_only, const int *done)
+struct ApplyEpilogue
+{
+   const double *x = nullptr;
+   const unsigned char *ess_mask = nullptr;
+   double *dot_out = nullptr;
+};
+
+static int exchange(b200pa_comm c, double *y, int owner_only, const int *done, const ApplyEpilogue &ep = ApplyEpilogue())
 {
    b200pa_ctx ctx = c->ctx;
    if (c->n_send == 0) { return 0; }
    const int bs = 256;
    int g = (c->n_send + bs - 1) / bs;
    g = std::min(g, ctx->num_sms * 8);
+   if (c->px)
+   {
+      const unsigned long long epoch = ++c->epoch_x;
+      const char *mb = (const char *)c->mailbox;
+      k_px_send<<<g, bs, 0, ctx->stream>>>(c->n_send, c->send_ldof.as<int>(), c->send_nbr.as<unsigned char>(), y, c->peers, epoch,
+                                           c->px_ticket.as<unsigned int>(), done);
+      B200PA_LAUNCHED();
+      const int g2 = std::max(1, std::min((c->n_shared + bs - 1) / bs, ctx->num_sms * 8));
+      const double *recv = (const double *)(mb + c->mb_recv) + (size_t)(epoch & 1ull) * (size_t)c->n_send;
+      k_px_recv<<<g2, bs, 0, ctx->stream>>>(c->n_shared, c->sh_ldof.as<int>(), c->sh_off.as<int>(), c->sh_src.as<int>(), recv, y, owner_only,
+                                            (const unsigned long long *)(mb + c->mb_flags_x), c->peers, epoch, c->px_err.as<int>(), done,
+                                            ep.x, ep.ess_mask, c->owner_mask.as<unsigned char>(), ctx->d_partials, ctx->d_ticket, ep.dot_out);
+      B200PA_LAUNCHED();
+      return 0;
+   }
    k_pack<<<g, bs, 0, ctx->stream>>>(c->n_send, c->send_ldof.as<int>(), y, c->sendbuf.as<double>(), done);
    B200PA_LAUNCHED();
    NCCL_CK(g_nccl.GroupStart());
@@ -291,15 +488,140 @@ static int exchange(b200pa_comm c, double *y, int owner_only, const int *done)
 }
 
 int comm_exchange_sum(b200pa_comm c, double *y, const int *done) { return exchange(c, y, 0, done); }
+bool comm_px(b200pa_comm c) { return c && c->px; }
+const unsigned char *comm_shared_mask(b200pa_comm c) { return c->shared_mask.as<unsigned char>(); }
+// peer path only: exchange + constraint fix-up of the shared dofs + their owned part of x.y -> *dot_out
+int comm_exchange_sum_apply(b200pa_comm c, double *y, const int *done, const double *x, const unsigned char *ess_mask, double *dot_out)
+{
+   ApplyEpilogue ep;
+   ep.x = x; ep.ess_mask = ess_mask; ep.dot_out = dot_out;
+   return exchange(c, y, 0, done, ep);
+}
 int comm_exchange_owner(b200pa_comm c, double *x) { return exchange(c, x, 1, nullptr); }
+
+// all-reduce of one PCG dot + the scalar step that follows it, in one launch (peer-memory path only;
+// returns 0 and does nothing when that path is off, the caller then uses the NCCL all-reduce + a scalar kernel)
+int comm_allreduce_scalar_step(b200pa_comm c, double *val, int step, void *pcg_state, double *norms, bool *handled,
+                               const double *extra)
+{
+   *handled = false;
+   if (!c->px || c->nranks == 1) { return 0; }
+   const unsigned long long epoch = ++c->epoch_ar;
+   const char *mb = (const char *)c->mailbox;
+   k_px_allreduce<<<1, 32, 0, c->ctx->stream>>>(val, 1, c->all, (const double *)(mb + c->mb_slots),
+                                               (const unsigned long long *)(mb + c->mb_flags_ar), epoch, c->px_err.as<int>(), step,
+                                               (PcgState *)pcg_state, norms, extra);
+   B200PA_LAUNCHED();
+   *handled = true;
+   return 0;
+}
 
 int comm_allreduce_sum_dev(b200pa_comm c, double *vals, int n)
 {
    if (c->nranks == 1) { return 0; }
+   if (c->px && n <= PX_AR_MAX)
+   {
+      const unsigned long long epoch = ++c->epoch_ar;
+      const char *mb = (const char *)c->mailbox;
+      k_px_allreduce<<<1, 32, 0, c->ctx->stream>>>(vals, n, c->all, (const double *)(mb + c->mb_slots),
+                                                  (const unsigned long long *)(mb + c->mb_flags_ar), epoch, c->px_err.as<int>(), 0, nullptr,
+                                                  nullptr, nullptr);
+      B200PA_LAUNCHED();
+      return 0;
+   }
    NCCL_CK(g_nccl.AllReduce(vals, vals, (size_t)n, ncclFloat64, ncclSum, c->nccl, c->ctx->stream));
    return 0;
 }
 } // namespace b200pa
+
+// ---- peer-memory set-up (two steps around one host-side all-gather of the handles and neighbour tables)
+extern "C" int b200pa_comm_px_prepare(b200pa_comm c, unsigned char handle_out[64])
+{
+   B200PA_REQUIRE(c && handle_out, "comm_px_prepare: NULL argument");
+   B200PA_REQUIRE(c->nranks <= 8 && c->n_nbr <= 26, "comm_px_prepare: peer path supports up to 8 ranks / 26 neighbours");
+   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+   b200pa_ctx ctx = c->ctx;
+   B200PA_CK(cudaSetDevice(ctx->device));
+   if (!c->mailbox)
+   {
+      auto up256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+      c->mb_flags_x = 0;
+      c->mb_flags_ar = up256(c->mb_flags_x + sizeof(unsigned long long) * c->nranks);
+      c->mb_slots = up256(c->mb_flags_ar + sizeof(unsigned long long) * c->nranks);
+      c->mb_recv = up256(c->mb_slots + sizeof(double) * 2 * c->nranks * PX_AR_MAX);
+      c->mb_bytes = up256(c->mb_recv + sizeof(double) * 2 * (size_t)std::max(c->n_send, 1));
+      B200PA_CK(cudaMalloc(&c->mailbox, c->mb_bytes));
+      B200PA_CK(cudaMemset(c->mailbox, 0, c->mb_bytes));
+      B200PA_CK(cudaDeviceSynchronize());
+   }
+   cudaIpcMemHandle_t h;
+   B200PA_CK(cudaIpcGetMemHandle(&h, c->mailbox));
+   std::memcpy(handle_out, &h, 64);
+   return 0;
+}
+
+// handles: nranks x 64 bytes (rank order); for every neighbour k (this rank's order): remote_off[k] = where the
+// neighbour expects this rank's block in its receive area, remote_nsend[k] = the neighbour's total send count
+extern "C" int b200pa_comm_px_connect(b200pa_comm c, const unsigned char *handles, const long long *remote_off,
+                                      const long long *remote_nsend)
+{
+   B200PA_REQUIRE(c && handles && (c->n_nbr == 0 || (remote_off && remote_nsend)), "comm_px_connect: NULL argument");
+   B200PA_REQUIRE(c->mailbox, "comm_px_connect: call b200pa_comm_px_prepare first");
+   b200pa_ctx ctx = c->ctx;
+   B200PA_CK(cudaSetDevice(ctx->device));
+   c->peer_mb.assign(c->nranks, nullptr);
+   for (int r = 0; r < c->nranks; ++r)
+   {
+      if (r == c->rank) { c->peer_mb[r] = c->mailbox; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + 64 * (size_t)r, 64);
+      B200PA_CK(cudaIpcOpenMemHandle(&c->peer_mb[r], h, cudaIpcMemLazyEnablePeerAccess));
+   }
+   // layout is the same function of (nranks, n_send) on every rank; only the recv offset depends on the peer's n_send,
+   // and that offset (mb_recv) depends on nranks only
+   std::vector<unsigned char> nbr_of((size_t)std::max(c->n_send, 1));
+   PxPeers &P = c->peers;
+   P.n_nbr = c->n_nbr;
+   for (int k = 0; k < c->n_nbr; ++k)
+   {
+      char *pm = (char *)c->peer_mb[c->nbr_rank[k]];
+      P.recv[k] = (double *)(pm + c->mb_recv) + remote_off[k];
+      P.parity_stride[k] = remote_nsend[k];
+      P.flag[k] = (unsigned long long *)(pm + c->mb_flags_x) + c->rank;
+      P.off[k] = c->nbr_off[k];
+      P.nbr_rank[k] = c->nbr_rank[k];
+      for (int i = c->nbr_off[k]; i < c->nbr_off[k + 1]; ++i) { nbr_of[i] = (unsigned char)k; }
+   }
+   P.off[c->n_nbr] = c->n_send;
+   PxAll &A = c->all;
+   A.nranks = c->nranks; A.rank = c->rank;
+   for (int r = 0; r < c->nranks; ++r)
+   {
+      char *pm = (char *)c->peer_mb[r];
+      A.slot[r] = (double *)(pm + c->mb_slots);
+      A.flag[r] = (unsigned long long *)(pm + c->mb_flags_ar);
+   }
+   if (alloc(c->send_nbr, nbr_of.size()) || alloc(c->px_err, sizeof(int)) || alloc(c->px_ticket, sizeof(unsigned int))) { return 1; }
+   B200PA_CK(cudaMemcpy(c->send_nbr.p, nbr_of.data(), nbr_of.size(), cudaMemcpyHostToDevice));
+   B200PA_CK(cudaMemset(c->px_err.p, 0, sizeof(int)));
+   B200PA_CK(cudaMemset(c->px_ticket.p, 0, sizeof(unsigned int)));
+   B200PA_CK(cudaDeviceSynchronize());
+   c->px = true;
+   return 0;
+}
+
+// 0 = no error; nonzero = a peer wait timed out since the last query (clears the flag).  Synchronises the stream.
+extern "C" int b200pa_comm_px_error(b200pa_comm c)
+{
+   if (!c || !c->px) { return 0; }
+   int h = 0;
+   cudaSetDevice(c->ctx->device);
+   cudaMemcpyAsync(&h, c->px_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->ctx->stream);
+   cudaStreamSynchronize(c->ctx->stream);
+   if (h) { cudaMemsetAsync(c->px_err.p, 0, sizeof(int), c->ctx->stream); }
+   return h;
+}
+extern "C" int b200pa_comm_px_enabled(b200pa_comm c) { return c && c->px ? 1 : 0; }
 
 extern "C" int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev)
 {

@@ -11,4 +11,11 @@ const unsigned char *comm_owner_mask(b200pa_comm c);
 int comm_exchange_sum(b200pa_comm c, double *yL_dev, const int *done);
 int comm_exchange_owner(b200pa_comm c, double *xL_dev);
 int comm_allreduce_sum_dev(b200pa_comm c, double *vals_dev, int n);
+// step: 1 init, 2 beta, 3 den (PCG scalar steps); *handled = false -> peer path off, nothing was launched
+int comm_allreduce_scalar_step(b200pa_comm c, double *val_dev, int step, void *pcg_state, double *norms, bool *handled,
+                               const double *extra_dev = nullptr);
+bool comm_px(b200pa_comm c);
+const unsigned char *comm_shared_mask(b200pa_comm c);
+int comm_exchange_sum_apply(b200pa_comm c, double *yL_dev, const int *done, const double *x_dev, const unsigned char *ess_mask,
+                            double *dot_out);
 } // namespace b200pa

@@ -5,55 +5,12 @@
 #include <cuda_runtime.h>
 
 #include "geometry.cuh"
+#include "pcg_state.cuh"
+#include "reduce.cuh"
 #include "tma.cuh"
 
 namespace b200pa
 {
-
-// ------------------------------------------------------------------ reductions
-// Deterministic: fixed shuffle tree per block, block partials summed in a fixed order by the
-// last block to finish (ticket counter).  ≙ general/reducers.hpp:451-592 without the host join.
-__device__ __forceinline__ double block_sum(double v)
-{
-   __shared__ double ws[32];
-   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-   for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); }
-   if (lane == 0) { ws[w] = v; }
-   __syncthreads();
-   if (w == 0)
-   {
-      v = lane < nw ? ws[lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); }
-   }
-   return v; // valid in thread 0
-}
-
-// returns true in thread 0 of the last block to finish, after *out has been written: the place to run a
-// scalar epilogue without another launch
-__device__ __forceinline__ bool grid_sum(double v, double *partials, unsigned int *ticket, double *out)
-{
-   const double bs = block_sum(v);
-   __shared__ bool last;
-   if (threadIdx.x == 0)
-   {
-      partials[blockIdx.x] = bs;
-      __threadfence();
-      const unsigned int t = atomicInc(ticket, gridDim.x - 1); // wraps back to 0: self-resetting
-      last = (t == gridDim.x - 1);
-   }
-   __syncthreads();
-   if (last)
-   {
-      __threadfence();
-      double s = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { s += ((volatile double *)partials)[i]; }
-      s = block_sum(s);
-      if (threadIdx.x == 0) { *out = s; return true; }
-   }
-   return false;
-}
 
 __global__ void k_dot(long long n, const double *__restrict__ a, const double *__restrict__ b,
                       double *partials, unsigned int *ticket, double *out)
@@ -64,64 +21,6 @@ __global__ void k_dot(long long n, const double *__restrict__ a, const double *_
       s = fma(a[i], b[i], s);
    }
    grid_sum(s, partials, ticket, out);
-}
-
-// Device-resident scalar state of CGSolver::Mult (linalg/solvers.cpp:869-1050).
-struct PcgState
-{
-   double nom, nom0, den, betanom, r0, alpha, beta;
-   double dot_a, dot_b;       // raw reduction results (before the scalar step / all-reduce)
-   double rel_tol, abs_tol;
-   int iter;                  // the reference's loop variable i
-   int max_iter;
-   int done, converged, final_iter, nonfinite;
-};
-
-
-// the scalar steps of the loop; run either as the epilogue of the reduction that produced their input
-// (single GPU) or as 1-thread kernels after the all-reduce (multi-GPU)
-__device__ __forceinline__ void pcg_scalar_init(PcgState *st, double *norms)
-{
-   const double nom = st->dot_a;
-   st->nom = st->nom0 = nom;
-   norms[0] = nom;
-   st->iter = 1;
-   if (!isfinite(nom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
-   if (nom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; st->betanom = nom; return; }
-   st->r0 = fmax(nom * st->rel_tol * st->rel_tol, st->abs_tol * st->abs_tol);
-   st->betanom = nom;
-   if (nom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = 0; }
-}
-
-__device__ __forceinline__ void pcg_scalar_den(PcgState *st)
-{
-   if (st->done) { return; }
-   const double den = st->dot_b;
-   st->den = den;
-   if (!isfinite(den)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = st->iter - 1; return; }
-   if (den == 0.0)
-   {
-      // before the loop: final_iter = 0; inside: final_iter = i (already incremented)
-      st->done = 1; st->converged = 0; st->final_iter = (st->iter == 1) ? 0 : st->iter;
-      return;
-   }
-   st->alpha = st->nom / den;
-}
-
-__device__ __forceinline__ void pcg_scalar_beta(PcgState *st, double *norms)
-{
-   if (st->done) { return; }
-   const double betanom = st->dot_a;
-   const int i = st->iter;
-   st->betanom = betanom;
-   norms[i] = betanom;
-   if (!isfinite(betanom)) { st->nonfinite = 1; st->done = 1; st->converged = 0; st->final_iter = i; return; }
-   if (betanom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = i; return; }
-   if (betanom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = i; return; }
-   if (i + 1 > st->max_iter) { st->done = 1; st->converged = 0; st->final_iter = st->max_iter; return; }
-   st->iter = i + 1;
-   st->beta = betanom / st->nom;
-   st->nom = betanom; // (:1026; alpha of the next pass uses it)
 }
 
 __global__ void k_pcg_scalar_init(PcgState *st, double *norms) { pcg_scalar_init(st, norms); }
@@ -185,6 +84,31 @@ __global__ void k_segment_sum(int ndofs, const int *__restrict__ offsets, const 
       // den = (d, A d) is complete: alpha / termination logic right here (linalg/solvers.cpp:1010-1024)
       if (grid_sum(acc, partials, ticket, dot_out) && st_epilogue) { pcg_scalar_den(st_epilogue); }
    }
+}
+
+// multi-GPU with the peer-memory exchange: shared dofs only get their local partial sum here (the exchange
+// kernel finishes them: remote contributions, constraint, their part of the dot); everything else is final
+template <bool CONSTR, bool DOT>
+__global__ void k_segment_sum_mg(int ndofs, const int *__restrict__ offsets, const double *__restrict__ yS, double *__restrict__ y,
+                                 const unsigned char *__restrict__ ess_mask, const double *__restrict__ x,
+                                 const unsigned char *__restrict__ shared_mask, double *partials, unsigned int *ticket,
+                                 double *dot_out, const int *done_flag)
+{
+   if (done_flag && *done_flag) { return; }
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ndofs; i += gridDim.x * blockDim.x)
+   {
+      double v = 0.0;
+      const int j1 = offsets[i + 1];
+      for (int j = offsets[i]; j < j1; ++j) { v += yS[j]; }
+      if (!shared_mask[i])
+      {
+         if (CONSTR && ess_mask[i]) { v = x[i]; }
+         if (DOT) { acc = fma(x[i], v, acc); }
+      }
+      y[i] = v;
+   }
+   if (DOT) { grid_sum(acc, partials, ticket, dot_out); }
 }
 
 // multi-GPU second pass after the shared-dof exchange: ConstrainedOperator fix-up and the

@@ -240,6 +240,20 @@ int b200pa_comm_build_tables(int rank, int ndofs, int n_nbr, const int *nbr_rank
                              const int *shared_ldofs, int *n_shared_out, int *sh_ldof, int *sh_off, int *sh_src,
                              unsigned char *owner_mask);
 const unsigned char *b200pa_comm_owner_mask(b200pa_comm c);   /* device pointer */
+/* Peer-memory path over NVLink / NVSwitch (optional, after set_tables): the exchange and the scalar
+ * all-reduce are then done by kernels that store straight into the peers' mailboxes (CUDA IPC mapped)
+ * and synchronise with release/acquire flags - no NCCL call inside the PCG loop.
+ *   1. every rank: b200pa_comm_px_prepare -> 64-byte cudaIpcMemHandle of its mailbox
+ *   2. host application all-gathers (handle, nbr_rank[], shared_offsets[]) of every rank
+ *   3. every rank: b200pa_comm_px_connect(handles[nranks*64], remote_off[n_nbr], remote_nsend[n_nbr]) where,
+ *      for neighbour k = rank q, remote_off[k] = q's shared_offsets[index of this rank in q's nbr_rank] and
+ *      remote_nsend[k] = q's shared_offsets[q's n_nbr]
+ * Waits are bounded; b200pa_comm_px_error() returns nonzero (and clears it) if one timed out. */
+int b200pa_comm_px_prepare(b200pa_comm c, unsigned char handle_out[64]);
+int b200pa_comm_px_connect(b200pa_comm c, const unsigned char *handles, const long long *remote_off,
+                           const long long *remote_nsend);
+int b200pa_comm_px_error(b200pa_comm c);
+int b200pa_comm_px_enabled(b200pa_comm c);
 int b200pa_form_set_comm(b200pa_form f, b200pa_comm c);
 /* (P P^T) y: every copy of a shared dof <- sum of all copies.  (P R) x: <- the owner's value. */
 int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev);

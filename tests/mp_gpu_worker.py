@@ -87,8 +87,9 @@ def main():
         low[gl[r]] = np.minimum(low[gl[r]], r)
     assert np.array_equal(ctx.to_host(v), xg[gid] + low[gid])
     dist.barrier()
+    comm.check_p2p()
     if rank == 0:
-        print(f"MULTI_OK world={world} p={p} apply={e1:.2e} diag={e2:.2e} pcg={e3:.2e} its={r2.final_iter}/{rs2.final_iter}", flush=True)
+        print(f"MULTI_OK world={world} p={p} p2p={comm.p2p_enabled()} apply={e1:.2e} diag={e2:.2e} pcg={e3:.2e} its={r2.final_iter}/{rs2.final_iter}", flush=True)
     f.close(); sp.close(); fs.close(); sps.close(); comm.close(); ctx.close()
     dist.destroy_process_group()
 
