@@ -44,7 +44,7 @@ b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_
 b200pa_form_constrained_mult b200pa_form_mult_phases b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
 b200pa_pcg_solve b200pa_pcg_solve_host
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
-b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
+b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_comm_px_disable b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
 b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
 """.split()
 
@@ -502,7 +502,12 @@ class Comm:
             qn, qo = info[q][1], info[q][2]
             idx = qn.index(self.rank)
             roff[k], rns[k] = qo[idx], qo[len(qn)]
-        check(lib().b200pa_comm_px_connect(self.h, handles, roff, rns))
+        ok = lib().b200pa_comm_px_connect(self.h, handles, roff, rns) == 0
+        oks = [None] * self.nranks
+        dist.all_gather_object(oks, ok)          # all ranks take the same decision
+        if not all(oks):
+            lib().b200pa_comm_px_disable(self.h)  # NCCL send/recv + all-reduce stay in place
+            return False
         dist.barrier()
         return True
 

@@ -622,6 +622,12 @@ extern "C" int b200pa_comm_px_error(b200pa_comm c)
    return h;
 }
 extern "C" int b200pa_comm_px_enabled(b200pa_comm c) { return c && c->px ? 1 : 0; }
+// back to the NCCL transport (collective decision of the host application, e.g. when one rank could not map a peer)
+extern "C" int b200pa_comm_px_disable(b200pa_comm c)
+{
+   if (c) { c->px = false; }
+   return 0;
+}
 
 extern "C" int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev)
 {

@@ -254,6 +254,7 @@ int b200pa_comm_px_connect(b200pa_comm c, const unsigned char *handles, const lo
                            const long long *remote_nsend);
 int b200pa_comm_px_error(b200pa_comm c);
 int b200pa_comm_px_enabled(b200pa_comm c);
+int b200pa_comm_px_disable(b200pa_comm c);   /* back to NCCL; must be called on every rank */
 int b200pa_form_set_comm(b200pa_form f, b200pa_comm c);
 /* (P P^T) y: every copy of a shared dof <- sum of all copies.  (P R) x: <- the owner's value. */
 int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev);

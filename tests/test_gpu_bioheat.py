@@ -147,3 +147,35 @@ def test_config2_norm_matches_reference_probe(ctx):
     assert abs(np.linalg.norm(d) - 36.909814340923262) <= 1e-12 * 36.909814340923262
     f.close()
     sp.close()
+
+
+@pytest.mark.parametrize("p,n", [(1, 40), (2, 48), (3, 24), (4, 16), (6, 9)])
+def test_bitwise_reproducible(ctx, p, n):
+    """compute-sanitizer is closed on the GPU pool, so race-freedom of the shared-memory phases, the TMA staging
+    and the atomic-free reductions is pinned the other way round: the apply, the diagonal and a 12-iteration PCG
+    are bitwise identical run to run (deterministic reductions; a race shows up as a flipped bit)."""
+    import torch
+    m, b, sp = build(ctx, p, n)
+    nd = m["ndofs"]
+    f = b200pa.Form(sp)
+    T0 = ctx.to_dev(37.0 + np.random.default_rng(3).random(nd))
+    f.assemble_diffusion(sp.coeff_linear(0.5, 0.02, 37.0, T0))
+    f.assemble_mass(np.array([3.6]))
+    f.set_essential(b200pa.essential_dofs(m["bdr_attr"], [1, 6]))
+    x = ctx.to_dev(np.random.default_rng(4).random(nd))
+    dinv = f.jacobi()
+    ref = None
+    for rep in range(3):
+        y = f.constrained_mult(x)
+        d = f.assemble_diagonal()
+        X = ctx.zeros(nd)
+        res, norms = f.pcg(dinv, x, X, 0.0, 0.0, 12)
+        ctx.sync()
+        cur = (y.clone(), d.clone(), X.clone(), norms.copy())
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2], ref[2])
+            assert np.array_equal(cur[3], ref[3])
+    f.close()
+    sp.close()
