@@ -65,6 +65,16 @@ class CoupledStep:
         res_t, _ = self.ft.pcg(self.ft.jacobi(), rhs, T1, rel_tol, 0.0, iters_t, want_norms=False)
         return dict(phi=phi, Be=Be, src=self.src, rhs=rhs, T1=T1, res_e=res_e, res_t=res_t)
 
+    def run(self, T0, nsteps, iters_e, iters_t, rel_tol=0.0):
+        """time loop (≙ BackwardEulerSolver::Step over ImplicitSolve, linalg/ode.cpp:682-696): T, phi and all
+        q-data stay on the device between steps; returns the list of temperatures [T^1 .. T^nsteps]"""
+        out, T = [], T0
+        for _ in range(nsteps):
+            o = self.step(T, iters_e, iters_t, rel_tol)
+            T = o["T1"]
+            out.append(o)
+        return out
+
     def close(self):
         for f in (self.fe, self.ft, self.fm):
             f.close()

@@ -417,6 +417,91 @@ static int bioheat(int argc, char **argv, bool dump)
    return 0;
 }
 
+
+// ------------------------------------------------------- several coupled steps
+// dump_bioheat_steps OUT p N iters nsteps: the coupled RF + bioheat step repeated, T^{n+1} feeding k(T), sigma(T)
+// of the next step (the time loop a BackwardEulerSolver::Step / ImplicitSolve driver runs, linalg/ode.cpp:682-696).
+static int bioheat_steps(int argc, char **argv)
+{
+   if (argc < 7) { cerr << "usage: dump_bioheat_steps OUT p N iters nsteps\n"; return 2; }
+   Dumper D(argv[2]);
+   const int p = atoi(argv[3]), N = atoi(argv[4]), iters = atoi(argv[5]), nsteps = atoi(argv[6]);
+   Device device("cpu");
+   const BioheatParams P;
+   Mesh mesh = Mesh::MakeCartesian3D(N, N, N, Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   const FiniteElement &el = *fes.GetTypicalFE();
+   const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+   QuadratureSpace qs(mesh, ir);
+   GridFunction T(&fes), phi(&fes);
+   FunctionCoefficient Tinit([](const Vector &x)
+   {
+      const double r2 = (x(0) - .5) * (x(0) - .5) + (x(1) - .5) * (x(1) - .5) + (x(2) - .5) * (x(2) - .5);
+      return 37.0 + 20.0 * exp(-40.0 * r2);
+   });
+   T.ProjectCoefficient(Tinit);
+   D.vec("T_step0", T);
+   D.iscalar("iters", iters); D.iscalar("nsteps", nsteps);
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()); ess_bdr = 0; ess_bdr[0] = 1; ess_bdr[5] = 1;
+   Array<int> ess; fes.GetEssentialTrueDofs(ess_bdr, ess);
+   const double V = P.V;
+   FunctionCoefficient phibc([=](const Vector &x) { return V * (1.0 - x(2)); });
+   const Operator *R = fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+   const QuadratureInterpolator *qi = fes.GetQuadratureInterpolator(qs);
+   qi->SetOutputLayout(QVectorLayout::byVDIM);
+   for (int step = 1; step <= nsteps; step++)
+   {
+      QuadratureFunction Tq(qs), kq(qs), sq(qs), mq(qs), rq(qs);
+      Tq.ProjectGridFunction(T);
+      for (int i = 0; i < Tq.Size(); i++)
+      {
+         kq(i) = P.k0 * (1.0 + P.ak * (Tq(i) - 37.0));
+         sq(i) = P.s0 * (1.0 + P.as * (Tq(i) - 37.0));
+         mq(i) = P.rc / P.dt + P.wbcb;
+      }
+      QuadratureFunctionCoefficient kc(kq), sc(sq), mc(mq);
+      phi = 0.0; phi.ProjectBdrCoefficient(phibc, ess_bdr);
+      BilinearForm ae(&fes); ae.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      ae.AddDomainIntegrator(new DiffusionIntegrator(sc)); ae.Assemble();
+      LinearForm be(&fes); be.Assemble();
+      OperatorPtr Ae; Vector Xe, Be; ae.FormLinearSystem(ess, phi, be, Ae, Xe, Be);
+      OperatorJacobiSmoother Me(ae, ess);
+      CGSolver cge; cge.SetRelTol(0.0); cge.SetAbsTol(0.0); cge.SetMaxIter(iters); cge.SetPrintLevel(-1);
+      cge.SetOperator(*Ae); cge.SetPreconditioner(Me);
+      cge.Mult(Be, Xe);
+      ae.RecoverFEMSolution(Xe, be, phi);
+      Vector ephi(R->Height()); R->Mult(phi, ephi);
+      Vector gq(3 * qs.GetSize()); qi->PhysDerivatives(ephi, gq);
+      for (int i = 0; i < qs.GetSize(); i++)
+      {
+         const double gx = gq(3 * i), gy = gq(3 * i + 1), gz = gq(3 * i + 2);
+         rq(i) = sq(i) * (gx * gx + gy * gy + gz * gz) + P.wbcb * P.Ta;
+      }
+      QuadratureFunctionCoefficient rcf(rq);
+      BilinearForm at(&fes); at.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      at.AddDomainIntegrator(new DiffusionIntegrator(kc));
+      at.AddDomainIntegrator(new MassIntegrator(mc)); at.Assemble();
+      ConstantCoefficient rcdt(P.rc / P.dt);
+      BilinearForm mrc(&fes); mrc.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      mrc.AddDomainIntegrator(new MassIntegrator(rcdt)); mrc.Assemble();
+      LinearForm bt(&fes); bt.AddDomainIntegrator(new DomainLFIntegrator(rcf, &ir)); bt.UseFastAssembly(true);
+      bt.Assemble(); Vector mT(fes.GetVSize()); mrc.Mult(T, mT); bt += mT;
+      GridFunction T1(&fes); T1 = T;
+      Array<int> noess; OperatorPtr At; Vector Xt, Bt; at.FormLinearSystem(noess, T1, bt, At, Xt, Bt, 1);
+      OperatorJacobiSmoother Mt(at, noess);
+      CGSolver cgt; cgt.SetRelTol(0.0); cgt.SetAbsTol(0.0); cgt.SetMaxIter(iters); cgt.SetPrintLevel(-1);
+      cgt.SetOperator(*At); cgt.SetPreconditioner(Mt); cgt.iterative_mode = true;
+      cgt.Mult(Bt, Xt);
+      at.RecoverFEMSolution(Xt, bt, T1);
+      T = T1;
+      D.vec("T_step" + to_string(step), T);
+      D.vec("phi_step" + to_string(step), phi);
+   }
+   cout << setprecision(17) << "dump_bioheat_steps ok: |T|=" << T.Norml2() << " max T=" << T.Max() << endl;
+   return 0;
+}
+
 // ---------------------------------------------------------------- time_apply
 // CPU reference timing of the PA diffusion+mass apply (L→L, A.Mult) and of a fixed
 // number of Jacobi-PCG iterations, on MakeCartesian3D(N^3), order p, q-data
@@ -558,6 +643,7 @@ int main(int argc, char **argv)
    if (cmd == "dump_case") { return dump_case(argc, argv); }
    if (cmd == "dump_bioheat") { return bioheat(argc, argv, true); }
    if (cmd == "time_bioheat") { return bioheat(argc, argv, false); }
+   if (cmd == "dump_bioheat_steps") { return bioheat_steps(argc, argv); }
    if (cmd == "time_apply") { return time_apply(argc, argv); }
    if (cmd == "ex1") { return ex1(argc, argv); }
    if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }

@@ -12,6 +12,7 @@ Fixtures (all float64 / int32, reference layouts):
   case_<tag>.npz      everything `ref_driver dump_case` writes for one small case
   numbering.npz       gather_map / ndofs for many (nx,ny,nz,p): pins the product-side hex builder
   bioheat_p2_n4.npz   the RF + bioheat coupled step of SURVEY §3.2/3.3 on a 4^3 mesh
+  bioheat_steps_p2_n4.npz   three consecutive coupled steps (T^{n+1} feeds k(T), sigma(T) of the next one)
 """
 import os
 import subprocess
@@ -82,6 +83,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "numbering.npz"), **num)
     d = run(["dump_bioheat", 2, 4, 8])
     np.savez_compressed(os.path.join(HERE, "bioheat_p2_n4.npz"), **d)
+    d = run(["dump_bioheat_steps", 2, 4, 12, 3])
+    np.savez_compressed(os.path.join(HERE, "bioheat_steps_p2_n4.npz"), **d)
     print("done")
 
 
