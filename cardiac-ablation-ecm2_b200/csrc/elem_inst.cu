@@ -70,7 +70,7 @@ int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
    }
    if (a.NE <= 0) { return 0; }
    // TMA bulk copies need 16-byte aligned sources (cudaMalloc gives 256)
-   if (C::TMA && ((((unsigned long long)a.pa_diff) | ((unsigned long long)a.pa_mass)) & 15ull)) { return (int)cudaErrorMisalignedAddress; }
+   if (((((unsigned long long)a.pa_diff) | ((unsigned long long)a.pa_mass)) & 15ull)) { return (int)cudaErrorMisalignedAddress; }
    ElemParams<D, Q> P;
    fill_params(P, a);
    const int nbatch = (a.NE + C::NEB - 1) / C::NEB;

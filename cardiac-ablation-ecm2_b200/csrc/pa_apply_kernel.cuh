@@ -39,34 +39,45 @@ struct ApplyCfg
 {
    static constexpr int D2 = D * D, D3 = D * D * D, Q2 = Q * Q, Q3 = Q * Q * Q;
    // elements per batch: one q-point column per thread
-#ifdef B200PA_TUNE_NEB   // tuning builds only (tools/tune.sh)
+   // tuned on B200 with tools/tune.sh + tools/tune_run.sh (profiles/r1c_tuning.txt, r1g_tuning.txt);
+   // the B200PA_TUNE_* macros exist for those tuning builds only
+#ifdef B200PA_TUNE_NEB
    static constexpr int NEB = B200PA_TUNE_NEB;
-   static constexpr int MINB = B200PA_TUNE_MINB;
-   static constexpr bool QPF = B200PA_TUNE_QPF;
-   static constexpr bool TMA = B200PA_TUNE_TMA;
 #else
-   // tuned on B200 with tools/tune.sh + tools/tune_run.sh (profiles/r1c_tuning.txt)
    static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 8 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
+#endif
+#ifdef B200PA_TUNE_MINB
+   static constexpr int MINB = B200PA_TUNE_MINB;
+#else
    static constexpr int MINB = (D == 2) ? 3 : (D == 3) ? 4 : (D <= 6) ? 3 : 2; // resident CTAs/SM the register budget allows
-   static constexpr bool QPF = true;  // q-data of batch b+1 is fetched while batch b is still being contracted ...
-   static constexpr bool TMA = true;  // ... by TMA bulk copies into shared memory (false: into registers, 7Q doubles/thread)
+#endif
+#ifdef B200PA_TUNE_L2HINT
+   static constexpr bool L2HINT = B200PA_TUNE_L2HINT;
+#else
+   static constexpr bool L2HINT = true; // q-data and index streams are read once per apply: L2 evict_first
 #endif
    static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
-   static constexpr int NIO = (NEB * D3 + NT - 1) / NT;          // gather / scatter items per thread
+   static constexpr int NIDX = NEB * D3;                         // E-entries per batch
+   static constexpr int NIO = (NIDX + NT - 1) / NT;              // gather / scatter items per thread
    // shared-memory strides found by tools/smem_strides.py (fewest bank-conflict wavefronts over all phases;
-   // conflict-free at p=2): SXS = slab stride of sXin/sXout, SQ = slab stride and ES = element stride of sE
+   // conflict-free at p=2): SXS = slab stride of sX, RQ / SQ / ES = row / slab / element stride of sE
    static constexpr int SXS = (D == 2) ? 6 : (D == 3) ? 9 : (D == 4) ? 20 : (D == 5) ? 25 : (D == 6) ? 38 : 55;
-   static constexpr int SQ = (D == 2) ? 11 : (D == 3) ? 19 : (D == 4) ? 25 : (D == 5) ? 37 : (D == 6) ? 49 : 71;
-   static constexpr int ES = (D == 2) ? 73 : (D == 3) ? 185 : (D == 4) ? 308 : (D == 5) ? 564 : (D == 6) ? 886 : 1505;
-   static_assert(SXS >= D2 && SQ >= Q2 && ES >= 3 * D * SQ, "strides too small");
+   static constexpr int RQ = (D == 7) ? 10 : Q;
+   static constexpr int SQ = (D == 2) ? 11 : (D == 3) ? 19 : (D == 4) ? 25 : (D == 5) ? 37 : (D == 6) ? 49 : 87;
+   static constexpr int ES = (D == 2) ? 73 : (D == 3) ? 185 : (D == 4) ? 308 : (D == 5) ? 564 : (D == 6) ? 886 : 1841;
+   static constexpr int BS = D;                                  // row stride of the staged basis rows sBt / sGt
+   static_assert(SXS >= D2 && SQ >= (Q - 1) * RQ + Q && ES >= 3 * D * SQ && BS >= D, "strides too small");
+   // shared-memory map (bytes): two x buffers (gather target of the next batch | input and output of this one),
+   // the work array sE, basis rows, three index buffers, and one staged batch of q-data in its global layout
+   // ([e][6][Q^3] and [e][Q^3]; +2 doubles of slack each for the 16-byte alignment of the bulk copies)
    static constexpr int SX_DOUBLES = NEB * D * SXS;
    static constexpr int SE_DOUBLES = NEB * ES;
-   // TMA mode: one batch of q-data staged in shared memory, global layout kept ([e][6][Q^3] and [e][Q^3]);
-   // +2 doubles of slack each for the 16-byte alignment of the bulk copies
-   static constexpr int SQD_DOUBLES = TMA ? (NEB * 6 * Q3 + 2) : 0;
-   static constexpr int SQM_DOUBLES = TMA ? (((NEB * Q3 + 2) + 1) & ~1) : 0;
-   static constexpr int WORK_DOUBLES = ((2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * D) + 1) & ~1;
-   static constexpr size_t SMEM_BYTES = sizeof(double) * (WORK_DOUBLES + SQD_DOUBLES + SQM_DOUBLES);
+   static constexpr int WORK_DOUBLES = 2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * BS;
+   static constexpr int IDX_OFF = WORK_DOUBLES * 8;              // int sGi[2][NIDX], sSl[NIDX]
+   static constexpr int QD_OFF = (IDX_OFF + 3 * NIDX * 4 + 15) & ~15;
+   static constexpr int SQD_DOUBLES = NEB * 6 * Q3 + 2;
+   static constexpr int SQM_DOUBLES = ((NEB * Q3 + 2) + 1) & ~1;
+   static constexpr size_t SMEM_BYTES = QD_OFF + sizeof(double) * (SQD_DOUBLES + SQM_DOUBLES);
 };
 
 template <int D, int Q, bool DIFF, bool MASS>
@@ -74,71 +85,73 @@ __global__ void __launch_bounds__(ApplyCfg<D, Q>::NT, ApplyCfg<D, Q>::MINB)
 pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
 {
    using C = ApplyCfg<D, Q>;
-   constexpr int D2 = C::D2, D3 = C::D3, Q2 = C::Q2, Q3 = C::Q3, NEB = C::NEB, NT = C::NT, NIO = C::NIO;
-   constexpr int SXS = C::SXS, SQ = C::SQ, ES = C::ES;
+   constexpr int D2 = C::D2, D3 = C::D3, Q2 = C::Q2, Q3 = C::Q3, NEB = C::NEB, NT = C::NT, NIO = C::NIO, NIDX = C::NIDX;
+   constexpr int SXS = C::SXS, SQ = C::SQ, ES = C::ES, RQ = C::RQ, BS = C::BS;
 #define Bm(q, d) P.bg.B[(q) + Q * (d)]
 #define Gm(q, d) P.bg.G[(q) + Q * (d)]
-   extern __shared__ double smem[];
-   double *sXin = smem;
-   double *sXout = sXin + C::SX_DOUBLES;
-   double *sE = sXout + C::SX_DOUBLES;
-   double *sBt = sE + C::SE_DOUBLES; // sBt[qy*D + dy] = B(qy,dy): the one runtime-indexed row of phase A
-   double *sGt = sBt + Q * D;
-   double *sQd = smem + C::WORK_DOUBLES;      // TMA mode: this batch's diffusion q-data (16-byte aligned)
-   double *sQm = sQd + C::SQD_DOUBLES;        //           and mass q-data
-   __shared__ unsigned long long qbar;        // TMA mode: "q-data of the current batch has landed"
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   double *sX = reinterpret_cast<double *>(smem_raw);          // sX[2][NEB*D][SXS]
+   double *sE = sX + 2 * C::SX_DOUBLES;
+   double *sBt = sE + C::SE_DOUBLES; // sBt[qy*BS + dy] = B(qy,dy): the one runtime-indexed row of phase A
+   double *sGt = sBt + Q * BS;
+   int *sGi = reinterpret_cast<int *>(smem_raw + C::IDX_OFF);  // sGi[2][NIDX]: gather indices, two batches deep
+   int *sSl = sGi + 2 * NIDX;                                  // sSl[NIDX]: slots of this batch
+   double *sQd = reinterpret_cast<double *>(smem_raw + C::QD_OFF); // this batch's diffusion q-data (16-byte aligned)
+   double *sQm = sQd + C::SQD_DOUBLES;                         //           and mass q-data
+   __shared__ unsigned long long qbar;                         // "q-data of the current batch has landed"
    const int tid = threadIdx.x;
    if (P.done && *P.done) { return; }
    const int nbatch = (P.NE + NEB - 1) / NEB;
    for (int i = tid; i < Q * D; i += NT)
    {
       const int q = i / D, d = i - q * D;
-      sBt[i] = P.bg.B[q + Q * d];
-      sGt[i] = P.bg.G[q + Q * d];
+      sBt[q * BS + d] = P.bg.B[q + Q * d];
+      sGt[q * BS + d] = P.bg.G[q + Q * d];
    }
 
    // fixed per-thread roles
    const int eB = tid / Q2, cB = tid - eB * Q2; // phase B column
    const bool actB = tid < NEB * Q2;
+   const unsigned long long pol = C::L2HINT ? l2_policy_evict_first() : 0ull;
+   const long long lim = (long long)P.NE * D3;
 
-   double O[DIFF ? Q : 1][6], Mq[MASS ? Q : 1]; // this thread's q-data column (prefetched one batch ahead)
-   double xg[NIO];                              // gathered x values (prefetched)
-   int gi[NIO];
-
-   auto load_qdata = [&](int b)
+   // The gather runs two batches ahead without tying up a register: every thread owns the E-entries
+   // t = tid + r*NT of a batch; it copies their gather indices (batch b+2) and slots (batch b) into shared
+   // memory with 4-byte cp.async (LDGSTS), reads its own indices of batch b+1 back and gathers x with 8-byte
+   // cp.async straight into the x buffer of batch b+1 (zero-filled for constrained entries, index < 0).
+   auto copy_idx = [&](int *dst, const int *src, int b)
    {
-      const long long eg = (long long)b * NEB + eB;
-      const bool ok = actB && eg < P.NE;
-      B200PA_UNROLL
-      for (int qz = 0; qz < Q; ++qz)
-      {
-         if (DIFF)
-         {
-            const double *d = P.pa_diff + (eg * 6) * Q3 + qz * Q2 + cB;
-            B200PA_UNROLL
-            for (int k = 0; k < 6; ++k) { O[qz][k] = ok ? __ldg(d + k * Q3) : 0.0; }
-         }
-         if (MASS) { Mq[qz] = ok ? __ldg(P.pa_mass + eg * Q3 + qz * Q2 + cB) : 0.0; }
-      }
-   };
-   auto load_gidx = [&](int b)
-   {
-      const long long base = (long long)b * NEB * D3;
-      const long long lim = (long long)P.NE * D3;
+      const long long base = (long long)b * NIDX;
       B200PA_UNROLL
       for (int r = 0; r < NIO; ++r)
       {
          const int t = tid + r * NT;
-         gi[r] = (t < NEB * D3 && base + t < lim) ? __ldg(P.gmap + base + t) : -1;
+         if (t < NIDX)
+         {
+            if (base + t < lim)
+            {
+               cp_async4(dst + t, src + base + t);
+            }
+            else { dst[t] = -1; }
+         }
       }
    };
-   auto load_x = [&]()
+   auto gather_x = [&](double *dst, const int *idx)
    {
       B200PA_UNROLL
-      for (int r = 0; r < NIO; ++r) { xg[r] = gi[r] >= 0 ? P.x[gi[r]] : 0.0; }
+      for (int r = 0; r < NIO; ++r)
+      {
+         const int t = tid + r * NT;
+         if (t < NIDX)
+         {
+            const int slab = t / D2, k = t - slab * D2;
+            const int g = idx[t];
+            cp_async8_zfill(dst + slab * SXS + k, P.x + (g >= 0 ? g : 0), g >= 0);
+         }
+      }
    };
 
-   // TMA mode: two bulk copies per batch (the batch's elements are contiguous in both q-data arrays).
+   // two bulk copies per batch (the batch's elements are contiguous in both q-data arrays).
    // The mass array's element stride (Q^3 doubles) is odd for odd Q, so its copy starts at the
    // 16-byte boundary below the batch and `mshift` (0 or 1 doubles) finds the data again.
    int mshift = 0;
@@ -165,51 +178,47 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          bytes_m = (unsigned)(nd * sizeof(double));
       }
       mbar_expect_tx(&qbar, bytes_d + bytes_m);
-      if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
-      if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
+      if (C::L2HINT)
+      {
+         if (DIFF) { tma_bulk_g2s_hint(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar, pol); }
+         if (MASS) { tma_bulk_g2s_hint(sQm, src_m, bytes_m, &qbar, pol); }
+      }
+      else
+      {
+         if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
+         if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
+      }
    };
    auto mass_shift = [&](int b) { return (int)(((unsigned long long)(P.pa_mass + (long long)b * NEB * Q3) >> 3) & 1ull); };
    unsigned qphase = 0;
-   if (C::TMA)
-   {
-      if (tid == 0) { mbar_init(&qbar, 1); }
-      __syncthreads();
-   }
+   if (tid == 0) { mbar_init(&qbar, 1); }
+   __syncthreads();
 
    int batch = blockIdx.x;
    if (batch < nbatch)
    {
-      load_gidx(batch);
-      if (C::TMA) { if (tid == 0) { tma_issue(batch); } }
-      else if (C::QPF) { load_qdata(batch); }
-      load_x();
+      if (tid == 0) { tma_issue(batch); }
+      copy_idx(sGi, P.gmap, batch);
+      if (batch + (int)gridDim.x < nbatch) { copy_idx(sGi + NIDX, P.gmap, batch + gridDim.x); }
+      cp_async_commit();
+      cp_async_wait_all();                 // the one exposed index latency of the CTA (own entries only: no barrier)
+      gather_x(sX, sGi);
+      cp_async_commit();
    }
-   for (; batch < nbatch; batch += gridDim.x)
+   int cur = 0;
+   for (; batch < nbatch; batch += gridDim.x, cur ^= 1)
    {
-      const long long base = (long long)batch * NEB * D3;
-      const long long lim = (long long)P.NE * D3;
       const int next = batch + gridDim.x;
+      double *sXin = sX + cur * C::SX_DOUBLES; // input of this batch; its output too once phase A is done
+      double *sXout = sXin;
 
       // ------------------------------------------------------------- stage-in
-      B200PA_UNROLL
-      for (int r = 0; r < NIO; ++r)
-      {
-         const int t = tid + r * NT;
-         if (t < NEB * D3)
-         {
-            const int slab = t / D2, k = t - slab * D2;
-            sXin[slab * SXS + k] = xg[r];
-         }
-      }
-      __syncthreads();
-      if (next < nbatch) { load_gidx(next); } // indices for the next batch fly during phase A
-      int sl[NIO];
-      B200PA_UNROLL
-      for (int r = 0; r < NIO; ++r)
-      {
-         const int t = tid + r * NT;
-         sl[r] = (t < NEB * D3 && base + t < lim) ? __ldg(P.slot + base + t) : -1;
-      }
+      cp_async_wait_all();
+      __syncthreads();                     // x of this batch has landed; everybody is done with the previous batch
+      if (next < nbatch) { gather_x(sX + (cur ^ 1) * C::SX_DOUBLES, sGi + (cur ^ 1) * NIDX); }
+      if (next + (int)gridDim.x < nbatch) { copy_idx(sGi + cur * NIDX, P.gmap, next + gridDim.x); }
+      copy_idx(sSl, P.slot, batch);
+      cp_async_commit();
 
       // ------------------------------------ phase A: (slab, qy) rows, y then x
       for (int task = tid; task < NEB * D * Q; task += NT)
@@ -219,7 +228,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          const double *xs = sXin + slab * SXS;
          double bq[D], gq[D];
          B200PA_UNROLL
-         for (int dy = 0; dy < D; ++dy) { bq[dy] = sBt[qy * D + dy]; if (DIFF) { gq[dy] = sGt[qy * D + dy]; } }
+         for (int dy = 0; dy < D; ++dy) { bq[dy] = sBt[qy * BS + dy]; if (DIFF) { gq[dy] = sGt[qy * BS + dy]; } }
          double tB[D], tG[D];
          B200PA_UNROLL
          for (int dx = 0; dx < D; ++dx) { tB[dx] = 0.0; tG[dx] = 0.0; }
@@ -234,7 +243,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
                if (DIFF) { tG[dx] = fma(gq[dy], xv, tG[dx]); }
             }
          }
-         double *o = sE + e * ES + dz * SQ + qy * Q;
+         double *o = sE + e * ES + dz * SQ + qy * RQ;
          B200PA_UNROLL
          for (int qx = 0; qx < Q; ++qx)
          {
@@ -256,18 +265,14 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // -------------------------------- phase B: column, q-point op, column^T
-      if (!C::QPF && !C::TMA) { load_qdata(batch); }
-      if (C::TMA)
-      {
-         mbar_wait(&qbar, qphase);
-         qphase ^= 1u;
-         if (MASS) { mshift = mass_shift(batch); }
-      }
-      const double *qd = sQd + (eB * 6) * Q3 + cB;         // TMA mode: this thread's column in the staged q-data
+      mbar_wait(&qbar, qphase);
+      qphase ^= 1u;
+      if (MASS) { mshift = mass_shift(batch); }
+      const double *qd = sQd + (eB * 6) * Q3 + cB;         // this thread's column in the staged q-data
       const double *qm = sQm + mshift + eB * Q3 + cB;
       if (actB)
       {
-         double *s = sE + eB * ES + cB;
+         double *s = sE + eB * ES + (cB / Q) * RQ + (cB % Q);
          double f0[D], f1[D], f2[D], p0[D], p1[D], p2[D];
          B200PA_UNROLL
          for (int dz = 0; dz < D; ++dz)
@@ -294,18 +299,13 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             double hX = 0.0, hY = 0.0, hZ = 0.0, hM = 0.0;
             if (DIFF)
             {
-               double o0, o1, o2, o3, o4, o5;
-               if (C::TMA)
-               {
-                  const double *d = qd + qz * Q2;
-                  o0 = d[0]; o1 = d[Q3]; o2 = d[2 * Q3]; o3 = d[3 * Q3]; o4 = d[4 * Q3]; o5 = d[5 * Q3];
-               }
-               else { o0 = O[qz][0]; o1 = O[qz][1]; o2 = O[qz][2]; o3 = O[qz][3]; o4 = O[qz][4]; o5 = O[qz][5]; }
+               const double *d = qd + qz * Q2;
+               const double o0 = d[0], o1 = d[Q3], o2 = d[2 * Q3], o3 = d[3 * Q3], o4 = d[4 * Q3], o5 = d[5 * Q3];
                hX = o0 * gX + o1 * gY + o2 * gZ;
                hY = o1 * gX + o3 * gY + o4 * gZ;
                hZ = o2 * gX + o4 * gY + o5 * gZ;
             }
-            if (MASS) { hM = (C::TMA ? qm[qz * Q2] : Mq[qz]) * val; }
+            if (MASS) { hM = qm[qz * Q2] * val; }
             B200PA_UNROLL
             for (int dz = 0; dz < D; ++dz)
             {
@@ -325,23 +325,17 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             s[(2 * D + dz) * SQ] = p2[dz];
          }
       }
-      // prefetch for the next batch: q-data column and gathered x (indices arrived during phase A)
-      if (next < nbatch)
-      {
-         if (C::QPF && !C::TMA) { load_qdata(next); }
-         load_x();
-      }
       __syncthreads();
       // every thread is done reading the staged q-data: refill the buffer with the next batch; the copy
       // flies during phases C1/C2, stage-out, stage-in and phase A of the next batch
-      if (C::TMA && next < nbatch && tid == 0) { tma_issue(next); }
+      if (next < nbatch && tid == 0) { tma_issue(next); }
 
       // ----------------------------------------------- phase C1: (slab, qy) rows, x^T
       for (int task = tid; task < NEB * D * Q; task += NT)
       {
          const int slab = task / Q, qy = task - slab * Q;
          const int e = slab / D, dz = slab - e * D;
-         double *io = sE + e * ES + dz * SQ + qy * Q;
+         double *io = sE + e * ES + dz * SQ + qy * RQ;
          double r0[Q], r1[Q], r2[Q];
          B200PA_UNROLL
          for (int qx = 0; qx < Q; ++qx)
@@ -381,8 +375,8 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          B200PA_UNROLL
          for (int qy = 0; qy < Q; ++qy)
          {
-            const double a = in[0 * D * SQ + qy * Q];
-            const double b = DIFF ? in[1 * D * SQ + qy * Q] : 0.0;
+            const double a = in[0 * D * SQ + qy * RQ];
+            const double b = DIFF ? in[1 * D * SQ + qy * RQ] : 0.0;
             B200PA_UNROLL
             for (int dy = 0; dy < D; ++dy)
             {
@@ -397,14 +391,19 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // --------------------------------------------------------------- stage-out
+      cp_async_wait_all();                 // own slot entries (issued a whole batch ago)
       B200PA_UNROLL
       for (int r = 0; r < NIO; ++r)
       {
          const int t = tid + r * NT;
-         if (t < NEB * D3 && sl[r] >= 0)
+         if (t < NIDX)
          {
-            const int slab = t / D2, k = t - slab * D2;
-            P.y[sl[r]] = sXout[slab * SXS + k];
+            const int sl = sSl[t];
+            if (sl >= 0)
+            {
+               const int slab = t / D2, k = t - slab * D2;
+               P.y[sl] = sXout[slab * SXS + k];
+            }
          }
       }
    }
