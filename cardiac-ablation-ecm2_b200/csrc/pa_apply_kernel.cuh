@@ -44,29 +44,46 @@ struct ApplyCfg
 #ifdef B200PA_TUNE_NEB
    static constexpr int NEB = B200PA_TUNE_NEB;
 #else
-   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 8 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
+   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 16 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
 #endif
 #ifdef B200PA_TUNE_MINB
    static constexpr int MINB = B200PA_TUNE_MINB;
 #else
-   static constexpr int MINB = (D == 2) ? 3 : (D == 3) ? 4 : (D <= 6) ? 3 : 2; // resident CTAs/SM the register budget allows
+   static constexpr int MINB = (D <= 2) ? 3 : (D == 3) ? 2 : (D <= 6) ? 3 : 2; // resident CTAs/SM the register budget allows
 #endif
 #ifdef B200PA_TUNE_L2HINT
    static constexpr bool L2HINT = B200PA_TUNE_L2HINT;
 #else
-   static constexpr bool L2HINT = true; // q-data and index streams are read once per apply: L2 evict_first
+   static constexpr bool L2HINT = (D <= 3); // q-data is read once per apply: L2 evict_first (measured: +3 % at p=2, -4 % at p=5)
 #endif
    static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int NIDX = NEB * D3;                         // E-entries per batch
    static constexpr int NIO = (NIDX + NT - 1) / NT;              // gather / scatter items per thread
-   // shared-memory strides found by tools/smem_strides.py (fewest bank-conflict wavefronts over all phases;
-   // conflict-free at p=2): SXS = slab stride of sX, RQ / SQ / ES = row / slab / element stride of sE
+   // shared-memory strides and lane -> task maps found by tools/smem_strides.py (fewest bank-conflict wavefronts
+   // over all phases; conflict-free at p=2 and p=3): SXS = slab stride of sX, RQ / SQ / ES = row / slab / element
+   // stride of sE, BS = row stride of the staged basis rows; MAPA_SLAB / MAPC_SLAB: consecutive lanes of the
+   // row phases A, C1 / of phase C2 walk the slabs (else the rows / columns of one slab)
+#ifdef B200PA_TUNE_LAYOUT0 // the layout of rounds r1c..r1f
+   static constexpr bool MAPA_SLAB = false, MAPC_SLAB = false;
    static constexpr int SXS = (D == 2) ? 6 : (D == 3) ? 9 : (D == 4) ? 20 : (D == 5) ? 25 : (D == 6) ? 38 : 55;
-   static constexpr int RQ = (D == 7) ? 10 : Q;
    static constexpr int SQ = (D == 2) ? 11 : (D == 3) ? 19 : (D == 4) ? 25 : (D == 5) ? 37 : (D == 6) ? 49 : 87;
    static constexpr int ES = (D == 2) ? 73 : (D == 3) ? 185 : (D == 4) ? 308 : (D == 5) ? 564 : (D == 6) ? 886 : 1841;
-   static constexpr int BS = D;                                  // row stride of the staged basis rows sBt / sGt
+   static constexpr int BS = D;
+   static constexpr int QES = 6 * Q3, QMS = Q3;
+#else
+   static constexpr bool MAPA_SLAB = (D == 4), MAPC_SLAB = (D == 4 || D == 6);
+   static constexpr int SXS = (D == 2) ? 6 : (D == 3) ? 9 : (D == 4) ? 17 : (D == 5) ? 25 : (D == 6) ? 38 : 55;
+   static constexpr int SQ = (D == 2) ? 11 : (D == 3) ? 19 : (D == 4) ? 28 : (D == 5) ? 37 : (D == 6) ? 49 : 87;
+   static constexpr int ES = (D == 2) ? 73 : (D == 3) ? 185 : (D == 4) ? 345 : (D == 5) ? 564 : (D == 6) ? 886 : 1841;
+   static constexpr int BS = D;
+   // element strides of the staged q-data: where Q^2 is not a multiple of 16 lanes the elements of a batch are
+   // staged by one bulk copy each, padded so that consecutive lanes keep hitting consecutive banks across the
+   // element boundary (possible for even Q only: bulk copies need 16-byte aligned ends)
+   static constexpr int QES = (D == 5) ? 6 * Q3 + 4 : 6 * Q3, QMS = (D == 5) ? Q3 + 12 : Q3;
+#endif
+   static constexpr int RQ = (D == 7) ? 10 : Q;
    static_assert(SXS >= D2 && SQ >= (Q - 1) * RQ + Q && ES >= 3 * D * SQ && BS >= D, "strides too small");
+   static_assert((QES == 6 * Q3 && QMS == Q3) || (Q % 2 == 0 && QES % 2 == 0 && QMS % 2 == 0), "padded q-data staging needs even Q");
    // shared-memory map (bytes): two x buffers (gather target of the next batch | input and output of this one),
    // the work array sE, basis rows, three index buffers, and one staged batch of q-data in its global layout
    // ([e][6][Q^3] and [e][Q^3]; +2 doubles of slack each for the 16-byte alignment of the bulk copies)
@@ -75,8 +92,8 @@ struct ApplyCfg
    static constexpr int WORK_DOUBLES = 2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * BS;
    static constexpr int IDX_OFF = WORK_DOUBLES * 8;              // int sGi[2][NIDX], sSl[NIDX]
    static constexpr int QD_OFF = (IDX_OFF + 3 * NIDX * 4 + 15) & ~15;
-   static constexpr int SQD_DOUBLES = NEB * 6 * Q3 + 2;
-   static constexpr int SQM_DOUBLES = ((NEB * Q3 + 2) + 1) & ~1;
+   static constexpr int SQD_DOUBLES = NEB * QES + 2;
+   static constexpr int SQM_DOUBLES = ((NEB * QMS + 2) + 1) & ~1;
    static constexpr size_t SMEM_BYTES = QD_OFF + sizeof(double) * (SQD_DOUBLES + SQM_DOUBLES);
 };
 
@@ -178,15 +195,19 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          bytes_m = (unsigned)(nd * sizeof(double));
       }
       mbar_expect_tx(&qbar, bytes_d + bytes_m);
-      if (C::L2HINT)
+      if (C::QES != 6 * Q3 || C::QMS != Q3)
       {
-         if (DIFF) { tma_bulk_g2s_hint(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar, pol); }
-         if (MASS) { tma_bulk_g2s_hint(sQm, src_m, bytes_m, &qbar, pol); }
+         // padded staging (even Q: every element starts 16-byte aligned in both arrays, no shift)
+         for (int e = 0; e < nel; ++e)
+         {
+            if (DIFF) { tma_bulk_g2s(sQd + e * C::QES, P.pa_diff + (e0 + e) * 6 * Q3, (unsigned)(6 * Q3 * sizeof(double)), &qbar, pol); }
+            if (MASS) { tma_bulk_g2s(sQm + e * C::QMS, P.pa_mass + (e0 + e) * Q3, (unsigned)(Q3 * sizeof(double)), &qbar, pol); }
+         }
       }
       else
       {
-         if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
-         if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
+         if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar, pol); }
+         if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar, pol); }
       }
    };
    auto mass_shift = [&](int b) { return (int)(((unsigned long long)(P.pa_mass + (long long)b * NEB * Q3) >> 3) & 1ull); };
@@ -223,7 +244,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // ------------------------------------ phase A: (slab, qy) rows, y then x
       for (int task = tid; task < NEB * D * Q; task += NT)
       {
-         const int slab = task / Q, qy = task - slab * Q;
+         const int slab = C::MAPA_SLAB ? task % (NEB * D) : task / Q, qy = C::MAPA_SLAB ? task / (NEB * D) : task - slab * Q;
          const int e = slab / D, dz = slab - e * D;
          const double *xs = sXin + slab * SXS;
          double bq[D], gq[D];
@@ -268,8 +289,8 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       mbar_wait(&qbar, qphase);
       qphase ^= 1u;
       if (MASS) { mshift = mass_shift(batch); }
-      const double *qd = sQd + (eB * 6) * Q3 + cB;         // this thread's column in the staged q-data
-      const double *qm = sQm + mshift + eB * Q3 + cB;
+      const double *qd = sQd + eB * C::QES + cB;         // this thread's column in the staged q-data
+      const double *qm = sQm + mshift + eB * C::QMS + cB;
       if (actB)
       {
          double *s = sE + eB * ES + (cB / Q) * RQ + (cB % Q);
@@ -333,7 +354,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // ----------------------------------------------- phase C1: (slab, qy) rows, x^T
       for (int task = tid; task < NEB * D * Q; task += NT)
       {
-         const int slab = task / Q, qy = task - slab * Q;
+         const int slab = C::MAPA_SLAB ? task % (NEB * D) : task / Q, qy = C::MAPA_SLAB ? task / (NEB * D) : task - slab * Q;
          const int e = slab / D, dz = slab - e * D;
          double *io = sE + e * ES + dz * SQ + qy * RQ;
          double r0[Q], r1[Q], r2[Q];
@@ -366,7 +387,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // ----------------------------------------------- phase C2: (slab, dx) columns, y^T
       for (int task = tid; task < NEB * D * D; task += NT)
       {
-         const int slab = task / D, dx = task - slab * D;
+         const int slab = C::MAPC_SLAB ? task % (NEB * D) : task / D, dx = C::MAPC_SLAB ? task / (NEB * D) : task - slab * D;
          const int e = slab / D, dz = slab - e * D;
          const double *in = sE + e * ES + dz * SQ + dx;
          double out[D];

@@ -47,9 +47,11 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last()
    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
    return pol;
 }
-__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
-                                                  unsigned long long pol)
+// pol == 0: no hint
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
+                                             unsigned long long pol)
 {
+   if (pol == 0ull) { tma_bulk_g2s(dst_smem, src_gmem, bytes, bar); return; }
    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                    smem_u32(dst_smem)),
                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
