@@ -26,11 +26,14 @@ METRIC = "GDOF/s of FP64 PA diffusion+mass apply"
 PHYS = dict(dt=0.5, rc=3.6e6, wbcb=4.0e4, Ta=37.0, k0=0.5, ak=0.02, s0=0.3, as_=0.015, V=30.0)
 
 
-def algorithmic_bytes_per_dof(p, ncomp=7):
-    """x_L read + y_L write + q-data + gather map + scatter indices + offsets"""
+def algorithmic_bytes_per_dof(p, ncomp=7, factorised=False):
+    """x_L read + y_L write + q-data + gather map + scatter indices + offsets.
+    factorised q-data (affine meshes): the six diffusion components per q-point become one scalar per q-point
+    and six doubles per element"""
     D, Q = p + 1, p + 2
     rq, rd = Q ** 3 / p ** 3, D ** 3 / p ** 3
-    total = 8 + 8 + 8 * ncomp * rq + 4 * rd + 4 * rd + 4
+    qbytes = 8 * ncomp * rq if not factorised else 8 * (ncomp - 5) * rq + 48 / p ** 3
+    total = 8 + 8 + qbytes + 4 * rd + 4 * rd + 4
     elem = total - 8 - 4          # the element kernel's share: everything but the y_L write and the offsets
     return total, elem
 
@@ -194,6 +197,9 @@ def main():
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--elems", "--n", dest="n", type=int, default=100, help="elements per direction per GPU")
     ap.add_argument("--ops", default="both", choices=["both", "diff"], help="diffusion+mass (headline) or diffusion only (configs[3] sweep)")
+    ap.add_argument("--qdata", default="stored", choices=["stored", "factorised"],
+                    help="diffusion q-data of the timed apply: the reference's six components per q-point (headline) or the "
+                         "factorised form for affine meshes (b200pa_form_set_factorised)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip PCG / implicit-step extras (profiling runs)")
     args = ap.parse_args()
@@ -242,7 +248,9 @@ def main():
     nq = ne * (p + 2) ** 3
     kq = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0)
     mq = ctx.coeff_eval(1, nq, PHYS["rc"] / PHYS["dt"] + PHYS["wbcb"], 0.0, 0.0)
+    fact = args.qdata == "factorised"
     form = b200pa.Form(sp)
+    form.set_factorised(fact)
     form.assemble_diffusion(kq)
     if args.ops == "both":
         form.assemble_mass(mq)
@@ -308,7 +316,7 @@ def main():
     Ke = max(3, min(K, 20))
     ms_e2e = timed(lambda: form.mult_host(xp, yp), Ke)
 
-    bytes_total, bytes_elem = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6)
+    bytes_total, bytes_elem = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6, fact)
     peak, peak_src = measured_peak_hbm()
     t_elem = ms_elem / K * 1e-3
     achieved = bytes_elem * nd / t_elem / 1e9
@@ -319,7 +327,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"configs[1]: Pennes bioheat operator k(T) diffusion + (rho c/dt + perfusion) mass, PA apply L->L, "
                                f"hex {GN[0]}x{GN[1]}x{GN[2]} (N={n}^3 per GPU), order {p}, {global_dofs} dofs",
-                   "order": p, "ops": args.ops, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
+                   "order": p, "ops": args.ops, "qdata": args.qdata, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
                    "partition": "x".join(map(str, grid)),
                    "exchange": ("none" if comm is None else ("peer-memory stores + flags over NVLink (CUDA IPC)" if comm.p2p_enabled()
                                                              else "NCCL send/recv + all-reduce")),
@@ -329,13 +337,65 @@ def main():
                 "api": "b200pa_form_mult_host (pinned host x -> H2D -> apply -> D2H -> pinned host y)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(p, n, args.ops), "algorithmic_bytes": bytes_elem * nd,
+                     "traffic": None if fact else measured_traffic(p, n, args.ops), "algorithmic_bytes": bytes_elem * nd,
                      "kernel": "pa_apply_kernel (gather + diffusion + mass + slot-order write)",
                      "bytes_per_dof": bytes_elem, "ms_per_launch": ms_elem / K, "peak_source": peak_src},
         "roofline_apply": {"achieved": bytes_total * nd / (ms_total / K * 1e-3) / 1e9, "frac": bytes_total * nd / (ms_total / K * 1e-3) / 1e9 / peak,
                            "bytes_per_dof": bytes_total, "ms_element_kernel": ms_elem / K, "ms_segment_sum": ms_seg / K},
         "clocks": clocks, "setup_s": t_setup,
     }
+
+    # ---- the same operator with the factorised diffusion q-data (the mesh is affine): what a caller who opts in gets
+    if not fact and sp.affine and not args.no_extras:
+        f2 = b200pa.Form(sp)
+        f2.set_factorised(True)
+        f2.assemble_diffusion(kq)
+        if args.ops == "both":
+            f2.assemble_mass(mq)
+        f2.set_essential(None)
+        if comm is not None:
+            f2.set_comm(comm)
+        y2 = ctx.empty(nd)
+        for _ in range(W):
+            f2.mult(x, y2)
+        ms2 = timed(lambda: f2.mult(x, y2), K)
+        ms2_elem = timed(lambda: f2.mult_phases(x, y2, 1), K)
+        bt2, be2 = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6, True)
+        f2.mult(x, y2)
+        form.mult(x, y)
+        diff = float((y2 - y).abs().max().item() / y.abs().max().item())
+        d2 = f2.jacobi()
+        lf2 = sp.domain_lf(ctx.coeff_eval(1, nq, PHYS["wbcb"] * PHYS["Ta"], 0.0, 0.0))
+        if comm is not None:
+            comm.exchange_sum(lf2)
+        rhs2 = ctx.add(lf2, 1.0, f2.mult(T0))
+        Tf = T0.clone()
+        f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 3, want_norms=False)
+        Tf.copy_(T0)
+        msp1 = timed(lambda: f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 20, want_norms=False), 1)
+        Tf.copy_(T0)
+        msp3 = timed(lambda: f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 60, want_norms=False), 1)
+
+        def implicit_step2():
+            k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0, out=kq)
+            f2.assemble_diffusion(k2)
+            if args.ops == "both":
+                f2.assemble_mass(mq)
+            dd = f2.jacobi()
+            Tf.copy_(T0)
+            return f2.pcg(dd, rhs2, Tf, 1e-8, 0.0, 500, want_norms=False)[0]
+
+        implicit_step2()
+        r2 = [None]
+        ms_step2 = timed(lambda: r2.__setitem__(0, implicit_step2()), 1)
+        line["factorised_qdata"] = {
+            "what": "same operator, diffusion q-data stored as w_q k_q per q-point + adj(J)adj(J)^T/detJ per element "
+                    "(b200pa_form_set_factorised; the mesh is affine)",
+            "value": global_dofs * K / (ms2 * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms2 / K, "ms_element_kernel": ms2_elem / K,
+            "bytes_per_dof": bt2, "hbm_frac_own_bytes": bt2 * nd / (ms2 / K * 1e-3) / 1e9 / peak,
+            "max_rel_diff_vs_stored": diff, "pcg_ms_per_iter_marginal": (msp3 - msp1) / 40,
+            "bioheat_step_ms": ms_step2, "bioheat_step_pcg_iters": r2[0].final_iter}
+        f2.close()
 
     # ---- extras on the same configuration: PCG iteration time and the implicit bioheat step
     if not args.no_extras:

@@ -38,6 +38,7 @@ b200pa_qphysgrad b200pa_domain_lf b200pa_dot b200pa_add b200pa_jacobi_setup b200
 b200pa_coeff_eval
 b200pa_space_create b200pa_space_destroy b200pa_space_set_geometry b200pa_space_geometry_from_vertices
 b200pa_space_offsets b200pa_space_indices b200pa_space_gather_map b200pa_space_J b200pa_space_detJ b200pa_space_W
+b200pa_space_is_affine b200pa_form_set_factorised b200pa_form_is_factorised
 b200pa_space_qvalues b200pa_space_qphysgrad b200pa_space_coeff_linear b200pa_space_joule b200pa_space_domain_lf
 b200pa_form_create b200pa_form_destroy b200pa_form_assemble_diffusion b200pa_form_assemble_mass
 b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_essential b200pa_form_mult
@@ -319,6 +320,10 @@ class Space:
         detJ = _f64(detJ) if isinstance(detJ, np.ndarray) else detJ
         check(lib().b200pa_space_set_geometry(self.h, _ptr(W), _ptr(J), _ptr(detJ)))
 
+    @property
+    def affine(self):
+        return lib().b200pa_space_is_affine(self.h) == 1
+
     def geometry_from_vertices(self, W, vertices, elem_vertices):
         v, ev = _f64(vertices), _i32(elem_vertices)
         check(lib().b200pa_space_geometry_from_vertices(self.h, _ptr(_f64(W)), len(v) // 3, _ptr(v), _ptr(ev)))
@@ -381,6 +386,14 @@ class Form:
         self.h = vp()
         self._keep = []
         check(lib().b200pa_form_create(space.h, C.byref(self.h)))
+
+    def set_factorised(self, on=True):
+        """factorised diffusion q-data (affine meshes): w_q c_q per q-point + one tensor per element"""
+        check(lib().b200pa_form_set_factorised(self.h, 1 if on else 0))
+
+    @property
+    def factorised(self):
+        return bool(lib().b200pa_form_is_factorised(self.h))
 
     def assemble_diffusion(self, Cq):
         if Cq is None:

@@ -23,7 +23,7 @@ def initial_temperature(lattice, gll, p, GN):
 class CoupledStep:
     """Keeps the three forms and the q-data buffers alive across time steps (device resident)."""
 
-    def __init__(self, ctx, sp, mesh, GN, P=PHYS, comm=None):
+    def __init__(self, ctx, sp, mesh, GN, P=PHYS, comm=None, factorised=False):
         self.ctx, self.sp, self.m, self.P, self.comm = ctx, sp, mesh, P, comm
         nq = sp.ne * sp.nq
         self.nq = nq
@@ -34,6 +34,9 @@ class CoupledStep:
         self.phi_bc = np.zeros(mesh["ndofs"])
         self.phi_bc[self.ess] = P["V"] * (1.0 - lat[self.ess, 2] / (mesh["p"] * GN[2]))
         self.fe, self.ft, self.fm = Form(sp), Form(sp), Form(sp)
+        if factorised:  # affine mesh: sigma(T), k(T) q-data as one scalar per q-point (b200pa_form_set_factorised)
+            self.fe.set_factorised(True)
+            self.ft.set_factorised(True)
         self.fe.set_essential(self.ess)
         self.ft.set_essential(None)
         self.fm.assemble_mass(np.array([P["rc"] / P["dt"]]))

@@ -93,7 +93,7 @@ static int run_element(b200pa_ctx ctx, int d1d, int q1d, int variant, const Elem
 
 template <int D1, int Q1>
 static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const double *pd, const double *pm,
-                        double *dE)
+                        const double *geo, double *dE)
 {
    // elements per CTA: q-data staging + the two contraction tensors within ~72 KB (3 CTAs per SM)
    constexpr int PER_E = (7 * Q1 * Q1 * Q1 + 7 * (Q1 * Q1 * D1 + Q1 * D1 * D1)) * 8;
@@ -107,7 +107,7 @@ static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const do
    {
       P.M[0][i] = hB[i] * hB[i]; P.M[1][i] = hB[i] * hG[i]; P.M[2][i] = hG[i] * hG[i];
    }
-   P.NE = ne; P.pa_diff = pd; P.pa_mass = pm; P.dE = dE;
+   P.NE = ne; P.pa_diff = pd; P.pa_mass = pm; P.geo = geo; P.dE = dE;
    const long long nbatch = (ne + NEB - 1) / NEB;
    const long long cap = (long long)ctx->num_sms * 3;
    kern<<<(int)(nbatch < cap ? nbatch : cap), 128, C::SMEM_BYTES, ctx->stream>>>(P);
@@ -115,19 +115,19 @@ static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const do
 
 // hB, hG: HOST copies of the 1-D basis tables
 static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *hB, const double *hG,
-                    const double *pd, const double *pm, double *dE)
+                    const double *pd, const double *pm, double *dE, const double *geo = nullptr)
 {
    B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
    if (ne <= 0) { return 0; }
    B200PA_REQUIRE(((((unsigned long long)pd) | ((unsigned long long)pm)) & 15ull) == 0, "pa_data must be 16-byte aligned (TMA bulk copies)");
    switch (d1d)
    {
-      case 2: launch_diag<2, 3>(ctx, ne, hB, hG, pd, pm, dE); break;
-      case 3: launch_diag<3, 4>(ctx, ne, hB, hG, pd, pm, dE); break;
-      case 4: launch_diag<4, 5>(ctx, ne, hB, hG, pd, pm, dE); break;
-      case 5: launch_diag<5, 6>(ctx, ne, hB, hG, pd, pm, dE); break;
-      case 6: launch_diag<6, 7>(ctx, ne, hB, hG, pd, pm, dE); break;
-      case 7: launch_diag<7, 8>(ctx, ne, hB, hG, pd, pm, dE); break;
+      case 2: launch_diag<2, 3>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 3: launch_diag<3, 4>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 4: launch_diag<4, 5>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 5: launch_diag<5, 6>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 6: launch_diag<6, 7>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 7: launch_diag<7, 8>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
    }
    B200PA_LAUNCHED();
    return 0;
@@ -150,6 +150,10 @@ struct b200pa_space_s
    // unless somebody asks for it (b200pa_space_J); set-up and q-point kernels rebuild it on the fly
    DevBuf vtx, ev, dxi;
    std::vector<double> hxi;
+   // factorised diffusion q-data (affine elements only): adj(J)adj(J)^T/det J per element; affine = every element
+   // is a parallelepiped to 1e-13 of its edge lengths (decided on the device by k_affine_geometry)
+   DevBuf geo6;
+   bool affine = false;
    DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
 };
 
@@ -158,6 +162,8 @@ struct b200pa_form_s
    b200pa_space sp = nullptr;
    DevBuf pa_diff, pa_mass;
    bool has_diff = false, has_mass = false;
+   bool factorised = false;     // pa_diff holds w_q c_q [Q^3,NE] and the space's geo6 completes it
+   bool want_factorised = false;
    int n_ess = 0;
    DevBuf ess, ess_mask, cgmap;
    DevBuf w1, w2;       // L-sized work vectors (EliminateRHS, host entry points)
@@ -561,7 +567,7 @@ extern "C" int b200pa_space_destroy(b200pa_space sp)
    if (!sp) { return 0; }
    cudaSetDevice(sp->ctx->device);
    cudaStreamSynchronize(sp->ctx->stream);
-   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->scratchE})
+   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->scratchE})
    {
       b->release();
    }
@@ -649,9 +655,25 @@ extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double
                                                                        sp->ev.as<int>(), nullptr, sp->detJ.as<double>());
       B200PA_LAUNCHED();
    }
+   sp->affine = false;
+   if (sp->ne > 0)
+   {
+      if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne)) { return 1; }
+      int *dflag = (int *)(ctx->d_ticket + 3);
+      B200PA_CK(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+      k_affine_geometry<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>(sp->ne, sp->vtx.as<double>(), sp->ev.as<int>(), 1e-13,
+                                                                    sp->geo6.as<double>(), dflag);
+      B200PA_LAUNCHED();
+      int flag = 1;
+      B200PA_CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(ctx->stream));
+      sp->affine = (flag == 0);
+   }
    B200PA_CK(cudaStreamSynchronize(ctx->stream));
    return 0;
 }
+
+extern "C" int b200pa_space_is_affine(b200pa_space sp) { return sp ? (sp->affine ? 1 : 0) : -1; }
 
 // Jacobians on demand (accessor / callers that want the reference's J array)
 static int ensure_J(b200pa_space sp)
@@ -793,13 +815,33 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
    B200PA_REQUIRE(f, "form is NULL");
    b200pa_space sp = f->sp;
    NEED_CTX(sp->ctx);
-   if (!C_any) { f->pa_diff.release(); f->has_diff = false; return 0; }
+   if (!C_any) { f->pa_diff.release(); f->has_diff = false; f->factorised = false; return 0; }
    B200PA_REQUIRE((sp->J.p || sp->vtx.p) && sp->W.p, "assemble_diffusion: space has no geometry");
    B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_diffusion: coefficient must have 1 or Q^3*NE entries");
    DevBuf cb;
    const void *dC = nullptr;
    if (to_device(sp->ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
    if (!f->pa_diff.owned) { f->pa_diff.release(); }
+   if (f->want_factorised)
+   {
+      // no silent change of representation: the caller asked for the factorised q-data, the mesh must allow it
+      B200PA_REQUIRE(sp->affine && sp->geo6.p, "assemble_diffusion: factorised q-data needs a mesh of affine elements given by its "
+                                               "vertices (b200pa_space_geometry_from_vertices)");
+      f->pa_diff.release(); // size differs from the stored form
+      int rcf = alloc(f->pa_diff, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1));
+      if (!rcf && sp->ne > 0)
+      {
+         k_coeff_times_w<<<grid1d(sp->ctx, sp->nQ), 256, 0, sp->ctx->stream>>>((long long)sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(),
+                                                                             (const double *)dC, nc == 1, f->pa_diff.as<double>());
+         g_launches++;
+         if (cudaGetLastError() != cudaSuccess) { rcf = fail("factorised diffusion set-up kernel launch failed"); }
+      }
+      if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
+      f->has_diff = (rcf == 0);
+      f->factorised = f->has_diff;
+      return rcf;
+   }
+   if (f->factorised) { f->pa_diff.release(); f->factorised = false; }
    int rc = alloc(f->pa_diff, sizeof(double) * 6 * (size_t)std::max<long long>(sp->nQ, 1));
    if (!rc && sp->J.p)
    {
@@ -841,6 +883,7 @@ extern "C" int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev,
 {
    B200PA_REQUIRE(f, "form is NULL");
    f->pa_diff.release(); f->pa_mass.release();
+   f->factorised = false;
    f->has_diff = pa_diff_dev != nullptr; f->has_mass = pa_mass_dev != nullptr;
    if (pa_diff_dev)
    {
@@ -855,6 +898,18 @@ extern "C" int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev,
    return 0;
 }
 extern "C" const double *b200pa_form_pa_diff(b200pa_form f) { return f && f->has_diff ? f->pa_diff.as<double>() : nullptr; }
+
+// Factorised diffusion q-data (see k_affine_geometry): on = 1 makes the following b200pa_form_assemble_diffusion
+// calls store w_q c_q per q-point (8 B instead of 48 B) next to the space's per-element tensors.  Results agree
+// with the stored form to rounding (the reference evaluates J at every q-point of an element on which it is
+// constant).  Fails at assembly, loudly, when the mesh has a non-affine element.
+extern "C" int b200pa_form_set_factorised(b200pa_form f, int on)
+{
+   B200PA_REQUIRE(f, "form is NULL");
+   f->want_factorised = (on != 0);
+   return 0;
+}
+extern "C" int b200pa_form_is_factorised(b200pa_form f) { return f && f->factorised ? 1 : 0; }
 extern "C" const double *b200pa_form_pa_mass(b200pa_form f) { return f && f->has_mass ? f->pa_mass.as<double>() : nullptr; }
 
 extern "C" int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any)
@@ -909,6 +964,7 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
    a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>();
    a.pa_diff = f->has_diff ? f->pa_diff.as<double>() : nullptr;
    a.pa_mass = f->has_mass ? f->pa_mass.as<double>() : nullptr;
+   a.geo = (f->has_diff && f->factorised) ? sp->geo6.as<double>() : nullptr;
    a.done = done;
    if ((phases & 1) && run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
    if (sp->ndofs == 0 || !(phases & 2)) { return 0; }
@@ -1031,7 +1087,7 @@ extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
    B200PA_CK(cudaMemsetAsync(sp->scratchE.p, 0, sizeof(double) * (size_t)sp->nE, ctx->stream));
    if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->hB.data(), sp->hG.data(),
                 f->has_diff ? f->pa_diff.as<double>() : nullptr, f->has_mass ? f->pa_mass.as<double>() : nullptr,
-                sp->scratchE.as<double>()))
+                sp->scratchE.as<double>(), (f->has_diff && f->factorised) ? sp->geo6.as<double>() : nullptr))
    {
       return 1;
    }

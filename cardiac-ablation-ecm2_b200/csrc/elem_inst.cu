@@ -21,7 +21,7 @@ void fill_params(ElemParams<DD, QQ> &P, const ElemArgs &a)
    for (int i = 0; i < QQ * DD; ++i) { P.bg.B[i] = a.B[i]; P.bg.G[i] = a.G ? a.G[i] : 0.0; }
    P.NE = a.NE;
    P.x = a.x; P.gmap = a.gmap; P.y = a.y; P.slot = a.slot;
-   P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.J = a.J;
+   P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.geo = a.geo; P.J = a.J;
    P.f = a.f; P.detJ = a.detJ; P.W = a.W; P.nf = a.nf; P.done = a.done;
    P.ca = a.ca; P.cb = a.cb; P.cT0 = a.cT0; P.s = a.s;
    P.vtx = a.vtx; P.ev = a.ev;
@@ -53,11 +53,11 @@ int run(const ElemArgs &a, int num_sms, cudaStream_t stream)
 }
 
 // the hot path: gather -> diffusion (+ mass) -> slot write (pa_apply_kernel.cuh)
-template <bool DIFF, bool MASS>
+template <bool DIFF, bool MASS, bool AFF>
 int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
 {
-   using C = ApplyCfg<D, Q>;
-   auto kern = pa_apply_kernel<D, Q, DIFF, MASS>;
+   using C = ApplyCfg<D, Q, AFF>;
+   auto kern = pa_apply_kernel<D, Q, DIFF, MASS, AFF>;
    static int blocks_per_sm = 0;
    if (blocks_per_sm == 0)
    {
@@ -81,9 +81,10 @@ int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
 
 int run_apply_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
 {
-   if (a.pa_diff && a.pa_mass) { return run_fused<true, true>(a, num_sms, stream); }
-   if (a.pa_diff) { return run_fused<true, false>(a, num_sms, stream); }
-   if (a.pa_mass) { return run_fused<false, true>(a, num_sms, stream); }
+   if (a.pa_diff && a.geo) { return a.pa_mass ? run_fused<true, true, true>(a, num_sms, stream) : run_fused<true, false, true>(a, num_sms, stream); }
+   if (a.pa_diff && a.pa_mass) { return run_fused<true, true, false>(a, num_sms, stream); }
+   if (a.pa_diff) { return run_fused<true, false, false>(a, num_sms, stream); }
+   if (a.pa_mass) { return run_fused<false, true, false>(a, num_sms, stream); }
    return (int)cudaErrorInvalidValue;
 }
 

@@ -31,6 +31,7 @@ struct ElemArgs
    double *y = nullptr;
    const int *slot = nullptr;
    const double *pa_diff = nullptr, *pa_mass = nullptr;
+   const double *geo = nullptr;             // EV_APPLY_L2S: factorised diffusion q-data (pa_diff = c_q [Q^3,NE], geo [6,NE])
    const double *J = nullptr;
    const double *f = nullptr, *detJ = nullptr, *W = nullptr;
    long long nf = 0;

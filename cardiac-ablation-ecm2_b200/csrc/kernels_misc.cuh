@@ -226,6 +226,65 @@ __global__ void k_diffusion_setup_trilinear(int Q1D, long long NE, const double 
    }
 }
 
+// Factorised diffusion q-data for meshes of affine (parallelepiped) elements: J is constant over such an element,
+// so the reference's D(q) = (w_q / det J) c_q adj(J) adj(J)^T (bilininteg_diffusion_kernels.cpp:243-367) splits
+// into the per-element tensor below (6 doubles per ELEMENT) and the scalar w_q c_q per q-point.  One thread per
+// element; `flag` is raised when an element is not affine to `tol` (relative to its edge lengths).
+__global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, const int *__restrict__ ev, double tol,
+                                  double *__restrict__ geo6, int *flag)
+{
+   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
+   {
+      const int *v = ev + 8 * e;
+      double X[8][3];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+#pragma unroll
+         for (int r = 0; r < 3; ++r) { X[k][r] = vtx[3LL * v[k] + r]; }
+      }
+      // vertex order of the reference hexahedron (mesh/mesh.cpp:3757-3765): edges a = 0->1, b = 0->3, c = 0->4
+      double dev = 0.0, scale = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+      {
+         const double a = X[1][r] - X[0][r], b = X[3][r] - X[0][r], c = X[4][r] - X[0][r];
+         scale = fmax(scale, fmax(fabs(a), fmax(fabs(b), fabs(c))));
+         dev = fmax(dev, fabs(X[2][r] - (X[0][r] + a + b)));
+         dev = fmax(dev, fabs(X[5][r] - (X[0][r] + a + c)));
+         dev = fmax(dev, fabs(X[7][r] - (X[0][r] + b + c)));
+         dev = fmax(dev, fabs(X[6][r] - (X[0][r] + a + b + c)));
+      }
+      if (!(dev <= tol * scale)) { atomicOr(flag, 1); }
+      double Jm[9];
+      trilinear_jacobian(vtx, v, 0.5, 0.5, 0.5, Jm);
+      const double J11 = Jm[0], J21 = Jm[1], J31 = Jm[2], J12 = Jm[3], J22 = Jm[4], J32 = Jm[5], J13 = Jm[6], J23 = Jm[7], J33 = Jm[8];
+      const double detJ = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13);
+      const double w = 1.0 / detJ;
+      const double A11 = (J22 * J33) - (J23 * J32), A12 = (J32 * J13) - (J12 * J33), A13 = (J12 * J23) - (J22 * J13);
+      const double A21 = (J31 * J23) - (J21 * J33), A22 = (J11 * J33) - (J13 * J31), A23 = (J21 * J13) - (J11 * J23);
+      const double A31 = (J21 * J32) - (J31 * J22), A32 = (J31 * J12) - (J11 * J32), A33 = (J11 * J22) - (J12 * J21);
+      double *g = geo6 + 6 * e;
+      g[0] = w * (A11 * A11 + A12 * A12 + A13 * A13);
+      g[1] = w * (A11 * A21 + A12 * A22 + A13 * A23);
+      g[2] = w * (A11 * A31 + A12 * A32 + A13 * A33);
+      g[3] = w * (A21 * A21 + A22 * A22 + A23 * A23);
+      g[4] = w * (A21 * A31 + A22 * A32 + A23 * A33);
+      g[5] = w * (A31 * A31 + A32 * A32 + A33 * A33);
+   }
+}
+
+// the scalar half of the factorised q-data: c[i] = W[q] C[i]
+__global__ void k_coeff_times_w(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ C, int const_c,
+                                double *__restrict__ out)
+{
+   const long long n = NQ * NE;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      out[i] = W[i % NQ] * (const_c ? C[0] : C[i]);
+   }
+}
+
 // the "user forall over Q-points" of SURVEY §3.2/§3.3
 __global__ void k_coeff_eval(int kind, long long n, double a, double b, double T0, const double *__restrict__ T,
                              const double *__restrict__ s, const double *__restrict__ g, double *__restrict__ out)
@@ -267,6 +326,7 @@ struct DiagParams
    long long NE;
    const double *__restrict__ pa_diff;
    const double *__restrict__ pa_mass;
+   const double *__restrict__ geo; // factorised diffusion q-data: pa_diff = c_q [Q^3,NE], geo = adj(J)adj(J)^T/det J [6,NE]; else null
    double *__restrict__ dE;
 };
 
@@ -289,29 +349,31 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 // factor type of field f = D00, D01, D02, D11, D12, D22, mass in direction a: how many of the two indices
 // of D_ij equal a (0: BB, 1: BG, 2: GG); f and a are compile-time wherever this is used
 #define B200PA_MTYPE(f, a) ((((a) == 0 ? 0x0016u : ((a) == 1 ? 0x0184u : 0x0910u)) >> (2 * (f))) & 3u)
+   const double *geo = P.geo;
+   struct FieldCopy { const double *src; unsigned bytes; };
+   auto scalar_field = [&](const double *arr, double *sdst, long long e0, int nel)
+   {
+      const double *src = arr + e0 * Q3;
+      const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
+      src -= sh;
+      int nd = sh + nel * Q3;
+      if (nd & 1)
+      {
+         if (e0 + nel < NE) { nd += 1; }
+         else { nd -= 1; sdst[nd] = __ldg(src + nd); }
+      }
+      return FieldCopy{src, (unsigned)(nd * sizeof(double))};
+   };
    auto issue = [&](long long b)
    {
       const long long e0 = b * NEB;
       const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
-      unsigned bytes_d = 0, bytes_m = 0;
-      const double *src_m = nullptr;
-      if (pa_diff) { bytes_d = (unsigned)(nel * 6 * Q3 * sizeof(double)); }
-      if (pa_mass)
-      {
-         const double *src = pa_mass + e0 * Q3;
-         const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
-         src_m = src - sh;
-         int nd = sh + nel * Q3;
-         if (nd & 1)
-         {
-            if (e0 + nel < NE) { nd += 1; }
-            else { nd -= 1; sQm[nd] = __ldg(src_m + nd); }
-         }
-         bytes_m = (unsigned)(nd * sizeof(double));
-      }
-      mbar_expect_tx(&qbar, bytes_d + bytes_m);
-      if (pa_diff) { tma_bulk_g2s(sQd, pa_diff + e0 * 6 * Q3, bytes_d, &qbar); }
-      if (pa_mass) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar); }
+      FieldCopy cd{nullptr, 0}, cm{nullptr, 0};
+      if (pa_diff) { cd = geo ? scalar_field(pa_diff, sQd, e0, nel) : FieldCopy{pa_diff + e0 * 6 * Q3, (unsigned)(nel * 6 * Q3 * sizeof(double))}; }
+      if (pa_mass) { cm = scalar_field(pa_mass, sQm, e0, nel); }
+      mbar_expect_tx(&qbar, cd.bytes + cm.bytes);
+      if (pa_diff) { tma_bulk_g2s(sQd, cd.src, cd.bytes, &qbar); }
+      if (pa_mass) { tma_bulk_g2s(sQm, cm.src, cm.bytes, &qbar); }
    };
    const long long nbatch = (NE + NEB - 1) / NEB;
    unsigned phase = 0;
@@ -323,6 +385,7 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
       mbar_wait(&qbar, phase);
       phase ^= 1u;
       const int msh = pa_mass ? (int)(((unsigned long long)(pa_mass + e0 * Q3) >> 3) & 1ull) : 0;
+      const int dsh = (pa_diff && geo) ? (int)(((unsigned long long)(pa_diff + e0 * Q3) >> 3) & 1ull) : 0;
       // pass 1: contract qx.  task = (e, qz, qy), all seven fields: one row of Q1 q-data values each
       for (int t = threadIdx.x; t < nel * Q2; t += blockDim.x)
       {
@@ -331,7 +394,8 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
          for (int f = 0; f < NF; ++f)
          {
             const bool have = f < 6 ? pa_diff != nullptr : pa_mass != nullptr;
-            const double *src = f < 6 ? sQd + (e * 6 + f) * Q3 + row * Q1 : sQm + msh + e * Q3 + row * Q1;
+            const double *src = f < 6 ? (geo ? sQd + dsh + e * Q3 + row * Q1 : sQd + (e * 6 + f) * Q3 + row * Q1) : sQm + msh + e * Q3 + row * Q1;
+            const double scale = (f < 6 && geo && have) ? __ldg(geo + (e0 + e) * 6 + f) : 1.0;
             double out[D1];
 #pragma unroll
             for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
@@ -340,7 +404,7 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 #pragma unroll
                for (int q = 0; q < Q1; ++q)
                {
-                  const double v = src[q];
+                  const double v = scale * src[q];
 #pragma unroll
                   for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 0)][q + Q1 * d], v, out[d]); }
                }

@@ -34,7 +34,9 @@
 namespace b200pa
 {
 
-template <int D, int Q>
+// AFF: diffusion q-data in factorised form (affine elements): one scalar c_q = w_q k_q per q-point and the
+// per-element tensor adj(J) adj(J)^T / det J (6 doubles) instead of 6 doubles per q-point
+template <int D, int Q, bool AFF = false>
 struct ApplyCfg
 {
    static constexpr int D2 = D * D, D3 = D * D * D, Q2 = Q * Q, Q3 = Q * Q * Q;
@@ -44,17 +46,23 @@ struct ApplyCfg
 #ifdef B200PA_TUNE_NEB
    static constexpr int NEB = B200PA_TUNE_NEB;
 #else
-   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 16 : (D == 4) ? 5 : (D == 5) ? 3 : 2;
+   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 16 : (D == 4) ? 5 : (D == 5) ? 3 : (D == 6) ? 2 : 1;
 #endif
 #ifdef B200PA_TUNE_MINB
    static constexpr int MINB = B200PA_TUNE_MINB;
 #else
-   static constexpr int MINB = (D <= 2) ? 3 : (D == 3) ? 2 : (D <= 6) ? 3 : 2; // resident CTAs/SM the register budget allows
+   static constexpr int MINB = (D == 3) ? 2 : 3; // resident CTAs/SM the register budget allows
 #endif
 #ifdef B200PA_TUNE_L2HINT
    static constexpr bool L2HINT = B200PA_TUNE_L2HINT;
 #else
    static constexpr bool L2HINT = (D <= 3); // q-data is read once per apply: L2 evict_first (measured: +3 % at p=2, -4 % at p=5)
+#endif
+   // phase C2 stores its results straight to y_S[slot] (no staging through sX, one barrier less per batch)
+#ifdef B200PA_TUNE_FUSE_OUT
+   static constexpr bool FUSE_OUT = B200PA_TUNE_FUSE_OUT;
+#else
+   static constexpr bool FUSE_OUT = (D != 4); // measured: +2.5 % at p=4, -2 % at p=3, neutral elsewhere (profiles/r1j_*)
 #endif
    static constexpr int NT = ((NEB * Q2 + 31) / 32) * 32;
    static constexpr int NIDX = NEB * D3;                         // E-entries per batch
@@ -90,18 +98,20 @@ struct ApplyCfg
    static constexpr int SX_DOUBLES = NEB * D * SXS;
    static constexpr int SE_DOUBLES = NEB * ES;
    static constexpr int WORK_DOUBLES = 2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * BS;
-   static constexpr int IDX_OFF = WORK_DOUBLES * 8;              // int sGi[2][NIDX], sSl[NIDX]
+   static constexpr int GEO_DOUBLES = AFF ? 2 * NEB * 6 : 0;      // sGeo[2][NEB][6]
+   static constexpr int IDX_OFF = (WORK_DOUBLES + GEO_DOUBLES) * 8; // int sGi[2][NIDX], sSl[NIDX]
    static constexpr int QD_OFF = (IDX_OFF + 3 * NIDX * 4 + 15) & ~15;
-   static constexpr int SQD_DOUBLES = NEB * QES + 2;
+   static constexpr int SQD_DOUBLES = AFF ? (((NEB * QMS + 2) + 1) & ~1) : NEB * QES + 2;
    static constexpr int SQM_DOUBLES = ((NEB * QMS + 2) + 1) & ~1;
    static constexpr size_t SMEM_BYTES = QD_OFF + sizeof(double) * (SQD_DOUBLES + SQM_DOUBLES);
 };
 
-template <int D, int Q, bool DIFF, bool MASS>
-__global__ void __launch_bounds__(ApplyCfg<D, Q>::NT, ApplyCfg<D, Q>::MINB)
+template <int D, int Q, bool DIFF, bool MASS, bool AFF = false>
+__global__ void __launch_bounds__(ApplyCfg<D, Q, AFF>::NT, ApplyCfg<D, Q, AFF>::MINB)
 pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
 {
-   using C = ApplyCfg<D, Q>;
+   static_assert(!AFF || DIFF, "the factorised q-data is the diffusion integrator's");
+   using C = ApplyCfg<D, Q, AFF>;
    constexpr int D2 = C::D2, D3 = C::D3, Q2 = C::Q2, Q3 = C::Q3, NEB = C::NEB, NT = C::NT, NIO = C::NIO, NIDX = C::NIDX;
    constexpr int SXS = C::SXS, SQ = C::SQ, ES = C::ES, RQ = C::RQ, BS = C::BS;
 #define Bm(q, d) P.bg.B[(q) + Q * (d)]
@@ -111,6 +121,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    double *sE = sX + 2 * C::SX_DOUBLES;
    double *sBt = sE + C::SE_DOUBLES; // sBt[qy*BS + dy] = B(qy,dy): the one runtime-indexed row of phase A
    double *sGt = sBt + Q * BS;
+   double *sGeo = sGt + Q * BS;                                // AFF: sGeo[2][NEB][6], one batch ahead
    int *sGi = reinterpret_cast<int *>(smem_raw + C::IDX_OFF);  // sGi[2][NIDX]: gather indices, two batches deep
    int *sSl = sGi + 2 * NIDX;                                  // sSl[NIDX]: slots of this batch
    double *sQd = reinterpret_cast<double *>(smem_raw + C::QD_OFF); // this batch's diffusion q-data (16-byte aligned)
@@ -169,48 +180,58 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    };
 
    // two bulk copies per batch (the batch's elements are contiguous in both q-data arrays).
-   // The mass array's element stride (Q^3 doubles) is odd for odd Q, so its copy starts at the
-   // 16-byte boundary below the batch and `mshift` (0 or 1 doubles) finds the data again.
-   int mshift = 0;
+   // A scalar q-field (mass; AFF: the diffusion coefficient too) has an element stride of Q^3 doubles, odd for
+   // odd Q, so its copy starts at the 16-byte boundary below the batch and a shift of 0 or 1 doubles finds the
+   // data again; the very last double of the array is fetched with a plain load (never read past the buffer).
+   struct FieldCopy { const double *src; unsigned bytes; };
+   auto scalar_field = [&](const double *arr, double *sdst, long long e0, int nel)
+   {
+      const double *src = arr + e0 * Q3;
+      const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
+      src -= sh;
+      int nd = sh + nel * Q3;
+      if (nd & 1)
+      {
+         if (e0 + nel < P.NE) { nd += 1; }
+         else { nd -= 1; sdst[nd] = __ldg(src + nd); }
+      }
+      return FieldCopy{src, (unsigned)(nd * sizeof(double))};
+   };
+   auto field_shift = [&](const double *arr, int b) { return (int)(((unsigned long long)(arr + (long long)b * NEB * Q3) >> 3) & 1ull); };
+   int mshift = 0, dshift = 0;
    auto tma_issue = [&](int b)
    {
       const long long e0 = (long long)b * NEB;
       const int nel = (int)(P.NE - e0 < NEB ? P.NE - e0 : NEB);
-      unsigned bytes_d = 0, bytes_m = 0;
-      const double *src_m = nullptr;
-      if (DIFF) { bytes_d = (unsigned)(nel * 6 * Q3 * sizeof(double)); }
-      if (MASS)
+      constexpr bool PADDED = C::QES != 6 * Q3 || C::QMS != Q3; // even Q: every element starts 16-byte aligned, no shift
+      FieldCopy cd{nullptr, 0}, cm{nullptr, 0};
+      if (DIFF) { cd = AFF ? scalar_field(P.pa_diff, sQd, e0, nel) : FieldCopy{P.pa_diff + e0 * 6 * Q3, (unsigned)(nel * 6 * Q3 * sizeof(double))}; }
+      if (MASS) { cm = scalar_field(P.pa_mass, sQm, e0, nel); }
+      mbar_expect_tx(&qbar, cd.bytes + cm.bytes);
+      if (PADDED)
       {
-         const double *src = P.pa_mass + e0 * Q3;
-         const int sh = (int)(((unsigned long long)src >> 3) & 1ull);
-         src_m = src - sh;
-         int nd = sh + nel * Q3;
-         if (nd & 1)
-         {
-            // 16-byte granularity: take one double more, except at the very end of the array, where the
-            // last double is fetched with a plain load instead (never read past the caller's buffer)
-            if (e0 + nel < P.NE) { nd += 1; }
-            else { nd -= 1; sQm[nd] = __ldg(src_m + nd); }
-         }
-         bytes_m = (unsigned)(nd * sizeof(double));
-      }
-      mbar_expect_tx(&qbar, bytes_d + bytes_m);
-      if (C::QES != 6 * Q3 || C::QMS != Q3)
-      {
-         // padded staging (even Q: every element starts 16-byte aligned in both arrays, no shift)
          for (int e = 0; e < nel; ++e)
          {
-            if (DIFF) { tma_bulk_g2s(sQd + e * C::QES, P.pa_diff + (e0 + e) * 6 * Q3, (unsigned)(6 * Q3 * sizeof(double)), &qbar, pol); }
+            if (DIFF && !AFF) { tma_bulk_g2s(sQd + e * C::QES, P.pa_diff + (e0 + e) * 6 * Q3, (unsigned)(6 * Q3 * sizeof(double)), &qbar, pol); }
+            if (DIFF && AFF) { tma_bulk_g2s(sQd + e * C::QMS, P.pa_diff + (e0 + e) * Q3, (unsigned)(Q3 * sizeof(double)), &qbar, pol); }
             if (MASS) { tma_bulk_g2s(sQm + e * C::QMS, P.pa_mass + (e0 + e) * Q3, (unsigned)(Q3 * sizeof(double)), &qbar, pol); }
          }
       }
       else
       {
-         if (DIFF) { tma_bulk_g2s(sQd, P.pa_diff + e0 * 6 * Q3, bytes_d, &qbar, pol); }
-         if (MASS) { tma_bulk_g2s(sQm, src_m, bytes_m, &qbar, pol); }
+         if (DIFF) { tma_bulk_g2s(sQd, cd.src, cd.bytes, &qbar, pol); }
+         if (MASS) { tma_bulk_g2s(sQm, cm.src, cm.bytes, &qbar, pol); }
       }
    };
-   auto mass_shift = [&](int b) { return (int)(((unsigned long long)(P.pa_mass + (long long)b * NEB * Q3) >> 3) & 1ull); };
+   // AFF: the per-element tensors of a batch, 6 doubles each, by 8-byte cp.async (threads < 6 NEB)
+   auto copy_geo = [&](double *dst, int b)
+   {
+      if (AFF && tid < NEB * 6)
+      {
+         const long long i = (long long)b * NEB * 6 + tid;
+         cp_async8_zfill(dst + tid, P.geo + (i < (long long)P.NE * 6 ? i : 0), i < (long long)P.NE * 6);
+      }
+   };
    unsigned qphase = 0;
    if (tid == 0) { mbar_init(&qbar, 1); }
    __syncthreads();
@@ -219,6 +240,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    if (batch < nbatch)
    {
       if (tid == 0) { tma_issue(batch); }
+      copy_geo(sGeo, batch);
       copy_idx(sGi, P.gmap, batch);
       if (batch + (int)gridDim.x < nbatch) { copy_idx(sGi + NIDX, P.gmap, batch + gridDim.x); }
       cp_async_commit();
@@ -239,6 +261,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       if (next < nbatch) { gather_x(sX + (cur ^ 1) * C::SX_DOUBLES, sGi + (cur ^ 1) * NIDX); }
       if (next + (int)gridDim.x < nbatch) { copy_idx(sGi + cur * NIDX, P.gmap, next + gridDim.x); }
       copy_idx(sSl, P.slot, batch);
+      if (next < nbatch) { copy_geo(sGeo + (cur ^ 1) * NEB * 6, next); }
       cp_async_commit();
 
       // ------------------------------------ phase A: (slab, qy) rows, y then x
@@ -288,13 +311,22 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       // -------------------------------- phase B: column, q-point op, column^T
       mbar_wait(&qbar, qphase);
       qphase ^= 1u;
-      if (MASS) { mshift = mass_shift(batch); }
-      const double *qd = sQd + eB * C::QES + cB;         // this thread's column in the staged q-data
+      if (MASS) { mshift = C::QMS != Q3 ? 0 : field_shift(P.pa_mass, batch); }
+      if (AFF) { dshift = C::QMS != Q3 ? 0 : field_shift(P.pa_diff, batch); }
+      // this thread's column in the staged q-data
+      const double *qd = AFF ? sQd + dshift + eB * C::QMS + cB : sQd + eB * C::QES + cB;
       const double *qm = sQm + mshift + eB * C::QMS + cB;
       if (actB)
       {
          double *s = sE + eB * ES + (cB / Q) * RQ + (cB % Q);
          double f0[D], f1[D], f2[D], p0[D], p1[D], p2[D];
+         double Ce[6];
+         if (AFF)
+         {
+            const double *g = sGeo + cur * NEB * 6 + eB * 6;
+            B200PA_UNROLL
+            for (int k = 0; k < 6; ++k) { Ce[k] = g[k]; }
+         }
          B200PA_UNROLL
          for (int dz = 0; dz < D; ++dz)
          {
@@ -320,11 +352,21 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             double hX = 0.0, hY = 0.0, hZ = 0.0, hM = 0.0;
             if (DIFF)
             {
-               const double *d = qd + qz * Q2;
-               const double o0 = d[0], o1 = d[Q3], o2 = d[2 * Q3], o3 = d[3 * Q3], o4 = d[4 * Q3], o5 = d[5 * Q3];
-               hX = o0 * gX + o1 * gY + o2 * gZ;
-               hY = o1 * gX + o3 * gY + o4 * gZ;
-               hZ = o2 * gX + o4 * gY + o5 * gZ;
+               if (AFF)
+               {
+                  const double c = qd[qz * Q2];
+                  hX = c * (Ce[0] * gX + Ce[1] * gY + Ce[2] * gZ);
+                  hY = c * (Ce[1] * gX + Ce[3] * gY + Ce[4] * gZ);
+                  hZ = c * (Ce[2] * gX + Ce[4] * gY + Ce[5] * gZ);
+               }
+               else
+               {
+                  const double *d = qd + qz * Q2;
+                  const double o0 = d[0], o1 = d[Q3], o2 = d[2 * Q3], o3 = d[3 * Q3], o4 = d[4 * Q3], o5 = d[5 * Q3];
+                  hX = o0 * gX + o1 * gY + o2 * gZ;
+                  hY = o1 * gX + o3 * gY + o4 * gZ;
+                  hZ = o2 * gX + o4 * gY + o5 * gZ;
+               }
             }
             if (MASS) { hM = qm[qz * Q2] * val; }
             B200PA_UNROLL
@@ -382,6 +424,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             if (DIFF) { io[1 * D * SQ + dx] = s1; }
          }
       }
+      if (C::FUSE_OUT) { cp_async_wait_all(); } // the slots of this batch (any thread's copy) are read after the barrier
       __syncthreads();
 
       // ----------------------------------------------- phase C2: (slab, dx) columns, y^T
@@ -405,10 +448,25 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
                if (DIFF) { out[dy] = fma(Gm(qy, dy), b, out[dy]); }
             }
          }
-         double *xs = sXout + slab * SXS + dx;
-         B200PA_UNROLL
-         for (int dy = 0; dy < D; ++dy) { xs[dy * D] = out[dy]; }
+         if (C::FUSE_OUT)
+         {
+            // slot = position in the E->L CSR (copied into sSl a whole batch ago; < 0 beyond the last element)
+            const int *sl = sSl + slab * D2 + dx;
+            B200PA_UNROLL
+            for (int dy = 0; dy < D; ++dy)
+            {
+               const int k = sl[dy * D];
+               if (k >= 0) { P.y[k] = out[dy]; }
+            }
+         }
+         else
+         {
+            double *xs = sXout + slab * SXS + dx;
+            B200PA_UNROLL
+            for (int dy = 0; dy < D; ++dy) { xs[dy * D] = out[dy]; }
+         }
       }
+      if (C::FUSE_OUT) { continue; }
       __syncthreads();
 
       // --------------------------------------------------------------- stage-out

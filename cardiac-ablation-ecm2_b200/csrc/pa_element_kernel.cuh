@@ -51,6 +51,7 @@ struct ElemParams
    const int *__restrict__ slot;       // OUT_SLOT
    const double *__restrict__ pa_diff; // [Q^3,6,NE] or null
    const double *__restrict__ pa_mass; // [Q^3,NE]   or null
+   const double *__restrict__ geo;     // pa_apply_kernel<.., AFF>: adj(J) adj(J)^T / det J per element [6,NE]; pa_diff is then [Q^3,NE]
    const double *__restrict__ J;       // QOP_PHYSGRAD: [Q^3,3,3,NE]
    const double *__restrict__ f;       // QOP_LF: f [Q^3,NE] or 1 value
    const double *__restrict__ detJ;    // QOP_LF

@@ -58,6 +58,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                 : "memory");
 }
 
+// L2 prefetch of a contiguous global range by the TMA unit: nothing is written to shared memory and no LSU
+// wavefront is spent; `src` 16-byte aligned, `bytes` a multiple of 16
+__device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, unsigned bytes)
+{
+   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+// streaming 8-byte load (read-only path, no L1 allocation): q-data that was prefetched into L2
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+   double v;
+   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); // volatile: issued where written
+   return v;
+}
+
 // ---- per-thread asynchronous copies global -> shared (LDGSTS): no register is tied up while the data flies
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
 {

@@ -141,6 +141,10 @@ int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, const double
  * per q-point) unless it is asked for through b200pa_space_J(). */
 int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv,
                                         const double *vertices_any, const int *elem_vertices_any);
+/* 1 when every element of a space given by its vertices is affine (a parallelepiped to 1e-13 of its edge
+ * lengths; decided on the device), 0 otherwise, -1 for a NULL space.  Affine meshes admit the factorised
+ * diffusion q-data below. */
+int b200pa_space_is_affine(b200pa_space sp);
 /* read-only accessors to the device arrays (for tests and for the host mirror) */
 const int *b200pa_space_offsets(b200pa_space sp);
 const int *b200pa_space_indices(b200pa_space sp);
@@ -177,6 +181,14 @@ int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, long long nc);
 int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev, const double *pa_mass_dev);
 const double *b200pa_form_pa_diff(b200pa_form f);
 const double *b200pa_form_pa_mass(b200pa_form f);
+/* Factorised diffusion q-data.  On an affine element J is constant, so the reference's
+ * D(q) = (w_q / det J) c_q adj(J) adj(J)^T (PADiffusionSetup3D, bilininteg_diffusion_kernels.cpp:243-367) is the
+ * product of a per-ELEMENT tensor (6 doubles, kept by the space) and the scalar w_q c_q: 8 instead of 48 bytes per
+ * q-point for AssemblePA to write and AddMultPA / AssembleDiagonalPA to read.  on = 1: the following
+ * b200pa_form_assemble_diffusion calls store that form (b200pa_form_pa_diff then returns w_q c_q [Q^3,NE]); they
+ * fail, loudly, when b200pa_space_is_affine() is not 1.  Results agree with the stored form to rounding. */
+int b200pa_form_set_factorised(b200pa_form f, int on);
+int b200pa_form_is_factorised(b200pa_form f);
 /* ConstrainedOperator ctor (linalg/operator.cpp:511-526): essential true-dof list, DIAG_ONE */
 int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any);
 /* PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487-564): y = A x, L→L, unconstrained.
