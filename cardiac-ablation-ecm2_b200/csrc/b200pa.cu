@@ -602,6 +602,21 @@ extern "C" int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, c
    {
       if (borrow_or_copy(sp->ctx, J_any, 9 * (size_t)sp->nQ, sp->J)) { return 1; }
       sp->vtx.release(); sp->ev.release(); sp->hxi.clear(); // the host's Jacobians win over a trilinear rebuild
+      // per-element tensor of the factorised q-data + "every element is affine" (b200pa_space_is_affine)
+      sp->affine = false;
+      if (sp->ne > 0)
+      {
+         b200pa_ctx ctx = sp->ctx;
+         if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne)) { return 1; }
+         int *dflag = (int *)(ctx->d_ticket + 3);
+         B200PA_CK(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+         k_affine_from_J<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>((long long)q3, sp->ne, sp->J.as<double>(), 1e-13, sp->geo6.as<double>(), dflag);
+         B200PA_LAUNCHED();
+         int flag = 1;
+         B200PA_CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+         B200PA_CK(cudaStreamSynchronize(ctx->stream));
+         sp->affine = (flag == 0);
+      }
    }
    if (detJ_any) { if (borrow_or_copy(sp->ctx, detJ_any, (size_t)sp->nQ, sp->detJ)) { return 1; } }
    return 0;
@@ -825,8 +840,8 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
    if (f->want_factorised)
    {
       // no silent change of representation: the caller asked for the factorised q-data, the mesh must allow it
-      B200PA_REQUIRE(sp->affine && sp->geo6.p, "assemble_diffusion: factorised q-data needs a mesh of affine elements given by its "
-                                               "vertices (b200pa_space_geometry_from_vertices)");
+      B200PA_REQUIRE(sp->affine && sp->geo6.p, "assemble_diffusion: factorised q-data needs a mesh whose elements are all affine "
+                                               "(b200pa_space_is_affine)");
       f->pa_diff.release(); // size differs from the stored form
       int rcf = alloc(f->pa_diff, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1));
       if (!rcf && sp->ne > 0)

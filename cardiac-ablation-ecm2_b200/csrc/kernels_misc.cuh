@@ -274,6 +274,38 @@ __global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, 
    }
 }
 
+// The same per-element tensor from stored Jacobians (the host's GeometricFactors): J is taken at the first q-point
+// and the element counts as affine when no entry of J moves by more than tol * max|J| over its q-points.
+__global__ void k_affine_from_J(long long NQ, long long NE, const double *__restrict__ J, double tol, double *__restrict__ geo6, int *flag)
+{
+   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
+   {
+      const double *Je = J + e * 9 * NQ;
+      double J0[9], scale = 0.0, dev = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { J0[k] = Je[k * NQ]; scale = fmax(scale, fabs(J0[k])); }
+      for (long long q = 1; q < NQ; ++q)
+      {
+#pragma unroll
+         for (int k = 0; k < 9; ++k) { dev = fmax(dev, fabs(Je[k * NQ + q] - J0[k])); }
+      }
+      if (!(dev <= tol * scale)) { atomicOr(flag, 1); }
+      const double J11 = J0[0], J21 = J0[1], J31 = J0[2], J12 = J0[3], J22 = J0[4], J32 = J0[5], J13 = J0[6], J23 = J0[7], J33 = J0[8];
+      const double detJ = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13);
+      const double w = 1.0 / detJ;
+      const double A11 = (J22 * J33) - (J23 * J32), A12 = (J32 * J13) - (J12 * J33), A13 = (J12 * J23) - (J22 * J13);
+      const double A21 = (J31 * J23) - (J21 * J33), A22 = (J11 * J33) - (J13 * J31), A23 = (J21 * J13) - (J11 * J23);
+      const double A31 = (J21 * J32) - (J31 * J22), A32 = (J31 * J12) - (J11 * J32), A33 = (J11 * J22) - (J12 * J21);
+      double *g = geo6 + 6 * e;
+      g[0] = w * (A11 * A11 + A12 * A12 + A13 * A13);
+      g[1] = w * (A11 * A21 + A12 * A22 + A13 * A23);
+      g[2] = w * (A11 * A31 + A12 * A32 + A13 * A33);
+      g[3] = w * (A21 * A21 + A22 * A22 + A23 * A23);
+      g[4] = w * (A21 * A31 + A22 * A32 + A23 * A33);
+      g[5] = w * (A31 * A31 + A32 * A32 + A33 * A33);
+   }
+}
+
 // the scalar half of the factorised q-data: c[i] = W[q] C[i]
 __global__ void k_coeff_times_w(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ C, int const_c,
                                 double *__restrict__ out)

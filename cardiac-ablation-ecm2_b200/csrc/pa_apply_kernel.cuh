@@ -46,12 +46,12 @@ struct ApplyCfg
 #ifdef B200PA_TUNE_NEB
    static constexpr int NEB = B200PA_TUNE_NEB;
 #else
-   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? 16 : (D == 4) ? 5 : (D == 5) ? 3 : (D == 6) ? 2 : 1;
+   static constexpr int NEB = (D == 2) ? 28 : (D == 3) ? (AFF ? 8 : 16) : (D == 4) ? 5 : (D == 5) ? 3 : (D == 6) ? 2 : 1;
 #endif
 #ifdef B200PA_TUNE_MINB
    static constexpr int MINB = B200PA_TUNE_MINB;
 #else
-   static constexpr int MINB = (D == 3) ? 2 : 3; // resident CTAs/SM the register budget allows
+   static constexpr int MINB = (D == 3) ? (AFF ? 4 : 2) : (D == 7 && AFF) ? 5 : 3; // resident CTAs/SM the register budget allows
 #endif
 #ifdef B200PA_TUNE_L2HINT
    static constexpr bool L2HINT = B200PA_TUNE_L2HINT;

@@ -204,8 +204,10 @@ class PAOperator : public mfem::Operator
       out.assign(cv.HostRead(), cv.HostRead() + cv.Size());
    }
 public:
+   /// factorised = true: on a mesh whose elements are all affine (b200pa_space_is_affine) the diffusion q-data is kept
+   /// as w_q c_q per q-point + one tensor per element (b200pa_form_set_factorised); other meshes keep the stored form
    PAOperator(const mfem::FiniteElementSpace &fes_, mfem::Coefficient *kdiff, mfem::Coefficient *cmass,
-              const mfem::Array<int> &ess_tdof_list)
+              const mfem::Array<int> &ess_tdof_list, bool factorised = false)
       : mfem::Operator(fes_.GetVSize()), fes(fes_)
    {
       const mfem::FiniteElement &el = *fes.GetTypicalFE();
@@ -222,6 +224,7 @@ public:
                                               *ir, mfem::GeometricFactors::JACOBIANS | mfem::GeometricFactors::DETERMINANTS);
       Check(b200pa_space_set_geometry(sp, ir->GetWeights().HostRead(), geom->J.HostRead(), geom->detJ.HostRead()));
       Check(b200pa_form_create(sp, &form));
+      if (factorised && b200pa_space_is_affine(sp) == 1) { Check(b200pa_form_set_factorised(form, 1)); }
       std::vector<double> q;
       if (kdiff) { Project(kdiff, q); Check(b200pa_form_assemble_diffusion(form, q.data(), (long long)q.size())); }
       if (cmass) { Project(cmass, q); Check(b200pa_form_assemble_mass(form, q.data(), (long long)q.size())); }
@@ -229,6 +232,7 @@ public:
       Check(b200pa_form_set_essential(form, ess.Size(), ess.HostRead()));
    }
    ~PAOperator() { b200pa_form_destroy(form); b200pa_space_destroy(sp); }
+   bool Factorised() const { return b200pa_form_is_factorised(form) == 1; }
 
    /// ≙ ConstrainedOperator::Mult (linalg/operator.cpp:710-714) of the PA form, host vectors
    void Mult(const mfem::Vector &x, mfem::Vector &y) const override

@@ -141,8 +141,9 @@ int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, const double
  * per q-point) unless it is asked for through b200pa_space_J(). */
 int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv,
                                         const double *vertices_any, const int *elem_vertices_any);
-/* 1 when every element of a space given by its vertices is affine (a parallelepiped to 1e-13 of its edge
- * lengths; decided on the device), 0 otherwise, -1 for a NULL space.  Affine meshes admit the factorised
+/* 1 when every element of the space is affine (vertices: a parallelepiped to 1e-13 of its edge lengths; stored
+ * Jacobians: J constant over the element's q-points to 1e-13; decided on the device when the geometry is set),
+ * 0 otherwise, -1 for a NULL space.  Affine meshes admit the factorised
  * diffusion q-data below. */
 int b200pa_space_is_affine(b200pa_space sp);
 /* read-only accessors to the device arrays (for tests and for the host mirror) */

@@ -32,9 +32,12 @@ def test_all_golden_meshes_are_affine(ctx, dev):
     sp.close()
 
 
-def test_factorised_mult_diag_match_reference(ctx, dev):
+@pytest.mark.parametrize("geometry", ["vertices", "given"])
+def test_factorised_mult_diag_match_reference(ctx, dev, geometry):
+    """geometry from the vertices, or the reference's own Jacobians (what the MFEM binding passes)"""
     c = dev.c
-    sp = dev.space(geometry="vertices")
+    sp = dev.space(geometry=geometry)
+    assert sp.affine
     f = fact_form(dev, sp)
     assert f.factorised
     close(ctx.to_host(f.mult(dev["x"])), c["y"])
