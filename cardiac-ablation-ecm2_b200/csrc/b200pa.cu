@@ -862,6 +862,14 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
    {
       rc = b200pa_diffusion_setup(sp->ctx, sp->q1d, sp->ne, sp->W.as<double>(), sp->J.as<double>(), (const double *)dC, nc, f->pa_diff.as<double>());
    }
+   else if (!rc && sp->ne > 0 && sp->affine && sp->geo6.p)
+   {
+      const long long NQ = (long long)sp->q1d * sp->q1d * sp->q1d;
+      k_diffusion_setup_affine<<<grid1d(sp->ctx, sp->nQ), 256, 0, sp->ctx->stream>>>(NQ, sp->ne, sp->W.as<double>(), sp->geo6.as<double>(),
+                                                                                   (const double *)dC, nc == 1, f->pa_diff.as<double>());
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("diffusion set-up kernel launch failed"); }
+   }
    else if (!rc && sp->ne > 0)
    {
       k_diffusion_setup_trilinear<<<grid1d(sp->ctx, sp->nQ), 256, 0, sp->ctx->stream>>>(sp->q1d, sp->ne, sp->W.as<double>(), sp->dxi.as<double>(),

@@ -99,11 +99,19 @@ struct ApplyCfg
    static constexpr int SE_DOUBLES = NEB * ES;
    static constexpr int WORK_DOUBLES = 2 * SX_DOUBLES + SE_DOUBLES + 2 * Q * BS;
    static constexpr int GEO_DOUBLES = AFF ? 2 * NEB * 6 : 0;      // sGeo[2][NEB][6]
-   static constexpr int IDX_OFF = (WORK_DOUBLES + GEO_DOUBLES) * 8; // int sGi[2][NIDX], sSl[NIDX]
-   static constexpr int QD_OFF = (IDX_OFF + 3 * NIDX * 4 + 15) & ~15;
+   static constexpr int IDX_OFF = (WORK_DOUBLES + GEO_DOUBLES) * 8; // int sGi[2][NIDX], sSl[2][NIDX]
+   static constexpr int QD_OFF = (IDX_OFF + 4 * NIDX * 4 + 15) & ~15;
    static constexpr int SQD_DOUBLES = AFF ? (((NEB * QMS + 2) + 1) & ~1) : NEB * QES + 2;
    static constexpr int SQM_DOUBLES = ((NEB * QMS + 2) + 1) & ~1;
-   static constexpr size_t SMEM_BYTES = QD_OFF + sizeof(double) * (SQD_DOUBLES + SQM_DOUBLES);
+   // q-data stages: 2 = the next batch's q-data is requested a whole batch ahead into a second stage.  Measured on
+   // the factorised form (small stages): no gain at p <= 4, -10 % at p = 6 (profiles/r1l_*): one stage everywhere
+#ifdef B200PA_TUNE_QSTAGES
+   static constexpr int QSTAGES = B200PA_TUNE_QSTAGES;
+#else
+   static constexpr int QSTAGES = 1;
+#endif
+   static_assert(QSTAGES == 1 || QSTAGES == 2, "one or two q-data stages");
+   static constexpr size_t SMEM_BYTES = QD_OFF + sizeof(double) * QSTAGES * (SQD_DOUBLES + SQM_DOUBLES);
 };
 
 template <int D, int Q, bool DIFF, bool MASS, bool AFF = false>
@@ -123,10 +131,10 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    double *sGt = sBt + Q * BS;
    double *sGeo = sGt + Q * BS;                                // AFF: sGeo[2][NEB][6], one batch ahead
    int *sGi = reinterpret_cast<int *>(smem_raw + C::IDX_OFF);  // sGi[2][NIDX]: gather indices, two batches deep
-   int *sSl = sGi + 2 * NIDX;                                  // sSl[NIDX]: slots of this batch
-   double *sQd = reinterpret_cast<double *>(smem_raw + C::QD_OFF); // this batch's diffusion q-data (16-byte aligned)
-   double *sQm = sQd + C::SQD_DOUBLES;                         //           and mass q-data
-   __shared__ unsigned long long qbar;                         // "q-data of the current batch has landed"
+   int *sSl = sGi + 2 * NIDX;                                  // sSl[2][NIDX]: slots, one batch ahead
+   double *sQ0 = reinterpret_cast<double *>(smem_raw + C::QD_OFF); // q-data stages (16-byte aligned): diffusion, then mass
+   constexpr int QST = C::SQD_DOUBLES + C::SQM_DOUBLES;
+   __shared__ unsigned long long qbars[2];                     // "the q-data of stage s has landed"
    const int tid = threadIdx.x;
    if (P.done && *P.done) { return; }
    const int nbatch = (P.NE + NEB - 1) / NEB;
@@ -199,8 +207,10 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
    };
    auto field_shift = [&](const double *arr, int b) { return (int)(((unsigned long long)(arr + (long long)b * NEB * Q3) >> 3) & 1ull); };
    int mshift = 0, dshift = 0;
-   auto tma_issue = [&](int b)
+   auto tma_issue = [&](int b, int stage)
    {
+      double *sQd = sQ0 + stage * QST, *sQm = sQd + C::SQD_DOUBLES;
+      unsigned long long &qbar = qbars[stage];
       const long long e0 = (long long)b * NEB;
       const int nel = (int)(P.NE - e0 < NEB ? P.NE - e0 : NEB);
       constexpr bool PADDED = C::QES != 6 * Q3 || C::QMS != Q3; // even Q: every element starts 16-byte aligned, no shift
@@ -232,14 +242,15 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          cp_async8_zfill(dst + tid, P.geo + (i < (long long)P.NE * 6 ? i : 0), i < (long long)P.NE * 6);
       }
    };
-   unsigned qphase = 0;
-   if (tid == 0) { mbar_init(&qbar, 1); }
+   unsigned qphase = 0; // bit s: parity of stage s
+   if (tid == 0) { mbar_init(&qbars[0], 1); mbar_init(&qbars[1], 1); }
    __syncthreads();
 
    int batch = blockIdx.x;
    if (batch < nbatch)
    {
-      if (tid == 0) { tma_issue(batch); }
+      if (tid == 0) { tma_issue(batch, 0); }
+      copy_idx(sSl, P.slot, batch);
       copy_geo(sGeo, batch);
       copy_idx(sGi, P.gmap, batch);
       if (batch + (int)gridDim.x < nbatch) { copy_idx(sGi + NIDX, P.gmap, batch + gridDim.x); }
@@ -260,9 +271,10 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();                     // x of this batch has landed; everybody is done with the previous batch
       if (next < nbatch) { gather_x(sX + (cur ^ 1) * C::SX_DOUBLES, sGi + (cur ^ 1) * NIDX); }
       if (next + (int)gridDim.x < nbatch) { copy_idx(sGi + cur * NIDX, P.gmap, next + gridDim.x); }
-      copy_idx(sSl, P.slot, batch);
-      if (next < nbatch) { copy_geo(sGeo + (cur ^ 1) * NEB * 6, next); }
+      if (next < nbatch) { copy_idx(sSl + (cur ^ 1) * NIDX, P.slot, next); copy_geo(sGeo + (cur ^ 1) * NEB * 6, next); }
       cp_async_commit();
+      // two q-data stages: the next batch's q-data is requested now, a whole batch ahead
+      if (C::QSTAGES == 2 && next < nbatch && tid == 0) { tma_issue(next, cur ^ 1); }
 
       // ------------------------------------ phase A: (slab, qy) rows, y then x
       for (int task = tid; task < NEB * D * Q; task += NT)
@@ -309,8 +321,10 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // -------------------------------- phase B: column, q-point op, column^T
-      mbar_wait(&qbar, qphase);
-      qphase ^= 1u;
+      const int qs = C::QSTAGES == 2 ? cur : 0;
+      mbar_wait(&qbars[qs], (qphase >> qs) & 1u);
+      qphase ^= 1u << qs;
+      const double *sQd = sQ0 + qs * QST, *sQm = sQd + C::SQD_DOUBLES;
       if (MASS) { mshift = C::QMS != Q3 ? 0 : field_shift(P.pa_mass, batch); }
       if (AFF) { dshift = C::QMS != Q3 ? 0 : field_shift(P.pa_diff, batch); }
       // this thread's column in the staged q-data
@@ -391,7 +405,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
       // every thread is done reading the staged q-data: refill the buffer with the next batch; the copy
       // flies during phases C1/C2, stage-out, stage-in and phase A of the next batch
-      if (next < nbatch && tid == 0) { tma_issue(next); }
+      if (C::QSTAGES == 1 && next < nbatch && tid == 0) { tma_issue(next, 0); }
 
       // ----------------------------------------------- phase C1: (slab, qy) rows, x^T
       for (int task = tid; task < NEB * D * Q; task += NT)
@@ -424,7 +438,6 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
             if (DIFF) { io[1 * D * SQ + dx] = s1; }
          }
       }
-      if (C::FUSE_OUT) { cp_async_wait_all(); } // the slots of this batch (any thread's copy) are read after the barrier
       __syncthreads();
 
       // ----------------------------------------------- phase C2: (slab, dx) columns, y^T
@@ -451,7 +464,7 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
          if (C::FUSE_OUT)
          {
             // slot = position in the E->L CSR (copied into sSl a whole batch ago; < 0 beyond the last element)
-            const int *sl = sSl + slab * D2 + dx;
+            const int *sl = sSl + cur * NIDX + slab * D2 + dx;
             B200PA_UNROLL
             for (int dy = 0; dy < D; ++dy)
             {
@@ -470,14 +483,13 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       __syncthreads();
 
       // --------------------------------------------------------------- stage-out
-      cp_async_wait_all();                 // own slot entries (issued a whole batch ago)
       B200PA_UNROLL
       for (int r = 0; r < NIO; ++r)
       {
          const int t = tid + r * NT;
          if (t < NIDX)
          {
-            const int sl = sSl[t];
+            const int sl = sSl[cur * NIDX + t];
             if (sl >= 0)
             {
                const int slab = t / D2, k = t - slab * D2;

@@ -3,7 +3,7 @@
 # usage (GPU box): [QDATA=factorised] bash tools/tune_run.sh [N_for_p2]   (parity of the chosen variant is checked by the test-suite afterwards)
 declare -A NEL=([2]=200 [3]=100 [4]=67 [5]=50 [6]=40 [7]=34)
 [ -n "$1" ] && NEL[3]=$1
-for so in cardiac-ablation-ecm2_b200/libb200pa.so cardiac-ablation-ecm2_b200/libb200pa_d*.so; do
+for so in cardiac-ablation-ecm2_b200/libb200pa.so $(ls cardiac-ablation-ecm2_b200/libb200pa_d*.so 2>/dev/null); do
   name=$(basename $so .so)
   if [ "$name" == "libb200pa" ]; then ds="2 3 4 5 6 7"; else ds=$(echo $name | sed 's/libb200pa_d\([0-9]\)_.*/\1/'); fi
   for D in $ds; do
