@@ -3,28 +3,29 @@
 // (fem/restriction.cpp:109-129, fem/bilinearform_ext.cpp:543-557,
 //  fem/integ/bilininteg_diffusion_kernels.hpp:989-1214, fem/integ/bilininteg_mass_kernels.hpp:807-1033).
 //
-// Second design, driven by the first ncu capture (profiles/r1a_*): the slab/column kernel moved the
-// right bytes (DRAM traffic = algorithmic bytes) but kept only ~21 KB per SM in flight - HBM latency
-// bound at 39 % of peak with 25 % occupancy.  Changes:
-//   * small batches (NEB elements, NEB*Q^2 = one q-point column per thread) whose q-data is ONE
-//     contiguous range of each q-data array, fetched one batch ahead: thread 0 issues two TMA bulk
-//     copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) right after batch b's columns are
-//     done, and the copy flies during the whole of phases C/out/in/A of the next batch
-//     (3-4 CTAs/SM x 29-36 KB = 100-140 KB per SM in flight, Little's law needs ~45 KB); no register
-//     is tied up by the prefetch (the register-resident variant, QPF && !TMA, spilled for p >= 3);
-//   * the gather is prefetched the same way (indices one batch ahead, x values half a batch ahead);
-//   * fine-grained tasks - (slab,qy) rows instead of whole slabs - so the small batch still fills
-//     the CTA in the x/y contractions, and all B/G operands except one row per task stay
-//     compile-time kernel-parameter constants (free DFMA operands);
-//   * shared-memory strides chosen so that every phase is bank-conflict free at p=2.
+// Shape (DESIGN.md 4.1 has the history: four designs, each driven by an ncu capture):
+//   * persistent CTAs walk small batches of NEB elements; NEB*Q^2 threads = one q-point column each;
+//   * nothing on the memory path returns into a register:
+//       - the batch's q-data is ONE contiguous range of each q-data array: thread 0 issues two TMA bulk
+//         copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) into a shared-memory stage right
+//         after the previous batch's columns are done; the copy flies during phases C1/C2/A;
+//       - gather indices (two batches ahead), slots and - factorised form - element tensors (one batch
+//         ahead) are copied to shared memory by per-thread 4/8-byte cp.async (LDGSTS); every thread
+//         then reads ITS OWN indices back and gathers x with 8-byte cp.async (zero-fill form for
+//         constrained entries) straight into the x buffer of the next batch;
+//   * fine-grained tasks - (slab,qy) rows instead of whole slabs - so the small batch still fills the
+//     CTA in the x/y contractions; all B/G operands except one row per task are compile-time indices
+//     into the kernel-parameter constant bank;
+//   * per-order lane->task maps and shared-memory strides from a bank-conflict model
+//     (tools/smem_strides.py): conflict-free in every phase at p=2 and p=3.
 //
-//   stage-in : x (regs)                              -> sXin[e][dz][dy][dx]
+//   (cp.async) : x_L[gather]                         -> sX[next][e][dz][dy][dx]
 //   phase A  : task (e,dz,qy): y- then x-contraction -> sE[e][f][dz][qy][qx]        f < 3
 //   phase B  : task (e,qx,qy): z, q-point op, z^T    -> sE (in place)
 //   phase C1 : task (e,dz,qy): x^T                   -> sE[e][f][dz][qy][dx]        f < 2 (in place)
-//   phase C2 : task (e,dz,dx): y^T                   -> sXout[e][dz][dy][dx]
-//   stage-out: sXout -> y_S[slot]  (slot = position in the E->L CSR: the segmented reduction
-//              that follows streams contiguously and stays atomic-free, ascending element order)
+//   phase C2 : task (e,dz,dx): y^T                   -> y_S[slot]   (FUSE_OUT; else via sX and a stage-out pass)
+//   slot = position in the E->L CSR: the segmented reduction that follows streams contiguously and
+//   stays atomic-free, summing in ascending element order as fem/restriction.cpp:163-179.
 #pragma once
 #include <cuda_runtime.h>
 

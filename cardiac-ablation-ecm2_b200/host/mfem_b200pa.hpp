@@ -316,6 +316,97 @@ public:
    const std::vector<double> &GetResidualHistory() const { return norms; }
 };
 
+/// The Pennes bioheat equation as an mfem::TimeDependentOperator whose implicit solve runs on the GPU (pattern:
+/// ConductionOperator::ImplicitSolve, examples/ex16.cpp:326-379; stepped by BackwardEulerSolver::Step,
+/// linalg/ode.cpp:682-696 - or any SDIRK solver, they all call ImplicitSolve):
+///     rho c dT/dt = div k(T) grad T - w (T - Ta) + q,    k(T) = k0 (1 + ak (T - Tref)),   natural BCs
+///     ImplicitSolve(dt, T, dT):  [M(rho c + dt w) + dt K(k(T))] dT = -[K(k(T)) + M(w)] T + (w Ta + q, v)
+/// T, the q-data and all solver vectors stay on the device; only T comes up and dT goes back per call.
+class BioheatOperator : public mfem::TimeDependentOperator
+{
+public:
+   struct Physics { double rc = 3.6e6, w = 4.0e4, Ta = 37.0, q = 0.0, k0 = 0.5, ak = 0.02, Tref = 37.0; };
+private:
+   const mfem::FiniteElementSpace &fes;
+   Physics ph;
+   b200pa_space sp = nullptr;
+   b200pa_form fA = nullptr, fK = nullptr;
+   mutable DeviceBuffer dT, dk, drhs, dz, dlf, dkq, dkq_dt, dsrc, dcm, diag, dinv, dess;
+   long long nq = 0;
+   double rel_tol = 1e-8, abs_tol = 0.0;
+   int max_iter = 500;
+   mutable b200pa_pcg_result res{};
+   mutable int total_iters = 0;
+public:
+   BioheatOperator(const mfem::FiniteElementSpace &fes_, const Physics &p, bool factorised = false)
+      : mfem::TimeDependentOperator(fes_.GetVSize(), 0.0, mfem::TimeDependentOperator::IMPLICIT), fes(fes_), ph(p)
+   {
+      const mfem::FiniteElement &el = *fes.GetTypicalFE();
+      internal::PASetup s;
+      const mfem::IntegrationRule *ir = &mfem::DiffusionIntegrator::GetRule(el, el);
+      s.Init(fes, ir);
+      const mfem::ElementRestriction *R = dynamic_cast<const mfem::ElementRestriction *>(
+                                             fes.GetElementRestriction(mfem::ElementDofOrdering::LEXICOGRAPHIC));
+      MFEM_VERIFY(R, "b200pa: ElementRestriction expected");
+      Check(b200pa_space_create(Ctx(), s.d1d, s.q1d, s.ne, fes.GetNDofs(), R->GatherMap().HostRead(), s.maps->B.HostRead(),
+                                s.maps->G.HostRead(), &sp));
+      const mfem::GeometricFactors *geom = fes.GetMesh()->GetGeometricFactors(
+                                              *ir, mfem::GeometricFactors::JACOBIANS | mfem::GeometricFactors::DETERMINANTS);
+      Check(b200pa_space_set_geometry(sp, ir->GetWeights().HostRead(), geom->J.HostRead(), geom->detJ.HostRead()));
+      Check(b200pa_form_create(sp, &fA));
+      Check(b200pa_form_create(sp, &fK));
+      if (factorised && b200pa_space_is_affine(sp) == 1)
+      {
+         Check(b200pa_form_set_factorised(fA, 1));
+         Check(b200pa_form_set_factorised(fK, 1));
+      }
+      Check(b200pa_form_set_essential(fA, 0, nullptr));
+      Check(b200pa_form_set_essential(fK, 0, nullptr));
+      nq = (long long)s.nq * s.ne;
+      const size_t nb = sizeof(double) * height;
+      for (DeviceBuffer *b : {&dT, &dk, &drhs, &dz, &dlf, &diag, &dinv}) { b->Resize(nb); }
+      dkq.Resize(sizeof(double) * nq); dkq_dt.Resize(sizeof(double) * nq);
+      dsrc.Resize(sizeof(double)); dcm.Resize(sizeof(double)); dess.Resize(sizeof(int));
+      // constant parts: M(w) of the explicit operator and the load vector (w Ta + q, v)
+      const double wv = ph.w, src = ph.w * ph.Ta + ph.q;
+      Check(b200pa_form_assemble_mass(fK, &wv, 1));
+      dsrc.Upload(&src, sizeof(double));
+      Check(b200pa_space_domain_lf(sp, dsrc.D(), 1, dlf.D()));
+   }
+   ~BioheatOperator() { b200pa_form_destroy(fA); b200pa_form_destroy(fK); b200pa_space_destroy(sp); }
+   void SetSolverOptions(double rtol, double atol, int maxit) { rel_tol = rtol; abs_tol = atol; max_iter = maxit; }
+
+   /// dT = k solving the backward-Euler stage equation at T (TimeDependentOperator::ImplicitSolve, linalg/operator.hpp:343)
+   void ImplicitSolve(const mfem::real_t dt, const mfem::Vector &T, mfem::Vector &dT_dt) override
+   {
+      const size_t nb = sizeof(double) * height;
+      dT.Upload(T.HostRead(), nb);
+      // k(T) at the quadrature points, once for K and once scaled by dt for the system operator
+      Check(b200pa_space_coeff_linear(sp, ph.k0, ph.ak, ph.Tref, dT.D(), dkq.D()));
+      Check(b200pa_space_coeff_linear(sp, dt * ph.k0, ph.ak, ph.Tref, dT.D(), dkq_dt.D()));
+      Check(b200pa_form_assemble_diffusion(fK, dkq.D(), nq));
+      Check(b200pa_form_assemble_diffusion(fA, dkq_dt.D(), nq));
+      const double cm = ph.rc + dt * ph.w;
+      Check(b200pa_form_assemble_mass(fA, &cm, 1));
+      // rhs = (w Ta + q, v) - [K + M(w)] T
+      Check(b200pa_form_mult(fK, dT.D(), dz.D()));
+      Check(b200pa_add(Ctx(), height, dlf.D(), -1.0, dz.D(), drhs.D()));
+      // Jacobi-PCG from a zero initial guess
+      Check(b200pa_form_assemble_diagonal(fA, diag.D()));
+      Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), 0, dess.I(), 1.0, dinv.D()));
+      Check(b200pa_add(Ctx(), height, drhs.D(), -1.0, drhs.D(), dk.D())); // dk = 0
+      Check(b200pa_pcg_solve(fA, dinv.D(), drhs.D(), dk.D(), rel_tol, abs_tol, max_iter, &res, nullptr));
+      total_iters += res.final_iter;
+      dk.Download(dT_dt.HostWrite(), nb);
+   }
+   /// explicit form, for completeness (rho c M)^-1 of the right-hand side is not provided: implicit solvers only
+   void Mult(const mfem::Vector &, mfem::Vector &) const override { MFEM_ABORT("b200::BioheatOperator is IMPLICIT: use an implicit ODE solver"); }
+   int LastIterations() const { return res.final_iter; }
+   int TotalIterations() const { return total_iters; }
+   bool LastConverged() const { return res.converged != 0; }
+   bool Factorised() const { return b200pa_form_is_factorised(fA) == 1; }
+};
+
 } // namespace b200
 
 #endif

@@ -148,13 +148,82 @@ static int ex1_case(int order, int ref)
    return ok ? 0 : 1;
 }
 
+// (f)2 of SURVEY.md 8: the Pennes bioheat equation stepped by the reference's BackwardEulerSolver, once over a
+// TimeDependentOperator written with the reference's own PA forms / CGSolver / OperatorJacobiSmoother (pattern:
+// examples/ex16.cpp:326-379), once over b200::BioheatOperator (the same stage equation solved on the GPU).
+class RefBioheat : public TimeDependentOperator
+{
+   FiniteElementSpace &fes;
+   b200::BioheatOperator::Physics ph;
+   double rtol; int maxit;
+public:
+   mutable int total_iters = 0;
+   RefBioheat(FiniteElementSpace &f, const b200::BioheatOperator::Physics &p, double rt, int mi)
+      : TimeDependentOperator(f.GetVSize(), 0.0, IMPLICIT), fes(f), ph(p), rtol(rt), maxit(mi) {}
+   void Mult(const Vector &, Vector &) const override { MFEM_ABORT("implicit only"); }
+   void ImplicitSolve(const real_t dt, const Vector &T, Vector &k) override
+   {
+      const int n = fes.GetNDofs();
+      GridFunction kg(&fes), kdt(&fes);
+      for (int i = 0; i < n; i++) { kg[i] = ph.k0 * (1.0 + ph.ak * (T[i] - ph.Tref)); kdt[i] = dt * ph.k0 * (1.0 + ph.ak * (T[i] - ph.Tref)); }
+      GridFunctionCoefficient kc(&kg), kdtc(&kdt);
+      ConstantCoefficient wc(ph.w), cmc(ph.rc + dt * ph.w), srcc(ph.w * ph.Ta + ph.q);
+      BilinearForm K(&fes), A(&fes);
+      K.SetAssemblyLevel(AssemblyLevel::PARTIAL); A.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      K.AddDomainIntegrator(new mfem::DiffusionIntegrator(kc)); K.AddDomainIntegrator(new mfem::MassIntegrator(wc));
+      A.AddDomainIntegrator(new mfem::DiffusionIntegrator(kdtc)); A.AddDomainIntegrator(new mfem::MassIntegrator(cmc));
+      K.Assemble(); A.Assemble();
+      LinearForm lf(&fes); lf.AddDomainIntegrator(new DomainLFIntegrator(srcc)); lf.Assemble();
+      Vector z(n), rhs(lf); K.Mult(T, z); rhs -= z;
+      Array<int> none;
+      OperatorJacobiSmoother M(A, none);
+      CGSolver cg; cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(maxit); cg.SetPrintLevel(-1);
+      cg.SetOperator(A); cg.SetPreconditioner(M);
+      k = 0.0; cg.Mult(rhs, k);
+      total_iters += cg.GetNumIterations();
+   }
+};
+
+static int bioheat_case(int p, int nx, int nsteps, bool factorised)
+{
+   Mesh mesh = Mesh::MakeCartesian3D(nx, nx, nx, Element::HEXAHEDRON, 1.0, 1.0, 0.5);
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   b200::BioheatOperator::Physics ph; ph.q = 2.0e5;
+   FunctionCoefficient T0c([](const Vector &X) { const double r2 = pow(X(0) - 0.5, 2) + pow(X(1) - 0.5, 2) + pow(X(2) - 0.25, 2); return 37.0 + 20.0 * exp(-40.0 * r2); });
+   const double dt = 0.5;
+   auto run = [&](TimeDependentOperator &op, Vector &T)
+   {
+      GridFunction g(&fes); g.ProjectCoefficient(T0c); T = g;
+      BackwardEulerSolver ode; ode.Init(op);
+      real_t t = 0.0;
+      for (int s = 0; s < nsteps; s++) { real_t h = dt; ode.Step(T, t, h); }
+   };
+   const int n = fes.GetNDofs();
+   // fixed iteration count: the north star's 1e-10 on the solution
+   Vector Ta(n), Tb(n), Tc(n), Td(n);
+   RefBioheat r1(fes, ph, 0.0, 12); run(r1, Ta);
+   b200::BioheatOperator g1(fes, ph, factorised); g1.SetSolverOptions(0.0, 0.0, 12); run(g1, Tb);
+   // to a tolerance: iteration counts within +-1 per step
+   RefBioheat r2(fes, ph, 1e-8, 500); run(r2, Tc);
+   b200::BioheatOperator g2(fes, ph, factorised); g2.SetSolverOptions(1e-8, 0.0, 500); run(g2, Td);
+   const double e_fixed = rel(Tb, Ta), e_tol = rel(Td, Tc);
+   const bool ok = e_fixed <= 1e-10 && e_tol <= 1e-7 && abs(r2.total_iters - g2.TotalIterations()) <= nsteps && g2.LastConverged() &&
+                   g1.Factorised() == factorised;
+   cout << "{\"kind\":\"shim_bioheat\",\"p\":" << p << ",\"ndofs\":" << n << ",\"steps\":" << nsteps << ",\"factorised\":" << factorised
+        << ",\"T_rel_diff_fixed_iters\":" << e_fixed << ",\"T_rel_diff_tol\":" << e_tol << ",\"iters_ref\":" << r2.total_iters
+        << ",\"iters_gpu\":" << g2.TotalIterations() << ",\"ok\":" << (ok ? "true" : "false") << "}" << endl;
+   return ok ? 0 : 1;
+}
+
 int main(int argc, char **argv)
 {
    const string cmd = argc > 1 ? argv[1] : "";
    cout.precision(6);
-   Device device(argc > 6 ? argv[6] : "cpu");
+   Device device((cmd == "apply" && argc > 6) ? argv[6] : "cpu");
    if (cmd == "apply" && argc >= 6) { return apply_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true) | apply_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), false); }
    if (cmd == "ex1") { return ex1_case(argc > 2 ? atoi(argv[2]) : 3, argc > 3 ? atoi(argv[3]) : 3); }
-   cerr << "usage: shim_check apply p nx ny nz | ex1 [order refinements]\n";
+   if (cmd == "bioheat" && argc >= 5) { return bioheat_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), false) | bioheat_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true); }
+   cerr << "usage: shim_check apply p nx ny nz | ex1 [order refinements] | bioheat p nx steps\n";
    return 2;
 }

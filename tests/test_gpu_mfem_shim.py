@@ -42,3 +42,16 @@ def test_ex1_config0():
     r = run(["ex1", 3, 3, "omp"][:3])[0]
     assert r["ok"] and r["ndofs"] == 912673
     assert abs(r["iters_ref"] - 197) <= 1 and abs(r["iters_gpu"] - r["iters_ref"]) <= 1
+
+
+@pytest.mark.parametrize("p,n", [(2, 4), (3, 3)])
+def test_bioheat_time_stepping_through_mfem_ode_solver(p, n):
+    """SURVEY 8(f)2: mfem::BackwardEulerSolver stepping b200::BioheatOperator (TimeDependentOperator::ImplicitSolve
+    on the GPU) against the same operator written with the reference's PA forms + CGSolver + OperatorJacobiSmoother:
+    3 steps, temperature equal to 1e-10 at a fixed iteration count, iteration counts to 1e-8 within +-1 per step;
+    stored and factorised q-data"""
+    recs = run(["bioheat", p, n, 3])
+    assert len(recs) == 2 and {bool(r["factorised"]) for r in recs} == {False, True}
+    for r in recs:
+        assert r["ok"] and r["T_rel_diff_fixed_iters"] <= 1e-10
+        assert abs(r["iters_ref"] - r["iters_gpu"]) <= 3
