@@ -188,6 +188,9 @@ def reference_arm(args):
     return 0
 
 
+_JSON_OUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,10 +210,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner ("NCCL version ...", printed to stdout
-    # when NCCL_DEBUG=VERSION/INFO is set in the environment) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's "NCCL version ..." banner at any
+    # NCCL_DEBUG level >= VERSION): keep the real stdout aside for the JSON line and point fd 1 at stderr meanwhile
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -473,7 +478,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     form.close()
     sp.close()
     if comm is not None:

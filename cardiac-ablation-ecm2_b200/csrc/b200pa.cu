@@ -842,7 +842,7 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
       // no silent change of representation: the caller asked for the factorised q-data, the mesh must allow it
       B200PA_REQUIRE(sp->affine && sp->geo6.p, "assemble_diffusion: factorised q-data needs a mesh whose elements are all affine "
                                                "(b200pa_space_is_affine)");
-      f->pa_diff.release(); // size differs from the stored form
+      if (!f->factorised) { f->pa_diff.release(); } // coming from the stored form: give its 6x larger buffer back
       int rcf = alloc(f->pa_diff, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1));
       if (!rcf && sp->ne > 0)
       {
