@@ -44,6 +44,7 @@ b200pa_form_create b200pa_form_destroy b200pa_form_assemble_diffusion b200pa_for
 b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_essential b200pa_form_mult
 b200pa_form_constrained_mult b200pa_form_mult_phases b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
 b200pa_pcg_solve b200pa_pcg_solve_host
+b200pa_chebyshev_coeffs b200pa_power_method b200pa_chebyshev_mult b200pa_pcg_solve_chebyshev
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
 b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_comm_px_disable b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
 b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
@@ -140,6 +141,13 @@ def randomize(n, seed=1):
     out = np.empty(int(n))
     check(lib().b200pa_randomize(int(seed), C.c_longlong(int(n)), _ptr(out)))
     return out
+
+
+def chebyshev_coeffs(order, max_eig):
+    """OperatorChebyshevSmoother::Setup's polynomial coefficients (linalg/solvers.cpp:571-621)"""
+    c = np.zeros(int(order))
+    check(lib().b200pa_chebyshev_coeffs(int(order), C.c_double(max_eig), _ptr(c)))
+    return c
 
 
 def essential_dofs(bdr_attr, attrs):
@@ -462,6 +470,27 @@ class Form:
         fn = lib().b200pa_pcg_solve_host if host else lib().b200pa_pcg_solve
         check(fn(self.h, _ptr(dinv), _ptr(b), _ptr(x), C.c_double(rel_tol), C.c_double(abs_tol), int(max_iter),
                  C.byref(res), _ptr(norms) if want_norms else None))
+        if getattr(self, "_comm", None) is not None:
+            self._comm.check_p2p()
+        return res, (norms[:res.final_iter + 1] if want_norms else None)
+
+    # ---- OperatorChebyshevSmoother (linalg/solvers.cpp:455-657)
+    def power_method(self, dinv, v0, num_steps=10, tol=1e-8):
+        """largest eigenvalue of Dinv*A; v0 (device) = start vector, overwritten (reference: Vector::Randomize(12345))"""
+        lam = C.c_double(0.0)
+        check(lib().b200pa_power_method(self.h, _ptr(dinv), _ptr(v0), int(num_steps), C.c_double(tol), C.byref(lam)))
+        return lam.value
+
+    def chebyshev_mult(self, dinv, order, max_eig, x, y=None):
+        y = self.ctx.empty(self.sp.ndofs) if y is None else y
+        check(lib().b200pa_chebyshev_mult(self.h, _ptr(dinv), int(order), C.c_double(max_eig), _ptr(x), _ptr(y)))
+        return y
+
+    def pcg_chebyshev(self, dinv, order, max_eig, b, x, rel_tol=0.0, abs_tol=0.0, max_iter=100, want_norms=True):
+        res = PcgResult()
+        norms = np.zeros(max_iter + 2) if want_norms else None
+        check(lib().b200pa_pcg_solve_chebyshev(self.h, _ptr(dinv), int(order), C.c_double(max_eig), _ptr(b), _ptr(x), C.c_double(rel_tol),
+                                               C.c_double(abs_tol), int(max_iter), C.byref(res), _ptr(norms) if want_norms else None))
         if getattr(self, "_comm", None) is not None:
             self._comm.check_p2p()
         return res, (norms[:res.final_iter + 1] if want_norms else None)

@@ -167,7 +167,7 @@ struct b200pa_form_s
    int n_ess = 0;
    DevBuf ess, ess_mask, cgmap;
    DevBuf w1, w2;       // L-sized work vectors (EliminateRHS, host entry points)
-   DevBuf r, d, z;      // PCG work vectors (linalg/solvers.cpp:855-867)
+   DevBuf r, d, z, q;   // PCG work vectors (linalg/solvers.cpp:855-867); q = A d when the preconditioner needs z for itself
    DevBuf state, norms; // device-resident PCG scalars
    b200pa_comm comm = nullptr;
 };
@@ -817,7 +817,7 @@ extern "C" int b200pa_form_destroy(b200pa_form f)
    if (!f) { return 0; }
    cudaSetDevice(f->sp->ctx->device);
    cudaStreamSynchronize(f->sp->ctx->stream);
-   for (DevBuf *b : {&f->pa_diff, &f->pa_mass, &f->ess, &f->ess_mask, &f->cgmap, &f->w1, &f->w2, &f->r, &f->d, &f->z, &f->state, &f->norms})
+   for (DevBuf *b : {&f->pa_diff, &f->pa_mass, &f->ess, &f->ess_mask, &f->cgmap, &f->w1, &f->w2, &f->r, &f->d, &f->z, &f->q, &f->state, &f->norms})
    {
       b->release();
    }
@@ -1239,6 +1239,219 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    B200PA_CK(cudaStreamSynchronize(s));
    B200PA_REQUIRE(!hs.nonfinite, "pcg_solve: non-finite (B r, r) or (A d, d) (MFEM_VERIFY(IsFinite(...)), linalg/solvers.cpp:897,932,969,1011)");
    B200PA_REQUIRE(hs.done, "pcg_solve: internal error (loop ended without a terminal state)");
+   res->final_iter = hs.final_iter;
+   res->converged = hs.converged;
+   res->initial_norm = hs.nom0 >= 0.0 ? sqrt(hs.nom0) : hs.nom0;
+   res->final_norm = (hs.nom0 < 0.0) ? hs.nom0 : sqrt(hs.betanom);
+   if (norms_host)
+   {
+      B200PA_CK(cudaMemcpyAsync(norms_host, norms, sizeof(double) * ((size_t)hs.final_iter + 1), cudaMemcpyDeviceToHost, s));
+      B200PA_CK(cudaStreamSynchronize(s));
+   }
+   return 0;
+}
+
+// ---------------------------------------------------------- Chebyshev smoother
+// OperatorChebyshevSmoother::Setup, linalg/solvers.cpp:571-621 (host arithmetic, no device needed)
+extern "C" int b200pa_chebyshev_coeffs(int order, double max_eig, double *coeffs)
+{
+   B200PA_REQUIRE(coeffs, "chebyshev_coeffs: NULL argument");
+   B200PA_REQUIRE(order >= 1 && order <= 5, "Chebyshev smoother not implemented for this order (1..5, as linalg/solvers.cpp:618)");
+   const double upper_bound = 1.2 * max_eig, lower_bound = 0.3 * max_eig;
+   const double theta = 0.5 * (upper_bound + lower_bound), delta = 0.5 * (upper_bound - lower_bound);
+   const double t2 = theta * theta, d2 = delta * delta;
+   switch (order)
+   {
+      case 1: coeffs[0] = 1.0 / theta; break;
+      case 2:
+      {
+         const double a0 = 1.0 / (d2 - 2 * t2);
+         coeffs[0] = -4 * theta * a0; coeffs[1] = 2 * a0;
+         break;
+      }
+      case 3:
+      {
+         const double a0 = 3 * d2, a2 = 1.0 / (-4 * t2 * theta + theta * a0);
+         coeffs[0] = a2 * (a0 - 12 * t2); coeffs[1] = 12 / (a0 - 4 * t2); coeffs[2] = -4 * a2;
+         break;
+      }
+      case 4:
+      {
+         const double a2 = 8 * d2, a3 = 1.0 / (d2 * d2 + 8 * t2 * t2 - t2 * a2);
+         coeffs[0] = a3 * (32 * t2 * theta - 16 * theta * d2); coeffs[1] = a3 * (-48 * t2 + a2);
+         coeffs[2] = 32 * theta * a3; coeffs[3] = -8 * a3;
+         break;
+      }
+      default:
+      {
+         const double a0 = 5 * d2 * d2, a1 = t2 * t2, a4 = 60 * d2, a5 = 20 * d2;
+         const double a6 = 1.0 / (16 * a1 * theta - t2 * theta * a5 + theta * a0), a7 = 160 * t2;
+         const double a8 = 1.0 / (a0 + 16 * a1 - t2 * a5);
+         coeffs[0] = a6 * (a0 + 80 * a1 - t2 * a4); coeffs[1] = a8 * (a4 - a7); coeffs[2] = a6 * (-a5 + a7);
+         coeffs[3] = -80 * a8; coeffs[4] = 16 * a6;
+         break;
+      }
+   }
+   return 0;
+}
+
+// z = p(Dinv A) Dinv r: OperatorChebyshevSmoother::Mult, linalg/solvers.cpp:623-657, on the constrained operator.
+// st != NULL: called from the PCG - kernels return at once when st->done is set, and the last term carries the
+// reduction (r, z) with scalar step `scalar_step` as its epilogue when `norms_ep` is given.
+static int cheb_apply(b200pa_form f, const double *dinv, int order, const double *coeffs, const double *r, double *z, PcgState *st,
+                      bool want_dot, double *norms_ep, int scalar_step)
+{
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   const int n = sp->ndofs;
+   if (n == 0) { return 0; }
+   if (need_work(f)) { return 1; }
+   double *res = f->w1.as<double>(), *helper = f->w2.as<double>();
+   const unsigned char *own = f->comm ? comm_owner_mask(f->comm) : nullptr;
+   const int grid = grid1d(ctx, n);
+   cudaStream_t s = ctx->stream;
+   for (int k = 0; k < order; ++k)
+   {
+      const bool dot = want_dot && k == order - 1;
+      const double *src = r;
+      if (k > 0)
+      {
+         if (form_apply(f, res, helper, true, nullptr, st ? &st->done : nullptr)) { return 1; }
+         src = helper;
+      }
+      if (k == 0 && dot) { k_cheb_term<true, true><<<grid, 256, 0, s>>>(n, src, dinv, coeffs[k], res, z, r, own, ctx->d_partials, ctx->d_ticket, st, norms_ep, scalar_step); }
+      else if (k == 0) { k_cheb_term<true, false><<<grid, 256, 0, s>>>(n, src, dinv, coeffs[k], res, z, r, own, nullptr, nullptr, st, nullptr, 0); }
+      else if (dot) { k_cheb_term<false, true><<<grid, 256, 0, s>>>(n, src, dinv, coeffs[k], res, z, r, own, ctx->d_partials, ctx->d_ticket, st, norms_ep, scalar_step); }
+      else { k_cheb_term<false, false><<<grid, 256, 0, s>>>(n, src, dinv, coeffs[k], res, z, r, own, nullptr, nullptr, st, nullptr, 0); }
+      B200PA_LAUNCHED();
+   }
+   return 0;
+}
+
+extern "C" int b200pa_chebyshev_mult(b200pa_form f, const double *dinv_dev, int order, double max_eig, const double *x_dev, double *y_dev)
+{
+   B200PA_REQUIRE(f && dinv_dev && x_dev && y_dev, "chebyshev_mult: NULL argument");
+   NEED_CTX(f->sp->ctx);
+   B200PA_REQUIRE(f->cgmap.p, "chebyshev_mult: call b200pa_form_set_essential first (n_ess may be 0)");
+   double c[5];
+   if (b200pa_chebyshev_coeffs(order, max_eig, c)) { return 1; }
+   return cheb_apply(f, dinv_dev, order, c, x_dev, y_dev, nullptr, false, nullptr, 0);
+}
+
+// PowerMethod::EstimateLargestEigenvalue (linalg/operator.cpp:871-928) for Dinv * A, the operator the reference's
+// OperatorChebyshevSmoother hands it (linalg/solvers.cpp:497-511).  v0_dev: start vector (the reference:
+// Vector::Randomize(seed), b200pa_randomize), overwritten.  One GPU (the reference's serial PowerMethod).
+extern "C" int b200pa_power_method(b200pa_form f, const double *dinv_dev, double *v0_dev, int num_steps, double tolerance, double *max_eig)
+{
+   B200PA_REQUIRE(f && dinv_dev && v0_dev && max_eig, "power_method: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(!f->comm, "power_method: one GPU only (pass the estimate to the other ranks)");
+   B200PA_REQUIRE(f->cgmap.p, "power_method: call b200pa_form_set_essential first (n_ess may be 0)");
+   const int n = sp->ndofs;
+   if (need_work(f)) { return 1; }
+   DevBuf v1b;
+   if (alloc(v1b, sizeof(double) * (size_t)std::max(n, 1))) { return 1; }
+   double *a = v0_dev, *b = v1b.as<double>(), *t = f->w1.as<double>();
+   double eigenvalue = 1.0;
+   int rc = 0;
+   for (int iter = 0; iter < num_steps && !rc; ++iter)
+   {
+      double normV0 = 0.0, eigenvalueNew = 0.0;
+      rc = b200pa_dot(ctx, n, a, a, &normV0);
+      if (rc) { break; }
+      if (n > 0) { k_div_scalar<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, a, sqrt(normV0)); g_launches++; }
+      rc = form_apply(f, a, t, true, nullptr, nullptr) || b200pa_jacobi_mult(ctx, n, dinv_dev, t, b) || b200pa_dot(ctx, n, a, b, &eigenvalueNew);
+      if (rc) { break; }
+      const double diff = std::fabs((eigenvalueNew - eigenvalue) / eigenvalue);
+      eigenvalue = eigenvalueNew;
+      std::swap(a, b);
+      if (diff < tolerance) { break; }
+   }
+   if (!rc && a != v0_dev) { rc = cudaMemcpyAsync(v0_dev, a, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess; }
+   cudaStreamSynchronize(ctx->stream);
+   v1b.release();
+   *max_eig = eigenvalue;
+   return rc;
+}
+
+// CGSolver::Mult (linalg/solvers.cpp:869-1050) with the Chebyshev smoother as the preconditioner: the same device-
+// resident scalar state and scalar steps as b200pa_pcg_solve; per iteration `order` operator applies.
+extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev, int order, double max_eig, const double *b_dev,
+                                          double *x_dev, double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
+                                          double *norms_host)
+{
+   B200PA_REQUIRE(f && dinv_dev && b_dev && x_dev && res, "pcg_solve_chebyshev: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(max_iter >= 0, "pcg_solve_chebyshev: max_iter < 0");
+   B200PA_REQUIRE(f->cgmap.p, "pcg_solve_chebyshev: call b200pa_form_set_essential first (n_ess may be 0)");
+   double c[5];
+   if (b200pa_chebyshev_coeffs(order, max_eig, c)) { return 1; }
+   const int n = sp->ndofs;
+   const size_t vb = sizeof(double) * (size_t)std::max(n, 1);
+   if (alloc(f->r, vb) || alloc(f->d, vb) || alloc(f->z, vb) || alloc(f->q, vb)) { return 1; }
+   if (alloc(f->state, sizeof(PcgState))) { return 1; }
+   if (alloc(f->norms, sizeof(double) * ((size_t)max_iter + 2))) { return 1; }
+   double *r = f->r.as<double>(), *d = f->d.as<double>(), *z = f->z.as<double>(), *q = f->q.as<double>();
+   PcgState *st = f->state.as<PcgState>();
+   double *norms = f->norms.as<double>();
+   cudaStream_t s = ctx->stream;
+   const int grid = grid1d(ctx, n);
+   PcgState h0;
+   std::memset(&h0, 0, sizeof(h0));
+   h0.rel_tol = rel_tol; h0.abs_tol = abs_tol; h0.max_iter = max_iter; h0.iter = 1;
+   B200PA_CK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
+   B200PA_CK(cudaMemsetAsync(norms, 0, sizeof(double) * ((size_t)max_iter + 2), s));
+   const bool fused_scalars = (f->comm == nullptr);
+   double *ep_norms = fused_scalars ? norms : nullptr;
+   PcgState *ep_st = fused_scalars ? st : nullptr;
+   auto reduce_step = [&](double *val, int step) -> int
+   {
+      bool handled = false;
+      const double *extra = (step == 3 && comm_px(f->comm)) ? &st->dot_b2 : nullptr;
+      if (comm_allreduce_scalar_step(f->comm, val, step, st, norms, &handled, extra)) { return 1; }
+      if (handled) { return 0; }
+      if (comm_allreduce_sum_dev(f->comm, val, 1)) { return 1; }
+      if (step == 1) { k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms); }
+      else if (step == 2) { k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms); }
+      else { k_pcg_scalar_den<<<1, 1, 0, s>>>(st); }
+      B200PA_LAUNCHED();
+      return 0;
+   };
+   // r = b - A x; z = B r; d = z; nom = (d, r)
+   if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
+   if (n > 0) { k_residual<<<grid, 256, 0, s>>>(n, b_dev, r); B200PA_LAUNCHED(); }
+   if (cheb_apply(f, dinv_dev, order, c, r, z, st, true, ep_norms, 1)) { return 1; }
+   if (!fused_scalars && reduce_step(&st->dot_a, 1)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(d, z, vb, cudaMemcpyDeviceToDevice, s));
+   if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+   if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
+   int *h_done = (int *)(ctx->h_result + 4);
+   *h_done = 0;
+   const int poll = 4;
+   for (int it = 1; it <= std::max(max_iter, 1); ++it)
+   {
+      if (n > 0) { k_pcg_update_plain<<<grid, 256, 0, s>>>(n, x_dev, r, q, d, st); B200PA_LAUNCHED(); }
+      if (cheb_apply(f, dinv_dev, order, c, r, z, st, true, ep_norms, 2)) { return 1; }
+      if (!fused_scalars && reduce_step(&st->dot_a, 2)) { return 1; }
+      if (n > 0) { k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st); B200PA_LAUNCHED(); }
+      if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+      if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
+      if (it % poll == 0)
+      {
+         B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+         B200PA_CK(cudaStreamSynchronize(s));
+         if (*h_done) { break; }
+      }
+   }
+   PcgState hs;
+   B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
+   B200PA_CK(cudaStreamSynchronize(s));
+   B200PA_REQUIRE(!hs.nonfinite, "pcg_solve_chebyshev: non-finite (B r, r) or (A d, d)");
+   B200PA_REQUIRE(hs.done, "pcg_solve_chebyshev: internal error (loop ended without a terminal state)");
    res->final_iter = hs.final_iter;
    res->converged = hs.converged;
    res->initial_norm = hs.nom0 >= 0.0 ? sqrt(hs.nom0) : hs.nom0;

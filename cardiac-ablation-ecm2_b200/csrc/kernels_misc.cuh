@@ -652,4 +652,60 @@ __global__ void k_pcg_direction(int n, const double *__restrict__ z, double *__r
    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { d[i] = fma(beta, d[i], z[i]); }
 }
 
+// ------------------------------------------------------------ Chebyshev smoother
+// One polynomial term of OperatorChebyshevSmoother::Mult (linalg/solvers.cpp:641-656), fused into one pass:
+//   res = dinv .* src;   z = (FIRST ? 0 : z) + c * res
+// DOT (last term, when a PCG called): partial of (r, z) over the owned dofs and, on one GPU, the scalar step of
+// the PCG that consumes it (step 1: after the initial residual, 2: inside the loop) as the reduction's epilogue.
+template <bool FIRST, bool DOT>
+__global__ void k_cheb_term(int n, const double *__restrict__ src, const double *__restrict__ dinv, double c,
+                            double *__restrict__ res, double *__restrict__ z, const double *__restrict__ r,
+                            const unsigned char *__restrict__ own_mask, double *partials, unsigned int *ticket, PcgState *st,
+                            double *norms_epilogue, int scalar_step)
+{
+   if (st && st->done) { return; }
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      const double ri = dinv[i] * src[i];
+      const double zi = FIRST ? c * ri : fma(c, ri, z[i]);
+      res[i] = ri;
+      z[i] = zi;
+      if (DOT && (!own_mask || own_mask[i])) { acc = fma(r[i], zi, acc); }
+   }
+   if (DOT)
+   {
+      if (grid_sum(acc, partials, ticket, &st->dot_a) && norms_epilogue)
+      {
+         if (scalar_step == 1) { pcg_scalar_init(st, norms_epilogue); }
+         else { pcg_scalar_beta(st, norms_epilogue); }
+      }
+   }
+}
+
+// r = b - r (r holds A x on entry)   (linalg/solvers.cpp:875-879)
+__global__ void k_residual(int n, const double *__restrict__ b, double *__restrict__ r)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { r[i] = b[i] - r[i]; }
+}
+
+// x += alpha d; r -= alpha q   (:956-957) - the general-preconditioner form of k_pcg_update
+__global__ void k_pcg_update_plain(int n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ q,
+                                   const double *__restrict__ d, const PcgState *st)
+{
+   if (st->done) { return; }
+   const double alpha = st->alpha;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      x[i] = fma(alpha, d[i], x[i]);
+      r[i] = fma(-alpha, q[i], r[i]);
+   }
+}
+
+// v /= s   (PowerMethod: v0 /= sqrt(normV0), linalg/operator.cpp:900)
+__global__ void k_div_scalar(int n, double *__restrict__ v, double s)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { v[i] = v[i] / s; }
+}
+
 } // namespace b200pa

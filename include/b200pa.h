@@ -227,6 +227,23 @@ int b200pa_pcg_solve_host(b200pa_form f, const double *dinv_dev, const double *b
                           double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
                           double *norms_host);
 
+/* OperatorChebyshevSmoother (linalg/solvers.cpp:455-657) on the constrained PA operator, orders 1..5.
+ *   b200pa_chebyshev_coeffs : ::Setup's polynomial coefficients (:571-621); host arithmetic, needs no device
+ *   b200pa_power_method     : PowerMethod::EstimateLargestEigenvalue (linalg/operator.cpp:871-928) of Dinv*A, the
+ *                             estimate the smoother's second constructor computes (:497-511: 10 steps, 1e-8, start
+ *                             vector Vector::Randomize(12345) - b200pa_randomize); v0_dev is overwritten; one GPU
+ *   b200pa_chebyshev_mult   : ::Mult (:623-657): y = p(Dinv A) Dinv x; dinv = b200pa_jacobi_setup(damping 1)
+ *   b200pa_pcg_solve_chebyshev : CGSolver::Mult with that smoother as the preconditioner (same result struct,
+ *                             stopping rule and residual history as b200pa_pcg_solve) */
+int b200pa_chebyshev_coeffs(int order, double max_eig, double *coeffs_host);
+int b200pa_power_method(b200pa_form f, const double *dinv_dev, double *v0_dev, int num_steps, double tolerance,
+                        double *max_eig);
+int b200pa_chebyshev_mult(b200pa_form f, const double *dinv_dev, int order, double max_eig, const double *x_dev,
+                          double *y_dev);
+int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev, int order, double max_eig, const double *b_dev,
+                               double *x_dev, double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
+                               double *norms_host);
+
 /* ------------------------------------------------------ multi-GPU (one rank per GPU) */
 /* Shared-dof exchange ≙ DeviceConformingProlongationOperator::{Mult,MultTranspose}
  * (fem/pfespace.cpp:5259-5532; GroupCommunicator, general/communication.cpp:723-1120) and

@@ -456,11 +456,134 @@ double orc_dot(long n, const double *a, const double *b)
    return r;
 }
 
-/* linalg/solvers.cpp:869-1050 */
+
+/* ------------------------------------------------------- Chebyshev smoother, power method */
+/* OperatorChebyshevSmoother::Setup, linalg/solvers.cpp:557-621 (the coefficient formulas verbatim in meaning;
+ * dinv is the Jacobi one: 1/diag, 1 on essential dofs, :561-569).  Returns nonzero for an order outside 1..5. */
+int orc_chebyshev_coeffs(int order, double max_eig, double *coeffs)
+{
+   const double upper_bound = 1.2 * max_eig, lower_bound = 0.3 * max_eig;
+   const double theta = 0.5 * (upper_bound + lower_bound), delta = 0.5 * (upper_bound - lower_bound);
+   switch (order - 1)
+   {
+      case 0: coeffs[0] = 1.0 / theta; break;
+      case 1:
+      {
+         const double tmp_0 = 1.0 / (pow(delta, 2) - 2 * pow(theta, 2));
+         coeffs[0] = -4 * theta * tmp_0;
+         coeffs[1] = 2 * tmp_0;
+         break;
+      }
+      case 2:
+      {
+         const double tmp_0 = 3 * pow(delta, 2), tmp_1 = pow(theta, 2);
+         const double tmp_2 = 1.0 / (-4 * pow(theta, 3) + theta * tmp_0);
+         coeffs[0] = tmp_2 * (tmp_0 - 12 * tmp_1);
+         coeffs[1] = 12 / (tmp_0 - 4 * tmp_1);
+         coeffs[2] = -4 * tmp_2;
+         break;
+      }
+      case 3:
+      {
+         const double tmp_0 = pow(delta, 2), tmp_1 = pow(theta, 2), tmp_2 = 8 * tmp_0;
+         const double tmp_3 = 1.0 / (pow(delta, 4) + 8 * pow(theta, 4) - tmp_1 * tmp_2);
+         coeffs[0] = tmp_3 * (32 * pow(theta, 3) - 16 * theta * tmp_0);
+         coeffs[1] = tmp_3 * (-48 * tmp_1 + tmp_2);
+         coeffs[2] = 32 * theta * tmp_3;
+         coeffs[3] = -8 * tmp_3;
+         break;
+      }
+      case 4:
+      {
+         const double tmp_0 = 5 * pow(delta, 4), tmp_1 = pow(theta, 4), tmp_2 = pow(theta, 2), tmp_3 = pow(delta, 2);
+         const double tmp_4 = 60 * tmp_3, tmp_5 = 20 * tmp_3;
+         const double tmp_6 = 1.0 / (16 * pow(theta, 5) - pow(theta, 3) * tmp_5 + theta * tmp_0);
+         const double tmp_7 = 160 * tmp_2;
+         const double tmp_8 = 1.0 / (tmp_0 + 16 * tmp_1 - tmp_2 * tmp_5);
+         coeffs[0] = tmp_6 * (tmp_0 + 80 * tmp_1 - tmp_2 * tmp_4);
+         coeffs[1] = tmp_8 * (tmp_4 - tmp_7);
+         coeffs[2] = tmp_6 * (-tmp_5 + tmp_7);
+         coeffs[3] = -80 * tmp_8;
+         coeffs[4] = 16 * tmp_6;
+         break;
+      }
+      default: return 1;
+   }
+   return 0;
+}
+
+/* OperatorChebyshevSmoother::Mult, linalg/solvers.cpp:623-657, on the constrained operator */
+void orc_chebyshev_mult(const orc_operator *op, const double *dinv, int order, const double *coeffs, const double *x,
+                        double *y, double *work, double *workE)
+{
+   const int n = op->ndofs;
+   double *residual = malloc(sizeof(double) * n), *helper = malloc(sizeof(double) * n);
+   memcpy(residual, x, sizeof(double) * n);
+   for (int i = 0; i < n; ++i) { y[i] = 0.0; }
+   for (int k = 0; k < order; ++k)
+   {
+      if (k > 0)
+      {
+         orc_constrained_mult(op, residual, helper, work, workE);
+         memcpy(residual, helper, sizeof(double) * n);
+      }
+      for (int i = 0; i < n; ++i) { residual[i] *= dinv[i]; }
+      for (int i = 0; i < n; ++i) { y[i] += coeffs[k] * residual[i]; }
+   }
+   free(residual); free(helper);
+}
+
+/* PowerMethod::EstimateLargestEigenvalue, linalg/operator.cpp:871-928, for opr = Dinv * A (the ProductOperator of
+ * linalg/solvers.cpp:500-501).  v0: start vector on entry (the caller's Vector::Randomize(seed)), work space after. */
+double orc_power_method(const orc_operator *op, const double *dinv, double *v0, int num_steps, double tolerance)
+{
+   const int n = op->ndofs;
+   const long nE = (long)op->NE * op->D1D * op->D1D * op->D1D;
+   double *v1 = malloc(sizeof(double) * n), *t = malloc(sizeof(double) * n);
+   double *work = malloc(sizeof(double) * n), *workE = malloc(sizeof(double) * 2 * nE);
+   double *a = v0, *b = v1;
+   double eigenvalue = 1.0;
+   for (int iter = 0; iter < num_steps; ++iter)
+   {
+      const double normV0 = orc_dot(n, a, a);
+      const double s = sqrt(normV0);
+      for (int i = 0; i < n; ++i) { a[i] /= s; }
+      orc_constrained_mult(op, a, t, work, workE);
+      orc_jacobi_mult(n, dinv, t, b);
+      const double eigenvalueNew = orc_dot(n, a, b);
+      const double diff = fabs((eigenvalueNew - eigenvalue) / eigenvalue);
+      eigenvalue = eigenvalueNew;
+      { double *sw = a; a = b; b = sw; }
+      if (diff < tolerance) { break; }
+   }
+   if (a != v0) { memcpy(v0, a, sizeof(double) * n); }
+   free(v1); free(t); free(work); free(workE);
+   return eigenvalue;
+}
+
+/* linalg/solvers.cpp:869-1050; preconditioner = Jacobi (cheb_order = 0) or the Chebyshev smoother of that order */
+static void orc_precond(const orc_operator *op, const double *dinv, int cheb_order, const double *coeffs, const double *r,
+                        double *z, double *work, double *workE)
+{
+   if (cheb_order > 0) { orc_chebyshev_mult(op, dinv, cheb_order, coeffs, r, z, work, workE); }
+   else { orc_jacobi_mult(op->ndofs, dinv, r, z); }
+}
+
+int orc_pcg_prec(const orc_operator *op, const double *dinv, int cheb_order, double max_eig, const double *b, double *x,
+                 double rel_tol, double abs_tol, int max_iter, int *converged, double *final_norm, double *norms);
+
 int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double *x,
             double rel_tol, double abs_tol, int max_iter, int *converged, double *final_norm,
             double *norms)
 {
+   return orc_pcg_prec(op, dinv, 0, 0.0, b, x, rel_tol, abs_tol, max_iter, converged, final_norm, norms);
+}
+
+int orc_pcg_prec(const orc_operator *op, const double *dinv, int cheb_order, double max_eig, const double *b, double *x,
+                 double rel_tol, double abs_tol, int max_iter, int *converged, double *final_norm, double *norms)
+{
+   double coeffs[5] = {0, 0, 0, 0, 0};
+   if (cheb_order > 0 && orc_chebyshev_coeffs(cheb_order, max_eig, coeffs)) { *converged = 0; *final_norm = -1.0; return -1; }
    const int n = op->ndofs;
    const long nE = (long)op->NE * op->D1D * op->D1D * op->D1D;
    double *r = malloc(sizeof(double) * n), *d = malloc(sizeof(double) * n), *z = malloc(sizeof(double) * n);
@@ -470,7 +593,7 @@ int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double 
    /* iterative_mode: r = b - A x  (:875-879; subtract(b, r, r)) */
    orc_constrained_mult(op, x, r, work, workE);
    for (int k = 0; k < n; ++k) { r[k] = b[k] - r[k]; }
-   orc_jacobi_mult(n, dinv, r, z);
+   orc_precond(op, dinv, cheb_order, coeffs, r, z, work, workE);
    memcpy(d, z, sizeof(double) * n);
    nom = orc_dot(n, d, r);
    if (norms) { norms[0] = nom; }
@@ -487,7 +610,7 @@ int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double 
       alpha = nom / den;
       for (int k = 0; k < n; ++k) { x[k] = x[k] + alpha * d[k]; }
       { const double ma = -alpha; for (int k = 0; k < n; ++k) { r[k] = r[k] + ma * z[k]; } }
-      orc_jacobi_mult(n, dinv, r, z);
+      orc_precond(op, dinv, cheb_order, coeffs, r, z, work, workE);
       betanom = orc_dot(n, r, z);
       if (norms) { norms[i] = betanom; }
       if (betanom < 0.0) { final_iter = i; break; }

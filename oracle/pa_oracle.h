@@ -68,6 +68,13 @@ double orc_dot(long n, const double *a, const double *b);
  * ConstrainedOperator of `op` as operator; iterative_mode = true.
  * Returns final_iter; *converged, *final_norm as the reference sets them; norms[i] = (B r, r)
  * after iteration i (i = 0..final_iter) when norms != NULL (size max_iter+1). */
+/* OperatorChebyshevSmoother (linalg/solvers.cpp:455-657), PowerMethod (linalg/operator.cpp:871-928) */
+int orc_chebyshev_coeffs(int order, double max_eig, double *coeffs);
+void orc_chebyshev_mult(const orc_operator *op, const double *dinv, int order, const double *coeffs, const double *x,
+                        double *y, double *work, double *workE);
+double orc_power_method(const orc_operator *op, const double *dinv, double *v0, int num_steps, double tolerance);
+int orc_pcg_prec(const orc_operator *op, const double *dinv, int cheb_order, double max_eig, const double *b, double *x,
+                 double rel_tol, double abs_tol, int max_iter, int *converged, double *final_norm, double *norms);
 int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double *x,
             double rel_tol, double abs_tol, int max_iter, int *converged, double *final_norm,
             double *norms);

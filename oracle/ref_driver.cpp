@@ -259,6 +259,55 @@ static int dump_case(int argc, char **argv)
          D.f64("pcg_tol_norms", rec.norms.data(), rec.norms.size());
       }
    }
+   // (f)4 of SURVEY 8: OperatorChebyshevSmoother (linalg/solvers.cpp:455-657) on the constrained operator, with the
+   // largest eigenvalue of D^-1 A from the reference's power method exactly as its second constructor runs it
+   // (solvers.cpp:497-511: ProductOperator(OperatorJacobiSmoother(diag, ess, 1.0), A), 10 steps, 1e-8, seed 12345)
+   {
+      GridFunction xg(&fes); xg = 0.0;
+      FunctionCoefficient bcf([&](const Vector &X) { return 30.0 * (1.0 - X(2) / sz) + X(0); });
+      if (ess.Size()) { xg.ProjectBdrCoefficient(bcf, ess_bdr); }
+      LinearForm b(&fes);
+      ConstantCoefficient one(1.0);
+      b.AddDomainIntegrator(new DomainLFIntegrator(one));
+      b.Assemble();
+      OperatorPtr A; Vector X, B;
+      a.FormLinearSystem(ess, xg, b, A, X, B);
+      OperatorJacobiSmoother invD(diag, ess, 1.0);
+      ProductOperator dp(&invD, A.Ptr(), false, false);
+      PowerMethod pm;
+      Vector ev(ND);
+      const double lam = pm.EstimateLargestEigenvalue(dp, ev, 10, 1e-8, 12345);
+      D.scalar("cheb_max_eig", lam);
+      { Vector v0(ND); v0.Randomize(12345); D.vec("cheb_v0", v0); }
+      for (int order = 1; order <= 5; order++)
+      {
+         OperatorChebyshevSmoother C(*A, diag, ess, order, lam);
+         Vector z(ND); C.Mult(x, z);
+         D.vec("cheb_z" + to_string(order), z);
+      }
+      OperatorChebyshevSmoother C3(*A, diag, ess, 3, lam);
+      {
+         CGSolver cg; NormRecorder rec;
+         cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(4); cg.SetPrintLevel(-1);
+         cg.SetOperator(*A); cg.SetPreconditioner(C3); cg.SetMonitor(rec);
+         cg.iterative_mode = true;
+         Vector Xk(X);
+         cg.Mult(B, Xk);
+         D.vec("X_cheb3_pcg4", Xk);
+         D.f64("cheb3_pcg_norms", rec.norms.data(), rec.norms.size());
+      }
+      {
+         CGSolver cg;
+         cg.SetRelTol(1e-8); cg.SetAbsTol(0.0); cg.SetMaxIter(5000); cg.SetPrintLevel(-1);
+         cg.SetOperator(*A); cg.SetPreconditioner(C3);
+         cg.iterative_mode = true;
+         Vector Xk(X);
+         cg.Mult(B, Xk);
+         D.vec("X_cheb3_tol", Xk);
+         D.iscalar("cheb3_tol_iters", cg.GetNumIterations());
+         D.iscalar("cheb3_tol_converged", cg.GetConverged());
+      }
+   }
    // a17/a18: q-point values and physical gradients of x; K15 RHS with q-data source
    {
       const QuadratureInterpolator *qi = fes.GetQuadratureInterpolator(qs);

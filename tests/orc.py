@@ -38,6 +38,9 @@ def lib():
         _lib = C.CDLL(build())
         _lib.orc_dot.restype = C.c_double
         _lib.orc_pcg.restype = C.c_int
+        _lib.orc_pcg_prec.restype = C.c_int
+        _lib.orc_chebyshev_coeffs.restype = C.c_int
+        _lib.orc_power_method.restype = C.c_double
         _lib.orc_jacobi_setup.restype = C.c_int
     return _lib
 
@@ -115,6 +118,32 @@ class Operator:
         it = lib().orc_pcg(C.byref(self.s), dp(f64(dinv)), dp(f64(b)), dp(x), C.c_double(rel_tol), C.c_double(abs_tol),
                            int(max_iter), C.byref(conv), C.byref(fn), dp(norms))
         return x, it, bool(conv.value), fn.value, norms[:it + 1]
+
+    def power_method(self, dinv, v0, num_steps=10, tol=1e-8):
+        """largest eigenvalue of Dinv*A from the start vector v0 (the reference: Vector::Randomize(12345))"""
+        v = f64(v0).copy()
+        return lib().orc_power_method(C.byref(self.s), dp(f64(dinv)), dp(v), int(num_steps), C.c_double(tol))
+
+    def chebyshev_mult(self, dinv, order, max_eig, x):
+        c = chebyshev_coeffs(order, max_eig)
+        y = np.zeros(self.ndofs)
+        lib().orc_chebyshev_mult(C.byref(self.s), dp(f64(dinv)), int(order), dp(c), dp(f64(x)), dp(y), dp(self.work), dp(self.workE))
+        return y
+
+    def pcg_chebyshev(self, dinv, order, max_eig, b, x0, rel_tol, abs_tol, max_iter):
+        x = f64(x0).copy()
+        conv = C.c_int(0)
+        fn = C.c_double(0)
+        norms = np.zeros(max_iter + 2)
+        it = lib().orc_pcg_prec(C.byref(self.s), dp(f64(dinv)), int(order), C.c_double(max_eig), dp(f64(b)), dp(x), C.c_double(rel_tol),
+                                C.c_double(abs_tol), int(max_iter), C.byref(conv), C.byref(fn), dp(norms))
+        return x, it, bool(conv.value), fn.value, norms[:it + 1]
+
+
+def chebyshev_coeffs(order, max_eig):
+    c = np.zeros(order)
+    assert lib().orc_chebyshev_coeffs(int(order), C.c_double(max_eig), dp(c)) == 0, "order outside 1..5"
+    return c
 
 
 def restrict_mult(NE, nd, gather_map, x):

@@ -325,3 +325,32 @@ def test_midsize_against_oracle(ctx, p, dims):
     close(norms, no, 1e-9)
     f.close()
     sp.close()
+
+
+def test_chebyshev_smoother_and_pcg(ctx, dev):
+    """OperatorChebyshevSmoother (linalg/solvers.cpp:455-657) - coefficients, the power-method eigenvalue
+    estimate, the smoother and PCG preconditioned with it against the reference's own outputs and the oracle"""
+    c = dev.c
+    sp = dev.space()
+    f = dev.form(sp)
+    dinv = f.jacobi()
+    lam_ref = float(c["cheb_max_eig"][0])
+    lam = f.power_method(dinv, ctx.to_dev(c["cheb_v0"]))
+    assert abs(lam - lam_ref) <= 1e-12 * lam_ref
+    assert abs(f.power_method(dinv, ctx.to_dev(b200pa.randomize(dev.nd, 12345))) - lam_ref) <= 1e-12 * lam_ref
+    for order in range(1, 6):
+        close(b200pa.chebyshev_coeffs(order, lam_ref), orc.chebyshev_coeffs(order, lam_ref), 1e-14)
+        close(ctx.to_host(f.chebyshev_mult(dinv, order, lam_ref, dev["x"])), c[f"cheb_z{order}"])
+    x = ctx.to_dev(c["X0"])
+    res, norms = f.pcg_chebyshev(dinv, 3, lam_ref, dev["B_rhs"], x, 0.0, 0.0, 4)
+    assert res.final_iter == 4
+    close(ctx.to_host(x), c["X_cheb3_pcg4"], TOL_PCG)
+    close(norms, c["cheb3_pcg_norms"], 1e-10)
+    x = ctx.to_dev(c["X0"])
+    res, _ = f.pcg_chebyshev(dinv, 3, lam_ref, dev["B_rhs"], x, 1e-8, 0.0, 5000)
+    assert abs(res.final_iter - int(c["cheb3_tol_iters"][0])) <= 1 and bool(res.converged) == bool(c["cheb3_tol_converged"][0])
+    close(ctx.to_host(x), c["X_cheb3_tol"], 1e-8)
+    with pytest.raises(b200pa.B200paError, match="order"):
+        f.chebyshev_mult(dinv, 6, lam_ref, dev["x"])
+    f.close()
+    sp.close()

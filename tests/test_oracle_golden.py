@@ -100,3 +100,21 @@ def test_qpoint_ops(case):
     bE = orc.domain_lf(c["NE"], c["D1D"], c["Q1D"], c["B"], c["detJ"], c["W"], c["lf_fq"])
     b = orc.restrict_mult_transpose(c["ndofs"], c["offsets"], c["indices"], bE)
     close(b, c["lf_b"])
+
+
+def test_chebyshev_and_power_method(case):
+    """OperatorChebyshevSmoother (linalg/solvers.cpp:455-657) and the power method behind its
+    eigenvalue estimate (linalg/operator.cpp:871-928) against the reference's own outputs"""
+    op = make_op(case)
+    dinv = op.jacobi_dinv()
+    lam_ref = float(case["cheb_max_eig"][0])
+    close(op.power_method(dinv, case["cheb_v0"]), lam_ref, 1e-13)
+    for order in range(1, 6):
+        close(op.chebyshev_mult(dinv, order, lam_ref, case["x"]), case[f"cheb_z{order}"], 1e-13)
+    x, it, conv, fn, norms = op.pcg_chebyshev(dinv, 3, lam_ref, case["B_rhs"], case["X0"], 0.0, 0.0, 4)
+    assert it == 4
+    close(x, case["X_cheb3_pcg4"], 1e-12)
+    close(norms, case["cheb3_pcg_norms"], 1e-11)
+    x, it, conv, fn, norms = op.pcg_chebyshev(dinv, 3, lam_ref, case["B_rhs"], case["X0"], 1e-8, 0.0, 5000)
+    assert it == int(case["cheb3_tol_iters"][0]) and conv == bool(case["cheb3_tol_converged"][0])
+    close(x, case["X_cheb3_tol"], 1e-10)
