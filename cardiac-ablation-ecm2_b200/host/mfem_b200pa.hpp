@@ -275,12 +275,19 @@ class PCGSolver : public mfem::Solver
    int max_iter = 10, print_level = -1;
    mutable b200pa_pcg_result res{};
    mutable std::vector<double> norms;
+   int cheb_order = 0;
+   double cheb_max_eig = 0.0;
 public:
    PCGSolver() : mfem::Solver(0, true) {}
    void SetRelTol(double t) { rel_tol = t; }
    void SetAbsTol(double t) { abs_tol = t; }
    void SetMaxIter(int n) { max_iter = n; }
    void SetPrintLevel(int l) { print_level = l; }
+   /// precondition with OperatorChebyshevSmoother(order) instead of OperatorJacobiSmoother (linalg/solvers.cpp:455-657);
+   /// max_eig <= 0: estimated at SetOperator time by the reference's power method (10 steps, 1e-8, seed 12345). Call
+   /// before SetOperator.
+   void SetChebyshev(int order, double max_eig = 0.0) { cheb_order = order; cheb_max_eig = max_eig; }
+   double GetMaxEigEstimate() const { return cheb_max_eig; }
    /// SetOperator + SetPreconditioner(OperatorJacobiSmoother(a, ess, damping)) in one
    void SetOperator(const mfem::Operator &o) override
    {
@@ -295,12 +302,32 @@ public:
       dess.Resize(sizeof(int) * std::max(op->ess.Size(), 1));
       if (op->ess.Size()) { dess.Upload(op->ess.HostRead(), sizeof(int) * op->ess.Size()); }
       Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), op->ess.Size(), dess.I(), damping, dinv.D()));
+      if (cheb_order > 0 && cheb_max_eig <= 0.0)
+      {
+         mfem::Vector v0(height);
+         v0.Randomize(12345);
+         DeviceBuffer dv;
+         dv.Upload(v0.HostRead(), sizeof(double) * height);
+         Check(b200pa_power_method(op->form, dinv.D(), dv.D(), 10, 1e-8, &cheb_max_eig));
+      }
    }
    void Mult(const mfem::Vector &b, mfem::Vector &x) const override
    {
       if (!iterative_mode) { x = 0.0; }
       norms.assign(max_iter + 2, 0.0);
-      Check(b200pa_pcg_solve_host(op->form, dinv.D(), b.HostRead(), x.HostReadWrite(), rel_tol, abs_tol, max_iter, &res, norms.data()));
+      if (cheb_order > 0)
+      {
+         DeviceBuffer db, dx;
+         db.Upload(b.HostRead(), sizeof(double) * height);
+         dx.Upload(x.HostRead(), sizeof(double) * height);
+         Check(b200pa_pcg_solve_chebyshev(op->form, dinv.D(), cheb_order, cheb_max_eig, db.D(), dx.D(), rel_tol, abs_tol, max_iter, &res,
+                                          norms.data()));
+         dx.Download(x.HostReadWrite(), sizeof(double) * height);
+      }
+      else
+      {
+         Check(b200pa_pcg_solve_host(op->form, dinv.D(), b.HostRead(), x.HostReadWrite(), rel_tol, abs_tol, max_iter, &res, norms.data()));
+      }
       if (print_level >= 1)
       {
          for (int i = 0; i <= res.final_iter; i++)

@@ -92,14 +92,31 @@ static int apply_case(int p, int nx, int ny, int nz, bool bc)
    solve0(0.0, 10, Xa, ia, ca); solve2(0.0, 10, Xb, ib, cb);
    solve0(1e-8, 5000, Xc, ic, cc); solve2(1e-8, 5000, Xd, id, cd);
 
+   // Chebyshev-preconditioned CG: the reference's OperatorChebyshevSmoother (order 3, its own power-method estimate)
+   // against b200::PCGSolver::SetChebyshev(3)
+   int ie = 0, ig = 0; double e_cheb = 0.0, lam_gpu = 0.0;
+   {
+      Vector dg(n); a.AssembleDiagonal(dg);
+      OperatorChebyshevSmoother C3(*A0, dg, ess, 3);
+      CGSolver cg; cg.SetRelTol(1e-8); cg.SetAbsTol(0.0); cg.SetMaxIter(5000); cg.SetPrintLevel(-1);
+      cg.SetOperator(*A0); cg.SetPreconditioner(C3); cg.iterative_mode = true;
+      Vector Xe(n); Xe = X0; cg.Mult(B0, Xe); ie = cg.GetNumIterations();
+      b200::PCGSolver cg2; cg2.SetRelTol(1e-8); cg2.SetAbsTol(0.0); cg2.SetMaxIter(5000); cg2.SetChebyshev(3);
+      cg2.SetOperator(A2); cg2.iterative_mode = true;
+      Vector Xg(n); Xg = xg; cg2.Mult(B2, Xg); ig = cg2.GetNumIterations(); lam_gpu = cg2.GetMaxEigEstimate();
+      e_cheb = rel(Xg, Xe);
+   }
+   const bool ok_cheb = abs(ie - ig) <= 1 && e_cheb <= 1e-6 && ig < id;
+
    const double e_apply1 = rel(y1, y0), e_diag1 = rel(d1, d0), e_apply2 = rel(y2, y0), e_diag2 = rel(d2, d0);
    const double e_con = rel(yc2, yc0), e_rhs = rel(B2, B0), e_pcg = rel(Xb, Xa), e_tol = rel(Xd, Xc);
-   const bool ok = ok3 && e_apply1 <= 1e-12 && e_diag1 <= 1e-12 && e_apply2 <= 1e-12 && e_diag2 <= 1e-12 && e_con <= 1e-12 &&
+   const bool ok = ok3 && ok_cheb && e_apply1 <= 1e-12 && e_diag1 <= 1e-12 && e_apply2 <= 1e-12 && e_diag2 <= 1e-12 && e_con <= 1e-12 &&
                    e_rhs <= 1e-12 && e_pcg <= 1e-10 && ia == 10 && ib == 10 && abs(ic - id) <= 1 && cc == cd;
    cout << "{\"kind\":\"shim_apply\",\"p\":" << p << ",\"ne\":" << mesh.GetNE() << ",\"ndofs\":" << n << ",\"bc\":" << bc
         << ",\"integrator_level\":{\"apply\":" << e_apply1 << ",\"diag\":" << e_diag1 << "}"
         << ",\"fused\":{\"apply\":" << e_apply2 << ",\"diag\":" << e_diag2 << ",\"constrained\":" << e_con << ",\"rhs\":" << e_rhs
         << ",\"pcg10\":" << e_pcg << ",\"pcg_tol\":" << e_tol << ",\"iters_ref\":" << ic << ",\"iters_gpu\":" << id << "}"
+        << ",\"chebyshev3\":{\"iters_ref\":" << ie << ",\"iters_gpu\":" << ig << ",\"solution\":" << e_cheb << ",\"max_eig\":" << lam_gpu << "}"
         << ",\"factorised\":{\"apply\":" << e_apply3 << ",\"diag\":" << e_diag3 << "}"
         << ",\"ok\":" << (ok ? "true" : "false") << "}" << endl;
    return ok ? 0 : 1;

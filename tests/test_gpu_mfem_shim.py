@@ -34,6 +34,9 @@ def test_mfem_drop_in(p, dims):
         f = r["fused"]
         assert max(f["apply"], f["diag"], f["constrained"], f["rhs"]) <= 1e-12 and f["pcg10"] <= 1e-10
         assert abs(f["iters_ref"] - f["iters_gpu"]) <= 1
+        assert max(r["factorised"].values()) <= 1e-12
+        ch = r["chebyshev3"]
+        assert abs(ch["iters_ref"] - ch["iters_gpu"]) <= 1 and ch["iters_gpu"] < f["iters_gpu"] and ch["solution"] <= 1e-6
 
 
 def test_ex1_config0():
