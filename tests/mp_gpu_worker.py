@@ -75,6 +75,27 @@ def main():
     r2, _ = f.pcg(f.jacobi(), ctx.to_dev(bg[gid]), X2, 1e-8, 0.0, 2000)
     rs2, _ = fs.pcg(fs.jacobi(), ser(bg), Xs2, 1e-8, 0.0, 2000)
     assert abs(r2.final_iter - rs2.final_iter) <= 1 and r2.converged and rs2.converged
+    # Chebyshev-preconditioned PCG (order 3), eigenvalue estimate from the serial power method, and the factorised
+    # q-data: partitioned == serial
+    lam = fs.power_method(fs.jacobi(), ctx.to_dev(b200pa.randomize(nglob, 12345)))
+    X3, Xs3 = ctx.zeros(m["ndofs"]), ctx.zeros(nglob)
+    r3, n3 = f.pcg_chebyshev(f.jacobi(), 3, lam, ctx.to_dev(bg[gid]), X3, 0.0, 0.0, 6)
+    rs3, ns3 = fs.pcg_chebyshev(fs.jacobi(), 3, lam, ser(bg), Xs3, 0.0, 0.0, 6)
+    e4 = cmp(X3, Xs3, 1e-10, "Chebyshev-PCG solution after 6 iterations")
+    assert r3.final_iter == rs3.final_iter == 6 and np.max(np.abs(n3 - ns3) / ns3) <= 1e-9
+    assert sp.affine
+    for g in (f, fs):
+        g.set_factorised(True)
+    lat, lats = m["lattice"].reshape(-1, 3), ms["lattice"].reshape(-1, 3)
+    tf = lambda L: ctx.to_dev(37.0 + 5.0 * np.sin(0.37 * L[:, 0]) * np.cos(0.21 * L[:, 1]) + 0.1 * L[:, 2])
+    f.assemble_diffusion(sp.coeff_linear(0.5, 0.02, 37.0, tf(lat)))
+    fs.assemble_diffusion(sps.coeff_linear(0.5, 0.02, 37.0, tf(lats)))
+    e5 = cmp(f.constrained_mult(ctx.to_dev(xg[gid])), fs.constrained_mult(ser(xg)), 1e-12, "factorised constrained apply")
+    X4, Xs4 = ctx.zeros(m["ndofs"]), ctx.zeros(nglob)
+    r4, _ = f.pcg(f.jacobi(), ctx.to_dev(bg[gid]), X4, 0.0, 0.0, 15)
+    rs4, _ = fs.pcg(fs.jacobi(), ser(bg), Xs4, 0.0, 0.0, 15)
+    cmp(X4, Xs4, 1e-10, "factorised PCG solution after 15 iterations")
+    cmp(X4, Xs, 1e-10, "factorised vs stored PCG solution")
     # bcast: owner value wins
     v = ctx.to_dev(xg[gid] + rank)
     comm.bcast(v)
@@ -89,7 +110,7 @@ def main():
     dist.barrier()
     comm.check_p2p()
     if rank == 0:
-        print(f"MULTI_OK world={world} p={p} p2p={comm.p2p_enabled()} apply={e1:.2e} diag={e2:.2e} pcg={e3:.2e} its={r2.final_iter}/{rs2.final_iter}", flush=True)
+        print(f"MULTI_OK world={world} p={p} p2p={comm.p2p_enabled()} apply={e1:.2e} diag={e2:.2e} pcg={e3:.2e} cheb={e4:.2e} fact={e5:.2e} its={r2.final_iter}/{rs2.final_iter}", flush=True)
     f.close(); sp.close(); fs.close(); sps.close(); comm.close(); ctx.close()
     dist.destroy_process_group()
 
