@@ -59,6 +59,16 @@ struct ApplyCfg
 #else
    static constexpr bool L2HINT = (D <= 3); // q-data is read once per apply: L2 evict_first (measured: +3 % at p=2, -4 % at p=5)
 #endif
+   // JAM tasks per thread in the row phases A, C1, C2 (unroll-and-jam): every B/G constant fetched into a uniform
+   // register (LDCU, or an R2UR pair when it was spilled) then feeds JAM DFMAs instead of one.  Measured with JAM = 2:
+   // 13-25 % SLOWER at p = 3..6 (profiles/r1n_tuning_unroll_and_jam.txt) - the row phases are short of threads, not of
+   // issue slots; kept for tuning builds only
+#ifdef B200PA_TUNE_JAM
+   static constexpr int JAM = B200PA_TUNE_JAM;
+#else
+   static constexpr int JAM = 1;
+#endif
+   static_assert(JAM == 1 || JAM == 2, "one or two tasks per thread");
    // phase C2 stores its results straight to y_S[slot] (no staging through sX, one barrier less per batch)
 #ifdef B200PA_TUNE_FUSE_OUT
    static constexpr bool FUSE_OUT = B200PA_TUNE_FUSE_OUT;
@@ -278,45 +288,77 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       if (C::QSTAGES == 2 && next < nbatch && tid == 0) { tma_issue(next, cur ^ 1); }
 
       // ------------------------------------ phase A: (slab, qy) rows, y then x
-      for (int task = tid; task < NEB * D * Q; task += NT)
       {
-         const int slab = C::MAPA_SLAB ? task % (NEB * D) : task / Q, qy = C::MAPA_SLAB ? task / (NEB * D) : task - slab * Q;
-         const int e = slab / D, dz = slab - e * D;
-         const double *xs = sXin + slab * SXS;
-         double bq[D], gq[D];
-         B200PA_UNROLL
-         for (int dy = 0; dy < D; ++dy) { bq[dy] = sBt[qy * BS + dy]; if (DIFF) { gq[dy] = sGt[qy * BS + dy]; } }
-         double tB[D], tG[D];
-         B200PA_UNROLL
-         for (int dx = 0; dx < D; ++dx) { tB[dx] = 0.0; tG[dx] = 0.0; }
-         B200PA_UNROLL
-         for (int dy = 0; dy < D; ++dy)
+         constexpr int JAM = C::JAM, NTASK = NEB * D * Q, NT2 = (NTASK + JAM - 1) / JAM;
+         for (int t0 = tid; t0 < NT2; t0 += NT)
          {
+            const double *xs[JAM];
+            double *o[JAM];
+            int qy[JAM];
+            bool ok[JAM];
             B200PA_UNROLL
-            for (int dx = 0; dx < D; ++dx)
+            for (int j = 0; j < JAM; ++j)
             {
-               const double xv = xs[dy * D + dx];
-               tB[dx] = fma(bq[dy], xv, tB[dx]);
-               if (DIFF) { tG[dx] = fma(gq[dy], xv, tG[dx]); }
+               const int task = t0 + j * NT2;
+               ok[j] = task < NTASK;
+               const int tk = ok[j] ? task : t0;
+               const int slab = C::MAPA_SLAB ? tk % (NEB * D) : tk / Q;
+               qy[j] = C::MAPA_SLAB ? tk / (NEB * D) : tk - slab * Q;
+               const int e = slab / D, dz = slab - e * D;
+               xs[j] = sXin + slab * SXS;
+               o[j] = sE + e * ES + dz * SQ + qy[j] * RQ;
             }
-         }
-         double *o = sE + e * ES + dz * SQ + qy * RQ;
-         B200PA_UNROLL
-         for (int qx = 0; qx < Q; ++qx)
-         {
-            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            double tB[JAM][D], tG[JAM][D];
             B200PA_UNROLL
-            for (int dx = 0; dx < D; ++dx)
+            for (int j = 0; j < JAM; ++j)
             {
-               if (DIFF)
+               double bq[D], gq[D];
+               B200PA_UNROLL
+               for (int dy = 0; dy < D; ++dy) { bq[dy] = sBt[qy[j] * BS + dy]; if (DIFF) { gq[dy] = sGt[qy[j] * BS + dy]; } }
+               B200PA_UNROLL
+               for (int dx = 0; dx < D; ++dx) { tB[j][dx] = 0.0; tG[j][dx] = 0.0; }
+               B200PA_UNROLL
+               for (int dy = 0; dy < D; ++dy)
                {
-                  f0 = fma(Gm(qx, dx), tB[dx], f0); // Gx By
-                  f1 = fma(Bm(qx, dx), tG[dx], f1); // Bx Gy
+                  B200PA_UNROLL
+                  for (int dx = 0; dx < D; ++dx)
+                  {
+                     const double xv = xs[j][dy * D + dx];
+                     tB[j][dx] = fma(bq[dy], xv, tB[j][dx]);
+                     if (DIFF) { tG[j][dx] = fma(gq[dy], xv, tG[j][dx]); }
+                  }
                }
-               f2 = fma(Bm(qx, dx), tB[dx], f2);    // Bx By
             }
-            if (DIFF) { o[0 * D * SQ + qx] = f0; o[1 * D * SQ + qx] = f1; }
-            o[2 * D * SQ + qx] = f2;
+            B200PA_UNROLL
+            for (int qx = 0; qx < Q; ++qx)
+            {
+               double f0[JAM], f1[JAM], f2[JAM];
+               B200PA_UNROLL
+               for (int j = 0; j < JAM; ++j) { f0[j] = 0.0; f1[j] = 0.0; f2[j] = 0.0; }
+               B200PA_UNROLL
+               for (int dx = 0; dx < D; ++dx)
+               {
+                  B200PA_UNROLL
+                  for (int j = 0; j < JAM; ++j)
+                  {
+                     if (DIFF)
+                     {
+                        f0[j] = fma(Gm(qx, dx), tB[j][dx], f0[j]); // Gx By
+                        f1[j] = fma(Bm(qx, dx), tG[j][dx], f1[j]); // Bx Gy
+                     }
+                     f2[j] = fma(Bm(qx, dx), tB[j][dx], f2[j]);    // Bx By
+                  }
+               }
+               B200PA_UNROLL
+               for (int j = 0; j < JAM; ++j)
+               {
+                  if (ok[j])
+                  {
+                     if (DIFF) { o[j][0 * D * SQ + qx] = f0[j]; o[j][1 * D * SQ + qx] = f1[j]; }
+                     o[j][2 * D * SQ + qx] = f2[j];
+                  }
+               }
+            }
          }
       }
       __syncthreads();
@@ -409,75 +451,128 @@ pa_apply_kernel(const __grid_constant__ ElemParams<D, Q> P)
       if (C::QSTAGES == 1 && next < nbatch && tid == 0) { tma_issue(next, 0); }
 
       // ----------------------------------------------- phase C1: (slab, qy) rows, x^T
-      for (int task = tid; task < NEB * D * Q; task += NT)
       {
-         const int slab = C::MAPA_SLAB ? task % (NEB * D) : task / Q, qy = C::MAPA_SLAB ? task / (NEB * D) : task - slab * Q;
-         const int e = slab / D, dz = slab - e * D;
-         double *io = sE + e * ES + dz * SQ + qy * RQ;
-         double r0[Q], r1[Q], r2[Q];
-         B200PA_UNROLL
-         for (int qx = 0; qx < Q; ++qx)
+         constexpr int JAM = C::JAM, NTASK = NEB * D * Q, NT2 = (NTASK + JAM - 1) / JAM;
+         for (int t0 = tid; t0 < NT2; t0 += NT)
          {
-            if (DIFF) { r0[qx] = io[0 * D * SQ + qx]; r1[qx] = io[1 * D * SQ + qx]; }
-            r2[qx] = io[2 * D * SQ + qx];
-         }
-         B200PA_UNROLL
-         for (int dx = 0; dx < D; ++dx)
-         {
-            double s02 = 0.0, s1 = 0.0;
+            double *io[JAM];
+            bool ok[JAM];
+            double r0[JAM][Q], r1[JAM][Q], r2[JAM][Q];
             B200PA_UNROLL
-            for (int qx = 0; qx < Q; ++qx)
+            for (int j = 0; j < JAM; ++j)
             {
-               if (DIFF)
+               const int task = t0 + j * NT2;
+               ok[j] = task < NTASK;
+               const int tk = ok[j] ? task : t0;
+               const int slab = C::MAPA_SLAB ? tk % (NEB * D) : tk / Q, qy = C::MAPA_SLAB ? tk / (NEB * D) : tk - slab * Q;
+               const int e = slab / D, dz = slab - e * D;
+               io[j] = sE + e * ES + dz * SQ + qy * RQ;
+               B200PA_UNROLL
+               for (int qx = 0; qx < Q; ++qx)
                {
-                  s02 = fma(Gm(qx, dx), r0[qx], s02);
-                  s1 = fma(Bm(qx, dx), r1[qx], s1);
+                  if (DIFF) { r0[j][qx] = io[j][0 * D * SQ + qx]; r1[j][qx] = io[j][1 * D * SQ + qx]; }
+                  r2[j][qx] = io[j][2 * D * SQ + qx];
                }
-               s02 = fma(Bm(qx, dx), r2[qx], s02);
             }
-            io[0 * D * SQ + dx] = s02; // row qy of field 0 / 1 now holds the x^T results (D <= Q)
-            if (DIFF) { io[1 * D * SQ + dx] = s1; }
+            B200PA_UNROLL
+            for (int dx = 0; dx < D; ++dx)
+            {
+               double s02[JAM], s1[JAM];
+               B200PA_UNROLL
+               for (int j = 0; j < JAM; ++j) { s02[j] = 0.0; s1[j] = 0.0; }
+               B200PA_UNROLL
+               for (int qx = 0; qx < Q; ++qx)
+               {
+                  B200PA_UNROLL
+                  for (int j = 0; j < JAM; ++j)
+                  {
+                     if (DIFF)
+                     {
+                        s02[j] = fma(Gm(qx, dx), r0[j][qx], s02[j]);
+                        s1[j] = fma(Bm(qx, dx), r1[j][qx], s1[j]);
+                     }
+                     s02[j] = fma(Bm(qx, dx), r2[j][qx], s02[j]);
+                  }
+               }
+               B200PA_UNROLL
+               for (int j = 0; j < JAM; ++j)
+               {
+                  if (ok[j])
+                  {
+                     io[j][0 * D * SQ + dx] = s02[j]; // row qy of field 0 / 1 now holds the x^T results (D <= Q)
+                     if (DIFF) { io[j][1 * D * SQ + dx] = s1[j]; }
+                  }
+               }
+            }
          }
       }
       __syncthreads();
 
       // ----------------------------------------------- phase C2: (slab, dx) columns, y^T
-      for (int task = tid; task < NEB * D * D; task += NT)
       {
-         const int slab = C::MAPC_SLAB ? task % (NEB * D) : task / D, dx = C::MAPC_SLAB ? task / (NEB * D) : task - slab * D;
-         const int e = slab / D, dz = slab - e * D;
-         const double *in = sE + e * ES + dz * SQ + dx;
-         double out[D];
-         B200PA_UNROLL
-         for (int dy = 0; dy < D; ++dy) { out[dy] = 0.0; }
-         B200PA_UNROLL
-         for (int qy = 0; qy < Q; ++qy)
+         constexpr int JAM = C::JAM, NTASK = NEB * D * D, NT2 = (NTASK + JAM - 1) / JAM;
+         for (int t0 = tid; t0 < NT2; t0 += NT)
          {
-            const double a = in[0 * D * SQ + qy * RQ];
-            const double b = DIFF ? in[1 * D * SQ + qy * RQ] : 0.0;
+            const double *in[JAM];
+            int slab[JAM], dx[JAM];
+            bool ok[JAM];
+            double out[JAM][D];
             B200PA_UNROLL
-            for (int dy = 0; dy < D; ++dy)
+            for (int j = 0; j < JAM; ++j)
             {
-               out[dy] = fma(Bm(qy, dy), a, out[dy]);
-               if (DIFF) { out[dy] = fma(Gm(qy, dy), b, out[dy]); }
+               const int task = t0 + j * NT2;
+               ok[j] = task < NTASK;
+               const int tk = ok[j] ? task : t0;
+               slab[j] = C::MAPC_SLAB ? tk % (NEB * D) : tk / D;
+               dx[j] = C::MAPC_SLAB ? tk / (NEB * D) : tk - slab[j] * D;
+               const int e = slab[j] / D, dz = slab[j] - e * D;
+               in[j] = sE + e * ES + dz * SQ + dx[j];
+               B200PA_UNROLL
+               for (int dy = 0; dy < D; ++dy) { out[j][dy] = 0.0; }
             }
-         }
-         if (C::FUSE_OUT)
-         {
-            // slot = position in the E->L CSR (copied into sSl a whole batch ago; < 0 beyond the last element)
-            const int *sl = sSl + cur * NIDX + slab * D2 + dx;
             B200PA_UNROLL
-            for (int dy = 0; dy < D; ++dy)
+            for (int qy = 0; qy < Q; ++qy)
             {
-               const int k = sl[dy * D];
-               if (k >= 0) { P.y[k] = out[dy]; }
+               double a[JAM], b[JAM];
+               B200PA_UNROLL
+               for (int j = 0; j < JAM; ++j)
+               {
+                  a[j] = in[j][0 * D * SQ + qy * RQ];
+                  b[j] = DIFF ? in[j][1 * D * SQ + qy * RQ] : 0.0;
+               }
+               B200PA_UNROLL
+               for (int dy = 0; dy < D; ++dy)
+               {
+                  B200PA_UNROLL
+                  for (int j = 0; j < JAM; ++j)
+                  {
+                     out[j][dy] = fma(Bm(qy, dy), a[j], out[j][dy]);
+                     if (DIFF) { out[j][dy] = fma(Gm(qy, dy), b[j], out[j][dy]); }
+                  }
+               }
             }
-         }
-         else
-         {
-            double *xs = sXout + slab * SXS + dx;
             B200PA_UNROLL
-            for (int dy = 0; dy < D; ++dy) { xs[dy * D] = out[dy]; }
+            for (int j = 0; j < JAM; ++j)
+            {
+               if (!ok[j]) { continue; }
+               if (C::FUSE_OUT)
+               {
+                  // slot = position in the E->L CSR (copied into sSl a whole batch ago; < 0 beyond the last element)
+                  const int *sl = sSl + cur * NIDX + slab[j] * D2 + dx[j];
+                  B200PA_UNROLL
+                  for (int dy = 0; dy < D; ++dy)
+                  {
+                     const int k = sl[dy * D];
+                     if (k >= 0) { P.y[k] = out[j][dy]; }
+                  }
+               }
+               else
+               {
+                  double *xs = sXout + slab[j] * SXS + dx[j];
+                  B200PA_UNROLL
+                  for (int dy = 0; dy < D; ++dy) { xs[dy * D] = out[j][dy]; }
+               }
+            }
          }
       }
       if (C::FUSE_OUT) { continue; }
