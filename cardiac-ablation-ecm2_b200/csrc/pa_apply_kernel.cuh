@@ -17,7 +17,7 @@
 //     CTA in the x/y contractions; all B/G operands except one row per task are compile-time indices
 //     into the kernel-parameter constant bank;
 //   * per-order lane->task maps and shared-memory strides from a bank-conflict model
-//     (tools/smem_strides.py): conflict-free in every phase at p=2 and p=3.
+//     (tools/smem_strides.py report): every phase over the work array conflict-free at p=2 and p=3.
 //
 //   (cp.async) : x_L[gather]                         -> sX[next][e][dz][dy][dx]
 //   phase A  : task (e,dz,qy): y- then x-contraction -> sE[e][f][dz][qy][qx]        f < 3
@@ -79,7 +79,7 @@ struct ApplyCfg
    static constexpr int NIDX = NEB * D3;                         // E-entries per batch
    static constexpr int NIO = (NIDX + NT - 1) / NT;              // gather / scatter items per thread
    // shared-memory strides and lane -> task maps found by tools/smem_strides.py (fewest bank-conflict wavefronts
-   // over all phases; conflict-free at p=2 and p=3): SXS = slab stride of sX, RQ / SQ / ES = row / slab / element
+   // over all phases; the work-array phases are conflict-free at p=2 and p=3): SXS = slab stride of sX, RQ / SQ / ES = row / slab / element
    // stride of sE, BS = row stride of the staged basis rows; MAPA_SLAB / MAPC_SLAB: consecutive lanes of the
    // row phases A, C1 / of phase C2 walk the slabs (else the rows / columns of one slab)
 #ifdef B200PA_TUNE_LAYOUT0 // the layout of rounds r1c..r1f

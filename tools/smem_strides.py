@@ -1,83 +1,159 @@
 #!/usr/bin/env python
-"""Search the shared-memory strides (SQ, ES, SXS) of pa_apply_kernel that minimise bank-conflict
-wavefronts, per order.  Model: 8-byte accesses are served per half-warp (16 lanes x 8 B = 128 B = all 32
-banks once); lanes reading the same address are one request; the cost of one warp instruction is the sum
-over its two half-warps of the maximum number of distinct addresses falling on one 8-byte bank."""
-import itertools
+"""Bank-conflict model of pa_apply_kernel's shared-memory phases and the search that chose its per-order strides
+and lane -> task maps (ApplyCfg in cardiac-ablation-ecm2_b200/csrc/pa_apply_kernel.cuh).
+
+Model: 8-byte accesses are served per half-warp (16 lanes x 8 B = 128 B = all 32 banks once); lanes reading the same
+address are one request; the cost of one warp-wide instruction is the sum over its half-warps of the largest number
+of distinct addresses that fall on one 8-byte bank.  Checked against ncu (`l1tex__data_pipe_lsu_wavefronts_mem_shared`,
+source page of profiles' r1e / r1h captures): 1486 modelled vs 1471 measured wavefronts per batch at p = 4.
+
+    python tools/smem_strides.py report          # wavefronts / ideal per phase for the configuration in the kernel
+    python tools/smem_strides.py search D NEB    # search (RQ, SQ, ES, SXS, BS, maps) for one order (minutes)
+"""
 import sys
 
-CFG = {2: 28, 3: 8, 4: 5, 5: 3, 6: 2, 7: 2}  # D -> NEB (pa_apply_kernel.cuh)
 
-
-def cost(addr_of_lane, nlanes):
-    """wavefronts of one warp-wide instruction family: lanes 0..nlanes-1 grouped in warps of 32"""
+def cost(addrs):
+    """wavefronts of one warp-wide 8-byte access; addrs[lane] = double index or None (inactive lane)"""
     tot = 0
-    for w0 in range(0, nlanes, 32):
-        for h0 in (w0, w0 + 16):
-            banks = {}
-            for l in range(h0, min(h0 + 16, nlanes)):
-                a = addr_of_lane(l)
-                if a is None:
-                    continue
+    for h0 in range(0, len(addrs), 16):
+        banks = {}
+        for a in addrs[h0:h0 + 16]:
+            if a is not None:
                 banks.setdefault(a % 16, set()).add(a)
-            if banks:
-                tot += max(len(v) for v in banks.values())
+        if banks:
+            tot += max(len(v) for v in banks.values())
     return tot
 
 
-def total(D, Q, NEB, SQ, ES, SXS):
-    Q2, D2 = Q * Q, D * D
+def ideal(addrs):
+    return sum(1 for h0 in range(0, len(addrs), 16) if any(a is not None for a in addrs[h0:h0 + 16]))
+
+
+def phases(D, Q, NEB, SXS, RQ, SQ, ES, BS, mapA="qy", mapC="dx", QES=None, QMS=None):
+    """{phase: [wavefronts, conflict-free wavefronts]} per batch of NEB elements (diffusion + mass, stored q-data)"""
+    Q2, D2, D3, Q3 = Q * Q, D * D, D ** 3, Q ** 3
     NT = ((NEB * Q2 + 31) // 32) * 32
-    c = 0
-    nA = NEB * D * Q
-    # phase A: reads of the x slab (one per (dy,dx)), writes of 3 fields x Q values
+    FS = D * SQ
+    QES = 6 * Q3 if QES is None else QES
+    QMS = Q3 if QMS is None else QMS
+    res = {}
+
+    def add(name, fn, n):
+        L = [fn(l) if l < n else None for l in range(((n + 31) // 32) * 32)]
+        c = i = 0
+        for s in range(0, len(L), NT):          # tasks beyond NT: the kernel loops
+            c += cost(L[s:s + NT])
+            i += ideal(L[s:s + NT])
+        r = res.setdefault(name, [0, 0])
+        r[0] += c
+        r[1] += i
+
+    nsl = NEB * D
+    tA = (lambda l: (l // Q, l % Q)) if mapA == "qy" else (lambda l: (l % nsl, l // nsl))     # (slab, qy)
+    tC = (lambda l: (l // D, l % D)) if mapC == "dx" else (lambda l: (l % nsl, l // nsl))     # (slab, dx)
+    sE = lambda slab, f, qy, x: (slab // D) * ES + f * FS + (slab % D) * SQ + qy * RQ + x
+    nA, nB, nC, nio = NEB * D * Q, NEB * Q2, NEB * D * D, NEB * D3
     for k in range(D2):
-        c += cost(lambda l: (l // Q) * SXS + k, nA)
-    rowpat = lambda l, x, f: ((l // Q) // D) * ES + ((l // Q) % D) * SQ + (l % Q) * Q + x + f * D * SQ
+        add("A.x", lambda l: tA(l)[0] * SXS + k, nA)
+    for dy in range(D):
+        for _ in range(2):
+            add("A.bg", lambda l: 10 ** 6 + tA(l)[1] * BS + dy, nA)
     for f in range(3):
         for qx in range(Q):
-            c += 2 * cost(lambda l: rowpat(l, qx, f), nA)      # A write + C1 read
+            add("A.w", lambda l: sE(tA(l)[0], f, tA(l)[1], qx), nA)
+            add("C1.r", lambda l: sE(tA(l)[0], f, tA(l)[1], qx), nA)
     for f in range(2):
         for dx in range(D):
-            c += cost(lambda l: rowpat(l, dx, f), nA)           # C1 write
-    # phase B: column reads + writes
-    nB = NEB * Q2
+            add("C1.w", lambda l: sE(tA(l)[0], f, tA(l)[1], dx), nA)
     for f in range(3):
         for dz in range(D):
-            c += 2 * cost(lambda l: (l // Q2) * ES + (l % Q2) + (f * D + dz) * SQ, nB)
-    # phase C2: reads (2 fields x Q), writes D
-    nC = NEB * D * D
+            fn = lambda l: (l // Q2) * ES + f * FS + dz * SQ + ((l % Q2) // Q) * RQ + (l % Q2) % Q
+            add("B.r", fn, nB)
+            add("B.w", fn, nB)
+    for k in range(6):
+        for qz in range(Q):
+            add("B.qd", lambda l: (l // Q2) * QES + k * Q3 + qz * Q2 + l % Q2, nB)
+    for qz in range(Q):
+        add("B.qm", lambda l: (l // Q2) * QMS + qz * Q2 + l % Q2, nB)
     for f in range(2):
         for qy in range(Q):
-            c += cost(lambda l: ((l // D) // D) * ES + ((l // D) % D) * SQ + (l % D) + qy * Q + f * D * SQ, nC)
+            add("C2.r", lambda l: sE(tC(l)[0], f, qy, tC(l)[1]), nC)
     for dy in range(D):
-        c += cost(lambda l: (l // D) * SXS + dy * D + (l % D), nC)
-    # stage in / out
-    nio = NEB * D * D2
-    for r in range((nio + NT - 1) // NT):
-        c += 2 * cost(lambda l: ((l + r * NT) // D2) * SXS + (l + r * NT) % D2 if l + r * NT < nio else None, NT)
-    return c
+        add("C2.w", lambda l: tC(l)[0] * SXS + dy * D + tC(l)[1], nC)   # staged output (FUSE_OUT stores to global instead)
+    add("gather", lambda l: (l // D2) * SXS + l % D2, nio)
+    return res
 
 
-def main():
-    for D, NEB in CFG.items():
-        Q = D + 1
-        base = (Q * Q | 1, None, D * D | 1)
-        cur_sq = 19 if D == 3 else (Q * Q | 1)
-        cur_es = 185 if D == 3 else (3 * D * cur_sq + (1 if (3 * D * cur_sq) % 2 == 0 else 0))
-        cur = total(D, Q, NEB, cur_sq, cur_es, D * D | 1)
-        best = None
-        for SQ in range(Q * Q, Q * Q + 17):
-            for pad in range(0, 17):
-                ES = 3 * D * SQ + pad
-                for SXS in range(D * D, D * D + 9):
-                    t = total(D, Q, NEB, SQ, ES, SXS)
-                    key = (t, ES * NEB + 2 * NEB * D * SXS)
-                    if best is None or key < best[0]:
-                        best = (key, SQ, ES, SXS)
-        print(f"D={D} Q={Q} NEB={NEB}: current (SQ={cur_sq}, ES={cur_es}, SXS={D*D|1}) cost {cur}; best SQ={best[1]} ES={best[2]} "
-              f"SXS={best[3]} cost {best[0][0]}", flush=True)
+# the configuration compiled into the kernel: D -> (NEB, SXS, RQ, SQ, ES, BS, mapA, mapC, QES, QMS)
+KERNEL = {
+    2: (28, 6, 3, 11, 73, 2, "qy", "dx", None, None),
+    3: (16, 9, 4, 19, 185, 3, "qy", "dx", None, None),
+    4: (5, 17, 5, 28, 345, 4, "slab", "slab", None, None),
+    5: (3, 25, 6, 37, 564, 5, "qy", "dx", 6 * 216 + 4, 216 + 12),
+    6: (2, 38, 7, 49, 886, 6, "qy", "slab", None, None),
+    7: (1, 55, 10, 87, 1841, 7, "qy", "dx", None, None),
+}
+
+
+def report():
+    for D, (NEB, SXS, RQ, SQ, ES, BS, mA, mC, QES, QMS) in KERNEL.items():
+        r = phases(D, D + 1, NEB, SXS, RQ, SQ, ES, BS, mA, mC, QES, QMS)
+        tot, idl = sum(v[0] for v in r.values()), sum(v[1] for v in r.values())
+        bad = {k: tuple(v) for k, v in r.items() if v[0] != v[1]}
+        print(f"p={D - 1} NEB={NEB}: {tot} wavefronts per batch, {idl} conflict-free ({tot / idl:.2f}x); phases with conflicts: {bad}")
+
+
+def search(D, NEB):
+    Q = D + 1
+    Q2, D2, D3 = Q * Q, D * D, D ** 3
+    NT = ((NEB * Q2 + 31) // 32) * 32
+    nsl = NEB * D
+    nA, nB, nC, nio = NEB * D * Q, NEB * Q2, NEB * D * D, NEB * D3
+    mapsA = {"qy": lambda l: (l // Q, l % Q), "slab": lambda l: (l % nsl, l // nsl)}
+    mapsC = {"dx": lambda l: (l // D, l % D), "slab": lambda l: (l % nsl, l // nsl)}
+
+    def ev(fn, n):
+        L = [fn(l) if l < n else None for l in range(((n + NT - 1) // NT) * NT)]
+        return sum(cost(L[s:s + NT]) for s in range(0, len(L), NT))
+
+    sx, bs = {}, {}
+    for mA, tA in mapsA.items():
+        for BS in range(D, D + 4):
+            c = 2 * sum(ev(lambda l: tA(l)[1] * BS + dy, nA) for dy in range(D))
+            if mA not in bs or c < bs[mA][0]:
+                bs[mA] = (c, BS)
+        for mC, tC in mapsC.items():
+            for SXS in range(D2, D2 + 17):
+                c = sum(ev(lambda l: tA(l)[0] * SXS + k, nA) for k in range(D2))
+                c += sum(ev(lambda l: tC(l)[0] * SXS + dy * D + tC(l)[1], nC) for dy in range(D))
+                c += ev(lambda l: (l // D2) * SXS + l % D2, nio)
+                if (mA, mC) not in sx or c < sx[(mA, mC)][0]:
+                    sx[(mA, mC)] = (c, SXS)
+    out = []
+    for RQ in range(Q, Q + 4):
+        for SQ in range((Q - 1) * RQ + Q, (Q - 1) * RQ + Q + 16):
+            FS = D * SQ
+            for pad in range(16):
+                ES = 3 * FS + pad
+                sE = lambda slab, f, qy, x: (slab // D) * ES + f * FS + (slab % D) * SQ + qy * RQ + x
+                cB = 2 * sum(ev(lambda l: (l // Q2) * ES + f * FS + dz * SQ + ((l % Q2) // Q) * RQ + (l % Q2) % Q, nB)
+                             for f in range(3) for dz in range(D))
+                for mA, tA in mapsA.items():
+                    cA = 2 * sum(ev(lambda l: sE(tA(l)[0], f, tA(l)[1], qx), nA) for f in range(3) for qx in range(Q))
+                    cA += sum(ev(lambda l: sE(tA(l)[0], f, tA(l)[1], dx), nA) for f in range(2) for dx in range(D))
+                    for mC, tC in mapsC.items():
+                        cC = sum(ev(lambda l: sE(tC(l)[0], f, qy, tC(l)[1]), nC) for f in range(2) for qy in range(Q))
+                        tot = cA + cB + cC + sx[(mA, mC)][0] + bs[mA][0]
+                        out.append((tot, NEB * ES, dict(RQ=RQ, SQ=SQ, ES=ES, SXS=sx[(mA, mC)][1], BS=bs[mA][1], mapA=mA, mapC=mC)))
+    out.sort(key=lambda t: (t[0], t[1]))
+    for t in out[:5]:
+        print(t)
+    print("best without changing the lane maps:", [t for t in out if t[2]["mapA"] == "qy" and t[2]["mapC"] == "dx"][0])
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) >= 4 and sys.argv[1] == "search":
+        search(int(sys.argv[2]), int(sys.argv[3]))
+    else:
+        report()
