@@ -48,6 +48,7 @@ b200pa_chebyshev_coeffs b200pa_power_method b200pa_chebyshev_mult b200pa_pcg_sol
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
 b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_comm_px_disable b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
 b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
+b200pa_hex_write_mesh b200pa_write_gridfunction
 """.split()
 
 
@@ -141,6 +142,18 @@ def randomize(n, seed=1):
     out = np.empty(int(n))
     check(lib().b200pa_randomize(int(seed), C.c_longlong(int(n)), _ptr(out)))
     return out
+
+
+def write_mesh(path, nx, ny, nz, sx=1.0, sy=1.0, sz=1.0, skew=False):
+    """Mesh::Print ("MFEM mesh v1.0") of the mesh hex_build numbers"""
+    check(lib().b200pa_hex_write_mesh(str(path).encode(), int(nx), int(ny), int(nz), C.c_double(sx), C.c_double(sy), C.c_double(sz),
+                                      int(bool(skew))))
+
+
+def write_gridfunction(path, p, values):
+    """GridFunction::Save of a scalar H1 order-p field in the builder's L-dof numbering"""
+    v = _f64(values)
+    check(lib().b200pa_write_gridfunction(str(path).encode(), int(p), C.c_longlong(v.size), _ptr(v)))
 
 
 def chebyshev_coeffs(order, max_eig):

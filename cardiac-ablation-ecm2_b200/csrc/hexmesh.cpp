@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -359,6 +360,66 @@ extern "C" int b200pa_hex_dof_lattice(int nx, int ny, int nz, int p, int *lattic
 {
    if (!lattice) { return hfail("hex_dof_lattice: NULL output"); }
    return b200pa_hex_build_part(nx, ny, nz, 0, 0, 0, nx, ny, nz, p, 1, 1, 1, 0, nullptr, nullptr, nullptr, nullptr, nullptr, lattice);
+}
+
+// ------------------------------------------------------------ results hand-off (wire formats)
+// Mesh::Print in the "MFEM mesh v1.0" format (mesh/mesh.cpp:12239-12360) for the mesh b200pa_hex_build numbers:
+// elements in the reference's space-filling-curve order, boundary quads and attributes exactly as
+// Mesh::Make3D adds them (mesh/mesh.cpp:3806-3940), vertices with 17 significant digits.  A mesh the reference
+// loads from this file gets the same H1 numbering as b200pa_hex_build (tests/test_wire_formats.py).
+extern "C" int b200pa_hex_write_mesh(const char *path, int nx, int ny, int nz, double sx, double sy, double sz, int skew)
+{
+   if (!path || nx < 1 || ny < 1 || nz < 1) { return hfail("hex_write_mesh: bad arguments"); }
+   FILE *f = std::fopen(path, "w");
+   if (!f) { return hfail("hex_write_mesh: cannot open the output file"); }
+   std::vector<int> sfc;
+   sfc_order(nx, ny, nz, sfc);
+   auto V = [&](int x, int y, int z) { return x + ((long long)y + (long long)z * (ny + 1)) * (nx + 1); };
+   const long long ne = (long long)nx * ny * nz, nv = (long long)(nx + 1) * (ny + 1) * (nz + 1);
+   std::fprintf(f, "MFEM mesh v1.0\n\n#\n# MFEM Geometry Types (see fem/geom.hpp):\n#\n# POINT       = 0\n# SEGMENT     = 1\n"
+                   "# TRIANGLE    = 2\n# SQUARE      = 3\n# TETRAHEDRON = 4\n# CUBE        = 5\n# PRISM       = 6\n# PYRAMID     = 7\n#\n");
+   std::fprintf(f, "\ndimension\n3\n\nelements\n%lld\n", ne);
+   for (long long k = 0; k < ne; ++k)
+   {
+      const int ex = sfc[3 * k], ey = sfc[3 * k + 1], ez = sfc[3 * k + 2];
+      std::fprintf(f, "1 5");
+      for (int m = 0; m < 8; ++m) { std::fprintf(f, " %lld", V(ex + CV[m][0], ey + CV[m][1], ez + CV[m][2])); }
+      std::fprintf(f, "\n");
+   }
+   std::fprintf(f, "\nboundary\n%lld\n", 2LL * ((long long)nx * ny + (long long)nx * nz + (long long)ny * nz));
+   auto quad = [&](int attr, long long a, long long b, long long c, long long d) { std::fprintf(f, "%d 3 %lld %lld %lld %lld\n", attr, a, b, c, d); };
+   for (int y = 0; y < ny; ++y) { for (int x = 0; x < nx; ++x) { quad(1, V(x, y, 0), V(x, y + 1, 0), V(x + 1, y + 1, 0), V(x + 1, y, 0)); } }
+   for (int y = 0; y < ny; ++y) { for (int x = 0; x < nx; ++x) { quad(6, V(x, y, nz), V(x + 1, y, nz), V(x + 1, y + 1, nz), V(x, y + 1, nz)); } }
+   for (int z = 0; z < nz; ++z) { for (int y = 0; y < ny; ++y) { quad(5, V(0, y, z), V(0, y, z + 1), V(0, y + 1, z + 1), V(0, y + 1, z)); } }
+   for (int z = 0; z < nz; ++z) { for (int y = 0; y < ny; ++y) { quad(3, V(nx, y, z), V(nx, y + 1, z), V(nx, y + 1, z + 1), V(nx, y, z + 1)); } }
+   for (int x = 0; x < nx; ++x) { for (int z = 0; z < nz; ++z) { quad(2, V(x, 0, z), V(x + 1, 0, z), V(x + 1, 0, z + 1), V(x, 0, z + 1)); } }
+   for (int x = 0; x < nx; ++x) { for (int z = 0; z < nz; ++z) { quad(4, V(x, ny, z), V(x, ny, z + 1), V(x + 1, ny, z + 1), V(x + 1, ny, z)); } }
+   std::fprintf(f, "\nvertices\n%lld\n3\n", nv);
+   for (int z = 0; z <= nz; ++z)
+      for (int y = 0; y <= ny; ++y)
+         for (int x = 0; x <= nx; ++x)
+         {
+            double v[3] = {((double)x / nx) * sx, ((double)y / ny) * sy, ((double)z / nz) * sz};
+            if (skew) { v[1] += 0.2 * v[0]; v[2] += 0.3 * v[0]; }
+            std::fprintf(f, "%.17g %.17g %.17g\n", v[0], v[1], v[2]);
+         }
+   const bool bad = std::ferror(f) != 0;
+   if (std::fclose(f) != 0 || bad) { return hfail("hex_write_mesh: write error"); }
+   return 0;
+}
+
+// GridFunction::Save (fem/gridfunc.cpp:4142-4165, FiniteElementSpace::Save fem/fespace.cpp:4395-4480) of a scalar H1
+// field of order p in the L-dof numbering of b200pa_hex_build: header + one value per line, 17 significant digits
+extern "C" int b200pa_write_gridfunction(const char *path, int p, long long n, const double *values)
+{
+   if (!path || p < 1 || n < 0 || (n > 0 && !values)) { return hfail("write_gridfunction: bad arguments"); }
+   FILE *f = std::fopen(path, "w");
+   if (!f) { return hfail("write_gridfunction: cannot open the output file"); }
+   std::fprintf(f, "FiniteElementSpace\nFiniteElementCollection: H1_3D_P%d\nVDim: 1\nOrdering: 0\n\n", p);
+   for (long long i = 0; i < n; ++i) { std::fprintf(f, "%.17g\n", values[i]); }
+   const bool bad = std::ferror(f) != 0;
+   if (std::fclose(f) != 0 || bad) { return hfail("write_gridfunction: write error"); }
+   return 0;
 }
 
 extern "C" int b200pa_randomize(int seed, long long n, double *out)

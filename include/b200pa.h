@@ -303,6 +303,11 @@ int b200pa_comm_allreduce_sum(b200pa_comm c, double *vals_dev, int n);
  *   elem_ijk     int32[3*ne] lattice position of every element (SFC order)
  *   bdr_attr_of_dof  uint8[ndofs]: bit a-1 set if the dof lies on boundary attribute a (1..6)
  */
+/* results hand-off in the reference's own text formats: Mesh::Print "MFEM mesh v1.0" (mesh/mesh.cpp:12239-12360) for the
+ * mesh b200pa_hex_build numbers, and GridFunction::Save (fem/gridfunc.cpp:4142-4165) for a scalar H1 field of order p in
+ * its L-dof numbering (host values).  GLVis / the reference load both; the loaded space has the builder's numbering. */
+int b200pa_hex_write_mesh(const char *path, int nx, int ny, int nz, double sx, double sy, double sz, int skew);
+int b200pa_write_gridfunction(const char *path, int p, long long n, const double *values_host);
 int b200pa_hex_sizes(int nx, int ny, int nz, int p, long long *ne, long long *nv, long long *ndofs);
 int b200pa_hex_build(int nx, int ny, int nz, int p, double sx, double sy, double sz, int skew,
                      int *gather_map, int *elem_vertices, double *vertices, int *elem_ijk,

@@ -686,6 +686,42 @@ static int check_inline(const char *path)
    return same ? 0 : 1;
 }
 
+// ------------------------------------------------------------------ load_check
+// The reference loading the product's wire formats: Mesh(file) + GridFunction(mesh, file); dumps what it sees so that
+// tests/test_wire_formats.py can compare with the builder (numbering, boundary attributes, values, an L2 norm).
+static int load_check(int argc, char **argv)
+{
+   if (argc < 5) { cerr << "load_check OUT mesh_file gridfunction_file\n"; return 2; }
+   Dumper D(argv[2]);
+   Device device("cpu");
+   Mesh mesh(argv[3], 1, 1);
+   ifstream gin(argv[4]);
+   MFEM_VERIFY(gin.good(), "cannot open the GridFunction file");
+   GridFunction gf(&mesh, gin);
+   FiniteElementSpace &fes = *gf.FESpace();
+   const ElementRestriction *R = dynamic_cast<const ElementRestriction *>(fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   MFEM_VERIFY(R, "no ElementRestriction");
+   D.iscalar("NE", mesh.GetNE()); D.iscalar("NV", mesh.GetNV()); D.iscalar("NBE", mesh.GetNBE());
+   D.iscalar("ndofs", fes.GetNDofs()); D.iscalar("order", fes.GetMaxElementOrder());
+   D.arr("gather_map", R->GatherMap());
+   D.vec("values", gf);
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()); ess_bdr = 0; ess_bdr[0] = 1; ess_bdr[5] = 1;
+   Array<int> ess; fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.arr("ess_z", ess);
+   Array<int> battr(mesh.GetNBE());
+   for (int i = 0; i < mesh.GetNBE(); i++) { battr[i] = mesh.GetBdrAttribute(i); }
+   D.arr("bdr_attributes", battr);
+   ConstantCoefficient zero(0.0);
+   D.scalar("l2_norm", gf.ComputeL2Error(zero));
+   {
+      Vector vx(3 * mesh.GetNV());
+      for (int i = 0; i < mesh.GetNV(); i++) { for (int d = 0; d < 3; d++) { vx(3 * i + d) = mesh.GetVertex(i)[d]; } }
+      D.vec("vertices", vx);
+   }
+   cout << "load_check ok: NE=" << mesh.GetNE() << " ndofs=" << fes.GetNDofs() << endl;
+   return 0;
+}
+
 int main(int argc, char **argv)
 {
    const string cmd = argc > 1 ? argv[1] : "";
@@ -694,6 +730,7 @@ int main(int argc, char **argv)
    if (cmd == "time_bioheat") { return bioheat(argc, argv, false); }
    if (cmd == "dump_bioheat_steps") { return bioheat_steps(argc, argv); }
    if (cmd == "time_apply") { return time_apply(argc, argv); }
+   if (cmd == "load_check") { return load_check(argc, argv); }
    if (cmd == "ex1") { return ex1(argc, argv); }
    if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }
    cerr << "usage: ref_driver dump_case|dump_bioheat|time_bioheat|time_apply|ex1|--check-inline ...\n";
