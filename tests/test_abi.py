@@ -47,3 +47,25 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".py")) or f == "Makefile":
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "liboracle" not in txt and "pa_oracle" not in txt and "oracle/" not in txt, os.path.join(d, f)
+
+
+def test_host_only_entry_points_work_without_a_gpu(tmp_path):
+    """entry points that are host arithmetic / host I/O by definition (no compute path): Chebyshev coefficients
+    (OperatorChebyshevSmoother::Setup) against the oracle's restatement, argument checking, the wire-format writers"""
+    import numpy as np
+    import b200pa
+    import orc
+    for order in range(1, 6):
+        for lam in (0.9, 1.388, 2.7):
+            a, b = b200pa.chebyshev_coeffs(order, lam), orc.chebyshev_coeffs(order, lam)
+            assert np.max(np.abs(a - b) / np.abs(b)) <= 1e-14
+    for bad in (0, 6):
+        with pytest.raises(b200pa.B200paError, match="order"):
+            b200pa.chebyshev_coeffs(bad, 1.0)
+    with pytest.raises(b200pa.B200paError):
+        b200pa.write_mesh(tmp_path / "no_such_dir" / "m.mesh", 2, 2, 2)
+    b200pa.write_mesh(tmp_path / "m.mesh", 2, 1, 1)
+    txt = (tmp_path / "m.mesh").read_text()
+    assert txt.startswith("MFEM mesh v1.0") and "\nelements\n2\n" in txt and "\nboundary\n10\n" in txt and "\nvertices\n12\n3\n" in txt
+    b200pa.write_gridfunction(tmp_path / "t.gf", 2, np.arange(45.0))
+    assert (tmp_path / "t.gf").read_text().startswith("FiniteElementSpace\nFiniteElementCollection: H1_3D_P2\nVDim: 1\nOrdering: 0\n\n0\n1\n")
