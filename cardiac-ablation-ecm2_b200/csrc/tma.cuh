@@ -41,12 +41,6 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first()
    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
    return pol;
 }
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-   unsigned long long pol;
-   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-   return pol;
-}
 // pol == 0: no hint
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
                                              unsigned long long pol)
@@ -56,20 +50,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                    smem_u32(dst_smem)),
                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                 : "memory");
-}
-
-// L2 prefetch of a contiguous global range by the TMA unit: nothing is written to shared memory and no LSU
-// wavefront is spent; `src` 16-byte aligned, `bytes` a multiple of 16
-__device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, unsigned bytes)
-{
-   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-// streaming 8-byte load (read-only path, no L1 allocation): q-data that was prefetched into L2
-__device__ __forceinline__ double ld_stream(const double *p)
-{
-   double v;
-   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); // volatile: issued where written
-   return v;
 }
 
 // ---- per-thread asynchronous copies global -> shared (LDGSTS): no register is tied up while the data flies
