@@ -43,3 +43,23 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                          text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_shared_memory_layout_model_of_the_kernel():
+    """tools/smem_strides.py holds the bank-conflict model the per-order layouts of pa_apply_kernel were chosen with;
+    the configuration compiled into the kernel must stay conflict-free in every phase over the work array at p=2
+    and p=3 and must agree with ApplyCfg in the source"""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import smem_strides as ss
+    for D in (3, 4):
+        NEB, SXS, RQ, SQ, ES, BS, mA, mC, QES, QMS = ss.KERNEL[D]
+        r = ss.phases(D, D + 1, NEB, SXS, RQ, SQ, ES, BS, mA, mC, QES, QMS)
+        for ph in ("A.w", "B.r", "B.w", "C1.r", "C1.w", "C2.r"):
+            assert r[ph][0] == r[ph][1], (D, ph, r[ph])
+    src = open(os.path.join(ROOT, "cardiac-ablation-ecm2_b200", "csrc", "pa_apply_kernel.cuh")).read()
+    new = src[src.index("#else", src.index("B200PA_TUNE_LAYOUT0")):]
+    for name, col in (("SXS", 1), ("SQ", 3), ("ES", 4)):
+        m = re.search(r"static constexpr int %s = ([^;]+);" % name, new)
+        vals = [int(v) for v in re.findall(r"\? (\d+)", m.group(1))] + [int(re.findall(r": (\d+)$", m.group(1).strip())[0])]
+        assert vals == [ss.KERNEL[D][col] for D in (2, 3, 4, 5, 6, 7)], (name, vals)
