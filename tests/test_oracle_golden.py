@@ -118,3 +118,24 @@ def test_chebyshev_and_power_method(case):
     x, it, conv, fn, norms = op.pcg_chebyshev(dinv, 3, lam_ref, case["B_rhs"], case["X0"], 1e-8, 0.0, 5000)
     assert it == int(case["cheb3_tol_iters"][0]) and conv == bool(case["cheb3_tol_converged"][0])
     close(x, case["X_cheb3_tol"], 1e-10)
+
+
+def test_factorised_qdata_reproduces_reference_pa_data(case):
+    """the factorisation behind b200pa_form_set_factorised, stated in numpy: on the (affine) golden meshes the
+    reference's pa_data D[Q^3,6,NE] = (w_q c_q) x (adj(J) adj(J)^T / det J taken once per element), to rounding"""
+    c = case
+    NQ, NE = c["Q1D"] ** 3, c["NE"]
+    J = c["J"].reshape(NE, 9, NQ)                      # J(q, row + 3 col, e), q fastest
+    assert np.max(np.abs(J - J[:, :, :1])) <= 1e-13 * np.max(np.abs(J))      # affine: J constant over an element
+    J0 = J[:, :, 0]
+    J11, J21, J31, J12, J22, J32, J13, J23, J33 = (J0[:, k] for k in range(9))
+    det = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13)
+    A = np.array([[J22 * J33 - J23 * J32, J32 * J13 - J12 * J33, J12 * J23 - J22 * J13],
+                  [J31 * J23 - J21 * J33, J11 * J33 - J13 * J31, J21 * J13 - J11 * J23],
+                  [J21 * J32 - J31 * J22, J31 * J12 - J11 * J32, J11 * J22 - J12 * J21]])          # [3,3,NE]
+    G = np.einsum("ike,jke->ije", A, A) / det                                                       # adj adj^T / det
+    geo6 = np.stack([G[0, 0], G[0, 1], G[0, 2], G[1, 1], G[1, 2], G[2, 2]], axis=1)                 # [NE,6]
+    kq = c["kq"] if c["kq"].size > 1 else np.full(NQ * NE, c["kq"][0])
+    cq = (np.tile(c["W"], NE) * kq).reshape(NE, 1, NQ)
+    D = (cq * geo6[:, :, None]).ravel()
+    close(D, c["pa_diff"], 1e-13)
