@@ -21,6 +21,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "cardiac-ablation-ecm2_b200"))
 
 GN, P_ORDER = (4, 3, 2), 2
+CHEB_ORDER, CHEB_MAX_EIG, CHEB_ITS = 3, 1.45, 5
 
 
 def kfun(xyz):
@@ -142,7 +143,42 @@ def worker(rank, world, port, ret):
         zz = A(d)
         den = dot(d, zz)
         nom = betanom
-    ret[rank] = dict(gid=gid, y=y, diag=diag, X=X, norms=np.array(norms), own=own, n_shared=len(sh_ldof))
+    # the same loop preconditioned by the Chebyshev smoother (b200pa_pcg_solve_chebyshev with a comm): every term of
+    # the polynomial applies the partitioned operator, dots stay owner-masked
+    coeffs = orc.chebyshev_coeffs(CHEB_ORDER, CHEB_MAX_EIG)
+
+    def cheb(rr):
+        res, zc = rr.copy(), np.zeros(nd)
+        for k in range(CHEB_ORDER):
+            if k > 0:
+                res = A(res)
+            res = dinv * res
+            zc = zc + coeffs[k] * res
+        return zc
+
+    Xc = np.zeros(nd)
+    r = rhs - A(Xc)
+    z = cheb(r)
+    d = z.copy()
+    nom = dot(d, r)
+    cnorms = [nom]
+    zz = A(d)
+    den = dot(zz, d)
+    for i in range(1, CHEB_ITS + 1):
+        alpha = nom / den
+        Xc += alpha * d
+        r -= alpha * zz
+        z = cheb(r)
+        betanom = dot(r, z)
+        cnorms.append(betanom)
+        if i == CHEB_ITS:
+            break
+        d = z + (betanom / nom) * d
+        zz = A(d)
+        den = dot(d, zz)
+        nom = betanom
+    ret[rank] = dict(gid=gid, y=y, diag=diag, X=X, norms=np.array(norms), own=own, n_shared=len(sh_ldof), Xc=Xc,
+                     cnorms=np.array(cnorms))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -173,6 +209,10 @@ def test_partitioned_matches_serial(world):
     d_ser[g_of_l] = un.diag()
     Xs, it, conv, fn, norms = op.pcg(op.jacobi_dinv(), bg[g_of_l], np.zeros(nglob), 0.0, 0.0, 12)
     X_ser[g_of_l] = Xs
+    Xcs, itc, _, _, cnorms = op.pcg_chebyshev(op.jacobi_dinv(), CHEB_ORDER, CHEB_MAX_EIG, bg[g_of_l], np.zeros(nglob), 0.0, 0.0, CHEB_ITS)
+    Xc_ser = np.empty(nglob)
+    Xc_ser[g_of_l] = Xcs
+    assert itc == CHEB_ITS
     covered = np.zeros(nglob, int)
     owned = np.zeros(nglob, int)
     for r in range(world):
@@ -185,6 +225,8 @@ def test_partitioned_matches_serial(world):
         assert np.max(np.abs(o["diag"] - d_ser[gid])) <= 1e-12 * np.max(np.abs(d_ser))
         assert np.max(np.abs(o["X"] - X_ser[gid])) <= 1e-10 * np.max(np.abs(X_ser))
         assert np.max(np.abs(o["norms"] - norms) / norms) <= 1e-9
+        assert np.max(np.abs(o["Xc"] - Xc_ser[gid])) <= 1e-10 * np.max(np.abs(Xc_ser))
+        assert np.max(np.abs(o["cnorms"] - cnorms) / cnorms) <= 1e-9
     assert covered.min() >= 1 and np.all(owned == 1)            # every dof owned exactly once
     # bit-identical copies of shared dofs on all sharers (ascending-rank summation order)
     for r in range(world):
