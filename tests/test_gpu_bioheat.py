@@ -79,19 +79,22 @@ def test_coupled_step_matches_reference(ctx):
     sp.close()
 
 
-def test_three_coupled_steps_match_reference(ctx):
+@pytest.mark.parametrize("factorised", [False, True])
+def test_three_coupled_steps_match_reference(ctx, factorised):
     """the time loop: T^{n+1} feeds k(T), sigma(T) of the next step; all state device-resident
-    (tests/golden/bioheat_steps_p2_n4.npz: the reference run of the same three steps, 12 PCG its per solve)"""
+    (tests/golden/bioheat_steps_p2_n4.npz: the reference run of the same three steps, 12 PCG its per solve);
+    with the stored and with the factorised sigma(T), k(T) q-data"""
     from b200pa.bioheat import CoupledStep
     g = dict(np.load(os.path.join(GOLDEN, "bioheat_steps_p2_n4.npz")))
     p, n = 2, 4
     m, b, sp = build(ctx, p, n)
-    cs = CoupledStep(ctx, sp, m, (n, n, n))
+    cs = CoupledStep(ctx, sp, m, (n, n, n), factorised=factorised)
     iters, nsteps = int(g["iters"][0]), int(g["nsteps"][0])
     outs = cs.run(ctx.to_dev(g["T_step0"]), nsteps, iters, iters)
     for k, o in enumerate(outs, 1):
         close(ctx.to_host(o["T1"]), g[f"T_step{k}"], 1e-10)
         close(ctx.to_host(o["phi"]), g[f"phi_step{k}"], 1e-10)
+    assert cs.fe.factorised == factorised and cs.ft.factorised == factorised
     cs.close()
     sp.close()
 
