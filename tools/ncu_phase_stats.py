@@ -13,6 +13,11 @@ def main():
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # a report may hold several launches: keep the first kernel's section (rows up to the next "Kernel Name" line)
+    nxt = [i for i, r in enumerate(rows) if i > 0 and r and r[0] == "Kernel Name"]
+    if nxt:
+        rows = rows[:nxt[0]]
+    rows = [r for r in rows if r]
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     R = rows[2:]
