@@ -5,11 +5,20 @@ on BASELINE.json configs[1]: the Pennes-bioheat operator k(T) grad + (rho c/dt +
 synthetic hex slab, order 2, N=100 per GPU (8,120,601 dofs per GPU), plus the PCG-iteration and
 implicit-step times of the same configuration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--order P] [--n N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--order P] [--elems N]
 
-One JSON line on rank 0.  A "step" is one operator apply.  N>1 (torchrun, one rank per GPU): the
-global mesh is a PX x PY x PZ grid of N^3-element boxes (weak scaling), every apply includes the
-shared-dof exchange over NCCL; value = global true dofs x K / max-over-ranks time.
+One JSON line on rank 0.  A "step" is one operator apply.  N>1 (torchrun, one rank per GPU): the global mesh
+is a PX x PY x PZ grid of N^3-element boxes (weak scaling), every apply includes the shared-dof exchange over
+NVLink; value = global true dofs x K / max-over-ranks time.
+
+Beside the headline the line carries (each leg can be switched off, `--legs` lists the ones to run):
+  N = 1   order_sweep (configs[3]: p = 1..6 at ~8 M dofs, diffusion+mass and diffusion only), c3 (configs[2]: the
+          coupled RF step at ~30 M dofs), c5_one_gpu (the per-GPU size of configs[4] on one GPU), pcg /
+          bioheat_step / rf_step / factorised_qdata on configs[1], cpu_baseline + parity against the reference CPU run;
+  N > 1   parity_multi (partitioned == serial on the communicator of the timed region, global ||Ax|| against a
+          one-GPU run of the same global mesh), weak_efficiency (the same per-GPU work without the exchange),
+          c5 (configs[4]: N=199 per GPU, 506 M dofs at 8 GPUs, weak), strong (the 398^3 mesh of configs[4] split
+          over the ranks).
 """
 import argparse
 import json
@@ -24,6 +33,10 @@ sys.path.insert(0, os.path.join(ROOT, "cardiac-ablation-ecm2_b200"))
 
 METRIC = "GDOF/s of FP64 PA diffusion+mass apply"
 PHYS = dict(dt=0.5, rc=3.6e6, wbcb=4.0e4, Ta=37.0, k0=0.5, ak=0.02, s0=0.3, as_=0.015, V=30.0)
+GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+SWEEP_N = {1: 200, 2: 100, 3: 67, 4: 50, 5: 40, 6: 34}       # ~8 M dofs at every order (configs[3])
+C5_N = 199                                                   # configs[4]: 398^3 elements, 506 M dofs over 2x2x2
+T_START = time.perf_counter()
 
 
 def algorithmic_bytes_per_dof(p, ncomp=7, factorised=False):
@@ -38,15 +51,46 @@ def algorithmic_bytes_per_dof(p, ncomp=7, factorised=False):
     return total, elem
 
 
+def global_dofs_of(GN, p):
+    return (GN[0] * p + 1) * (GN[1] * p + 1) * (GN[2] * p + 1)
+
+
+def workload_config(p, n, world, ops="both", qdata="stored"):
+    """the `config` both arms print (identical for the same command line)"""
+    grid = GRIDS[world]
+    GN = (n * grid[0], n * grid[1], n * grid[2])
+    gd = global_dofs_of(GN, p)
+    tot, _ = algorithmic_bytes_per_dof(p, 7 if ops == "both" else 6, qdata == "factorised")
+    what = "k(T) diffusion + (rho c/dt + perfusion) mass" if ops == "both" else "k(T) diffusion"
+    return {"workload": f"configs[1]: Pennes bioheat operator {what}, PA apply L->L, hex {GN[0]}x{GN[1]}x{GN[2]} "
+                        f"(N={n}^3 per GPU), order {p}, {gd} dofs",
+            "order": p, "ops": ops, "qdata": qdata, "elements_per_gpu": n ** 3, "dofs_per_gpu": global_dofs_of((n, n, n), p),
+            "global_dofs": gd, "partition": "x".join(map(str, grid)),
+            "l2": f"q-data + index streams = {tot * global_dofs_of((n, n, n), p) / 1e9:.2f} GB per step per GPU >> 126 MB L2, no flush needed"}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a thread every
+    ~2 ms (nvidia-smi -lms cannot go below ~20 ms: a 13 ms timed region would get one sample), nvidia-smi as the fallback"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.index, self.proc, self.stop, self.t, self.h, self.nv = [], index, None, False, None, None, None
+        self.marks = {}
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(self._nvml_index(nv))
+            self.nv = nv
+            self.smmax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -61,29 +105,54 @@ class ClockSampler:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _nvml_index(self, nv):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
-    def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
-            self.t.join(timeout=2)
-
-    def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+    def _poll(self):
+        nv = self.nv
+        # nvml.h: nvmlClocksEventReason{SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40}
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop:
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(get_reasons(self.h))
+                self.rows.append((time.perf_counter(), sm, [n for n, b in bits if rs & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.smmax = float(r[1])
+                self.rows.append((time.perf_counter(), float(r[0]), [n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def mark(self, name):
+        self.marks[name] = time.perf_counter()
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.proc:
+            self.proc.terminate()
+        if self.t:
+            self.t.join(timeout=2)
+
+    def summary(self, t0=None, t1=None):
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({n for r in rows for n in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": getattr(self, "smmax", None), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def measured_peak_hbm():
@@ -164,14 +233,19 @@ def oracle_port_cpu(p, n):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path, all host threads"""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads.  At --gpus N > 1 the
+    workload is the N-box mesh; one host runs a bounded sample of it: ONE box (the reference's int32 q-data indexing
+    ends at 5.6 M elements per rank at p=2), GDOF/s being a rate."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     p, n = args.order, args.n
+    world = args.gpus if args.gpus in GRIDS else 1
     r = run_reference_cpu(p, n, args.steps, args.warmup)
     if r is not None:
-        kind, sample = "reference", f"full workload: p={p}, N={n}, {r['ndofs']} dofs, {args.steps} applies, OpenMP device"
+        kind = "reference"
+        sample = (f"{'full workload' if world == 1 else 'one of the ' + str(world) + ' boxes of the workload'}: p={p}, N={n}, "
+                  f"{r['ndofs']} dofs, {args.steps} applies, OpenMP device on {r['cores']} threads")
     else:
         n_s = min(n, 40)
         r = oracle_port_cpu(p, n_s)
@@ -180,7 +254,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["t_apply_mean"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"bioheat PA diffusion+mass apply, hex N={n}^3, order {p}, {r['ndofs']} dofs (CPU, one node)"},
+            "config": workload_config(p, n, world, args.ops, "stored"),
             "cpu_baseline": {"value": v, "unit": "GDOF/s", "cores": r["cores"], "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -189,6 +263,226 @@ def reference_arm(args):
 
 
 _JSON_OUT = sys.stdout
+
+
+def hash01(gid):
+    """deterministic pseudo-random value in [0,1) per GLOBAL dof id: the same global vector on any partition"""
+    import numpy as np
+    z = gid.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+class Env:
+    """process-wide state: torch, ranks, context, communicator, timing helpers"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import b200pa
+        self.torch, self.dist, self.b = torch, dist, b200pa
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        if self.world not in GRIDS:
+            raise SystemExit(f"unsupported world size {self.world}")
+        self.grid = GRIDS[self.world]
+        self.ctx = b200pa.Context(self.local)
+        self.comm = None
+        if self.world > 1:
+            ids = [b200pa.Comm.unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            self.comm = b200pa.Comm(self.ctx, ids[0], self.rank, self.world)
+        self.peak, self.peak_src = measured_peak_hbm()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, reps, collective=True):
+        """CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+        collective=False: fn has no exchange inside (every rank on its own), still max over ranks"""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.ctx.torch_stream)
+        for _ in range(reps):
+            fn()
+        e1.record(self.ctx.torch_stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        self.barrier()
+        return ms
+
+    def allsum(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def free(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.synchronize()
+        self.torch.cuda.empty_cache()
+
+    def elapsed(self):
+        return time.perf_counter() - T_START
+
+
+class Problem:
+    """one partitioned bioheat operator: mesh part, space, stored-q-data form, consistent input vector"""
+
+    def __init__(self, env, GN, p, ops="both", qdata="stored", x_kind="hash", grid=None):
+        import numpy as np
+        b200pa, ctx = env.b, env.ctx
+        from b200pa import partition
+        self.env, self.p, self.ops, self.GN = env, p, ops, GN
+        self.grid = grid = env.grid if grid is None else grid
+        serial = grid == (1, 1, 1)
+        t0 = time.perf_counter()
+        rank = 0 if serial else env.rank
+        m = partition.build_part(GN, grid, rank, p, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
+        self.m, self.bas = m, b200pa.basis(p)
+        bas = self.bas
+        self.nd, self.ne = m["ndofs"], m["ne"]
+        self.sp = sp = b200pa.Space(ctx, p + 1, p + 2, self.ne, self.nd, m["gather_map"], bas["B"], bas["G"])
+        sp.geometry_from_vertices(bas["W"], m["vertices"], m["elem_vertices"])
+        m["gather_map"] = m["elem_vertices"] = m["vertices"] = None        # host copies are no longer needed
+        lat = m["lattice"].reshape(-1, 3)
+        xyz = (lat // p + bas["gll"][lat % p]) / np.array(GN, dtype=np.float64)
+        self.T0 = ctx.to_dev(37.0 + 20.0 * np.exp(-40.0 * ((xyz - 0.5) ** 2).sum(1)))
+        del xyz
+        self.nq = self.ne * (p + 2) ** 3
+        self.kq = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, self.T0)
+        self.mq = np.array([PHYS["rc"] / PHYS["dt"] + PHYS["wbcb"]])       # constant coefficient (CoefficientVector of size 1)
+        self.comm = None if serial else env.comm
+        self.owner = None
+        if self.comm is not None:
+            tabs = partition.shared_tables(m, grid, p)
+            self.comm.set_tables(self.nd, *tabs)
+            self.owner = b200pa.comm_build_tables(env.rank, self.nd, *tabs)[3].astype(bool)
+        self.form = self.make_form(qdata == "factorised")
+        self.global_dofs = global_dofs_of(GN, p)
+        if x_kind == "randomize":                                        # the reference's Vector::Randomize(1) (one rank)
+            self.xh = b200pa.randomize(self.nd, 1)
+        else:
+            self.xh = hash01(partition.global_ids(m, GN, p))
+        self.x = ctx.to_dev(self.xh)
+        self.y = ctx.empty(self.nd)
+        ctx.sync()
+        self.setup_s = time.perf_counter() - t0
+
+    def make_form(self, factorised=False, comm="default"):
+        f = self.env.b.Form(self.sp)
+        f.set_factorised(factorised)
+        f.assemble_diffusion(self.kq)
+        if self.ops == "both":
+            f.assemble_mass(self.mq)
+        f.set_essential(None)
+        c = self.comm if comm == "default" else comm
+        if c is not None:
+            f.set_comm(c)
+        return f
+
+    def global_sqnorm(self, v):
+        """sum over owned dofs of v^2, all ranks"""
+        import numpy as np
+        h = self.env.ctx.to_host(v)
+        s = float(np.sum(h[self.owner] ** 2)) if self.owner is not None else float(np.sum(h ** 2))
+        return self.env.allsum(s) if self.comm is not None else s
+
+    # ---------------------------------------------------------------- measurements
+    def apply_times(self, form, K, W, phases=True, collective=True):
+        x, y, env = self.x, self.y, self.env
+        for _ in range(W):
+            form.mult(x, y)
+        out = {"ms_apply": env.timed(lambda: form.mult(x, y), K, collective) / K}
+        if phases:
+            out["ms_elem"] = env.timed(lambda: form.mult_phases(x, y, 1), K, False) / K
+            out["ms_seg"] = env.timed(lambda: form.mult_phases(x, y, 2), K, collective) / K
+        return out
+
+    def roofline(self, t, factorised=False):
+        bt, be = algorithmic_bytes_per_dof(self.p, 7 if self.ops == "both" else 6, factorised)
+        peak = self.env.peak
+        r = {"gdof_per_s": self.global_dofs / (t["ms_apply"] * 1e-3) / 1e9, "ms_apply": t["ms_apply"],
+             "apply_frac": bt * self.nd / (t["ms_apply"] * 1e-3) / 1e9 / peak, "bytes_per_dof": bt}
+        if "ms_elem" in t:
+            r.update(ms_element_kernel=t["ms_elem"], ms_segment_sum=t["ms_seg"],
+                     kernel_frac=be * self.nd / (t["ms_elem"] * 1e-3) / 1e9 / peak)
+        return r
+
+    def rhs(self, form):
+        env, sp = self.env, self.sp
+        lf = sp.domain_lf(env.ctx.to_dev(__import__("numpy").array([PHYS["wbcb"] * PHYS["Ta"]])))
+        if form is not None and getattr(form, "_comm", None) is not None:
+            form._comm.exchange_sum(lf)      # local partial sums -> consistent L-vector
+        return env.ctx.add(lf, 1.0, form.mult(self.T0))
+
+    def pcg_times(self, form, rhs, its=20, collective=True):
+        env = self.env
+        dinv = form.jacobi()
+        T1 = self.T0.clone()
+        form.pcg(dinv, rhs, T1, 0.0, 0.0, 3, want_norms=False)
+        T1.copy_(self.T0)
+        ms1 = env.timed(lambda: form.pcg(dinv, rhs, T1, 0.0, 0.0, its, want_norms=False), 1, collective)
+        T1.copy_(self.T0)
+        ms3 = env.timed(lambda: form.pcg(dinv, rhs, T1, 0.0, 0.0, 3 * its, want_norms=False), 1, collective)
+        marginal = (ms3 - ms1) / (2 * its)       # without the two set-up applies and the final read-back
+        return {"ms_per_iter": ms1 / its, "iters": its, "gdof_per_s": self.global_dofs * its / (ms1 * 1e-3) / 1e9,
+                "ms_per_iter_marginal": marginal, "gdof_per_s_marginal": self.global_dofs / (marginal * 1e-3) / 1e9}
+
+    def implicit_step(self, form, rhs, rel_tol, max_iter, collective=True):
+        """k(T) q-data + PA set-up + Jacobi diagonal + PCG: (ms, result).  rel_tol = 0: exactly max_iter iterations"""
+        env, sp = self.env, self.sp
+        T1 = self.T0.clone()
+
+        def step():
+            k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, self.T0, out=self.kq)
+            form.assemble_diffusion(k2)
+            if self.ops == "both":
+                form.assemble_mass(self.mq)
+            d2 = form.jacobi()
+            T1.copy_(self.T0)
+            return form.pcg(d2, rhs, T1, rel_tol, 0.0, max_iter, want_norms=False)[0]
+
+        step()
+        res = [None]
+        ms = env.timed(lambda: res.__setitem__(0, step()), 1, collective)
+        return ms, res[0]
+
+    def close(self):
+        self.form.close()
+        self.sp.close()
+        self.T0 = self.kq = self.x = self.y = self.m = None
+        self.env.free()
+
+
+def leg_bioheat(P, form, collective=True, fixed_iters=10):
+    """PCG iteration time + the implicit bioheat step to tolerance and at a fixed iteration count"""
+    rhs = P.rhs(form)
+    out = {"pcg": P.pcg_times(form, rhs, 20, collective)}
+    ms, res = P.implicit_step(form, rhs, 1e-8, 500, collective)
+    out["bioheat_step"] = {"ms": ms, "pcg_iters": res.final_iter, "converged": bool(res.converged),
+                           "what": "k(T) q-data + PA setup + Jacobi diagonal + PCG to rel 1e-8"}
+    ms, res = P.implicit_step(form, rhs, 0.0, fixed_iters, collective)
+    out["bioheat_step_fixed"] = {"ms": ms, "pcg_iters": res.final_iter,
+                                 "what": f"the same step with exactly {fixed_iters} PCG iterations (comparable across GPU counts: "
+                                         "the iteration count to tolerance grows with the global mesh)"}
+    return out
 
 
 def main():
@@ -204,11 +498,17 @@ def main():
                     help="diffusion q-data of the timed apply: the reference's six components per q-point (headline) or the "
                          "factorised form for affine meshes (b200pa_form_set_factorised)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extras", action="store_true", help="skip PCG / implicit-step extras (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (profiling / tuning runs)")
+    ap.add_argument("--legs", default="all", help="comma list of: factorised,bioheat,rf,sweep,c3,c5,parity,strong (default all)")
+    ap.add_argument("--c5-elems", type=int, default=C5_N, help="per-GPU N of the configs[4] legs (tests use a small one)")
+    ap.add_argument("--budget-s", type=float, default=600.0, help="optional legs are skipped once the run is older than this")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
+    legs = set("factorised,bioheat,rf,sweep,c3,c5,parity,strong".split(",")) if args.legs == "all" else set(args.legs.split(","))
+    if args.no_extras:
+        legs = set()
 
     # rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's "NCCL version ..." banner at any
     # NCCL_DEBUG level >= VERSION): keep the real stdout aside for the JSON line and point fd 1 at stderr meanwhile
@@ -217,237 +517,202 @@ def main():
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
-    import b200pa
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    env = Env(args)
+    torch, b200pa, ctx = env.torch, env.b, env.ctx
+    rank, world = env.rank, env.world
+    args.gpus = world
     p, n, K, W = args.order, args.n, args.steps, args.warmup
-    from b200pa import partition
-    grid = partition.GRIDS.get(world)
-    if grid is None:
-        raise SystemExit(f"unsupported world size {world}")
+    grid = env.grid
     GN = (n * grid[0], n * grid[1], n * grid[2])
+    line_extra = {}
 
-    # ---- problem set-up (host builder -> device handles); not timed
-    t_setup = time.perf_counter()
-    m = partition.build_part(GN, grid, rank, p, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
-    bas = b200pa.basis(p)
-    ctx = b200pa.Context(local)
-    nd, ne = m["ndofs"], m["ne"]
-    sp = b200pa.Space(ctx, p + 1, p + 2, ne, nd, m["gather_map"], bas["B"], bas["G"])
-    sp.geometry_from_vertices(bas["W"], m["vertices"], m["elem_vertices"])
-    lat = m["lattice"].reshape(-1, 3)
-    gll = bas["gll"]
-    xyz = (lat // p + gll[lat % p]) / np.array(GN, dtype=np.float64)
-    T0h = 37.0 + 20.0 * np.exp(-40.0 * ((xyz - 0.5) ** 2).sum(1))
-    T0 = ctx.to_dev(T0h)
-    nq = ne * (p + 2) ** 3
-    kq = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0)
-    mq = ctx.coeff_eval(1, nq, PHYS["rc"] / PHYS["dt"] + PHYS["wbcb"], 0.0, 0.0)
+    def guarded(name, fn):
+        """optional legs never take the headline down; all ranks take the same decision"""
+        skip = env.elapsed() > args.budget_s
+        if world > 1:
+            t = torch.tensor([1.0 if skip else 0.0], device="cuda")
+            env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+            skip = bool(t.item() > 0)
+        if skip:
+            line_extra[name] = {"skipped": f"run older than --budget-s {args.budget_s:.0f} s"}
+            return
+        t0 = time.perf_counter()
+        try:
+            r = fn()
+            if isinstance(r, dict):
+                r["leg_s"] = time.perf_counter() - t0
+            line_extra[name] = r
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise          # a rank that drops out of a collective leg would hang the others: fail loudly instead
+            line_extra[name] = {"failed": f"{type(e).__name__}: {e}"[:400]}
+
+    # ---- multi-GPU correctness FIRST, on the communicator / transport the timed region uses
+    if world > 1 and "parity" in legs:
+        from b200pa import selfcheck
+        r = selfcheck.partitioned_vs_serial(ctx, env.comm, rank, world, p=2, GN=(16, 12, 8), full=False)
+        r["tolerances"] = {"apply": 1e-12, "pcg_fixed_iters": 1e-10, "iteration_counts": "+-1"}
+        line_extra["parity_multi"] = r
+
+    # ---- the headline problem (set-up not timed)
+    P = Problem(env, GN, p, args.ops, args.qdata, x_kind="randomize" if world == 1 else "hash")
+    form, x, y, nd, ne = P.form, P.x, P.y, P.nd, P.ne
+    comm = P.comm
     fact = args.qdata == "factorised"
-    form = b200pa.Form(sp)
-    form.set_factorised(fact)
-    form.assemble_diffusion(kq)
-    if args.ops == "both":
-        form.assemble_mass(mq)
-    form.set_essential(None)
-    comm = None
-    if world > 1:
-        ids = [b200pa.Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm = b200pa.Comm(ctx, ids[0], rank, world)
-        comm.set_tables(nd, *partition.shared_tables(m, grid, p))
-        form.set_comm(comm)
-    global_dofs = (GN[0] * p + 1) * (GN[1] * p + 1) * (GN[2] * p + 1)
-    xh = b200pa.randomize(nd, 1) if world == 1 else np.random.default_rng(1).random(nd)
-    x = ctx.to_dev(xh)
-    if comm is not None:
-        comm.bcast(x)          # consistent L-vector
-    y = ctx.empty(nd)
-    ctx.sync()
-    t_setup = time.perf_counter() - t_setup
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, reps):
-        """CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ctx.torch_stream)
-        for _ in range(reps):
-            fn()
-        e1.record(ctx.torch_stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
-        return ms
+    global_dofs = P.global_dofs
 
     # ---- the timed region: K applies, inputs resident in HBM
     for _ in range(W):
         form.mult(x, y)
-    with ClockSampler(local) as clk:
+    with ClockSampler(env.local) as clk:
         l0 = b200pa.launch_count()
-        ms_total = timed(lambda: form.mult(x, y), K)
+        clk.mark("t0")
+        ms_total = env.timed(lambda: form.mult(x, y), K)
+        clk.mark("t1")
         launches = b200pa.launch_count() - l0
         # dominant kernel alone (same stream, same inputs) for the roofline
-        ms_elem = timed(lambda: form.mult_phases(x, y, 1), K)
-        ms_seg = timed(lambda: form.mult_phases(x, y, 2), K)
+        ms_elem = env.timed(lambda: form.mult_phases(x, y, 1), K, False)
+        ms_seg = env.timed(lambda: form.mult_phases(x, y, 2), K)
+        # the same apply kept running so that the clock record has >= 10 samples under this load
+        reps_long = max(K, int(0.25 / max(ms_total / K * 1e-3, 1e-6)))
+        ms_long = env.timed(lambda: form.mult(x, y), reps_long)
     clocks = clk.summary()
+    clocks["samples_in_timed_region"] = clk.summary(clk.marks["t0"], clk.marks["t1"])["samples"]
+    clocks["sustained"] = {"applies": reps_long, "ms_per_step": ms_long / reps_long}
     form.mult(x, y)
-    ynorm2 = ctx.dot(y, y) if world == 1 else None
+    ynorm2 = P.global_sqnorm(y)
 
     # ---- e2e: the same apply through the host-buffer C-ABI entry point (pinned host x, y)
-    xp = torch.from_numpy(xh).pin_memory()
+    xp = torch.from_numpy(P.xh).pin_memory()
     yp = torch.empty(nd, dtype=torch.float64).pin_memory()
     for _ in range(3):
         form.mult_host(xp, yp)
     Ke = max(3, min(K, 20))
-    ms_e2e = timed(lambda: form.mult_host(xp, yp), Ke)
+    ms_e2e = env.timed(lambda: form.mult_host(xp, yp), Ke)
 
     bytes_total, bytes_elem = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6, fact)
-    peak, peak_src = measured_peak_hbm()
+    peak, peak_src = env.peak, env.peak_src
     t_elem = ms_elem / K * 1e-3
     achieved = bytes_elem * nd / t_elem / 1e9
     value = global_dofs * K / (ms_total * 1e-3) / 1e9
+    traffic = None if fact else measured_traffic(p, n, args.ops)
     line = {
         "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"configs[1]: Pennes bioheat operator k(T) diffusion + (rho c/dt + perfusion) mass, PA apply L->L, "
-                               f"hex {GN[0]}x{GN[1]}x{GN[2]} (N={n}^3 per GPU), order {p}, {global_dofs} dofs",
-                   "order": p, "ops": args.ops, "qdata": args.qdata, "elements_per_gpu": ne, "dofs_per_gpu": nd, "global_dofs": global_dofs,
-                   "partition": "x".join(map(str, grid)),
-                   "exchange": ("none" if comm is None else ("peer-memory stores + flags over NVLink (CUDA IPC)" if comm.p2p_enabled()
-                                                             else "NCCL send/recv + all-reduce")),
-                   "l2": f"q-data + index streams = {bytes_total * nd / 1e9:.2f} GB per step >> 126 MB L2, no flush needed"},
+        "config": workload_config(p, n, world, args.ops, args.qdata),
+        "transport": ("none (one GPU)" if comm is None else ("peer-memory stores + flags over NVLink (CUDA IPC mailboxes), no NCCL call in the loop"
+                                                             if comm.p2p_enabled() else "NCCL send/recv + all-reduce")),
         "e2e": {"value": global_dofs * Ke / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * nd,
                 "d2h_bytes_per_step": 8 * nd, "ms_per_step": ms_e2e / Ke,
                 "api": "b200pa_form_mult_host (pinned host x -> H2D -> apply -> D2H -> pinned host y)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None if fact else measured_traffic(p, n, args.ops), "algorithmic_bytes": bytes_elem * nd,
+                     "traffic": traffic,
+                     "traffic_source": None if traffic is None else "ncu --set full capture of this command committed under profiles/ (profiles/traffic.json); not measured in this run",
+                     "algorithmic_bytes": bytes_elem * nd,
                      "kernel": "pa_apply_kernel (gather + diffusion + mass + slot-order write)",
                      "bytes_per_dof": bytes_elem, "ms_per_launch": ms_elem / K, "peak_source": peak_src},
         "roofline_apply": {"achieved": bytes_total * nd / (ms_total / K * 1e-3) / 1e9, "frac": bytes_total * nd / (ms_total / K * 1e-3) / 1e9 / peak,
                            "bytes_per_dof": bytes_total, "ms_element_kernel": ms_elem / K, "ms_segment_sum": ms_seg / K},
-        "clocks": clocks, "setup_s": t_setup,
+        "clocks": clocks, "setup_s": P.setup_s,
+        "apply_sqnorm_global": ynorm2,
     }
 
-    # ---- the same operator with the factorised diffusion q-data (the mesh is affine): what a caller who opts in gets
-    if not fact and sp.affine and not args.no_extras:
-        f2 = b200pa.Form(sp)
-        f2.set_factorised(True)
-        f2.assemble_diffusion(kq)
-        if args.ops == "both":
-            f2.assemble_mass(mq)
-        f2.set_essential(None)
-        if comm is not None:
-            f2.set_comm(comm)
-        y2 = ctx.empty(nd)
-        for _ in range(W):
-            f2.mult(x, y2)
-        ms2 = timed(lambda: f2.mult(x, y2), K)
-        ms2_elem = timed(lambda: f2.mult_phases(x, y2, 1), K)
-        bt2, be2 = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6, True)
-        f2.mult(x, y2)
-        form.mult(x, y)
-        diff = float((y2 - y).abs().max().item() / y.abs().max().item())
-        d2 = f2.jacobi()
-        lf2 = sp.domain_lf(ctx.coeff_eval(1, nq, PHYS["wbcb"] * PHYS["Ta"], 0.0, 0.0))
-        if comm is not None:
-            comm.exchange_sum(lf2)
-        rhs2 = ctx.add(lf2, 1.0, f2.mult(T0))
-        Tf = T0.clone()
-        f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 3, want_norms=False)
-        Tf.copy_(T0)
-        msp1 = timed(lambda: f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 20, want_norms=False), 1)
-        Tf.copy_(T0)
-        msp3 = timed(lambda: f2.pcg(d2, rhs2, Tf, 0.0, 0.0, 60, want_norms=False), 1)
-
-        def implicit_step2():
-            k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0, out=kq)
-            f2.assemble_diffusion(k2)
-            if args.ops == "both":
-                f2.assemble_mass(mq)
-            dd = f2.jacobi()
-            Tf.copy_(T0)
-            return f2.pcg(dd, rhs2, Tf, 1e-8, 0.0, 500, want_norms=False)[0]
-
-        implicit_step2()
-        r2 = [None]
-        ms_step2 = timed(lambda: r2.__setitem__(0, implicit_step2()), 1)
-        line["factorised_qdata"] = {
-            "what": "same operator, diffusion q-data stored as w_q k_q per q-point + adj(J)adj(J)^T/detJ per element "
-                    "(b200pa_form_set_factorised; the mesh is affine)",
-            "value": global_dofs * K / (ms2 * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms2 / K, "ms_element_kernel": ms2_elem / K,
-            "bytes_per_dof": bt2, "hbm_frac_own_bytes": bt2 * nd / (ms2 / K * 1e-3) / 1e9 / peak,
-            "max_rel_diff_vs_stored": diff, "pcg_ms_per_iter_marginal": (msp3 - msp1) / 40,
-            "bioheat_step_ms": ms_step2, "bioheat_step_pcg_iters": r2[0].final_iter}
-        f2.close()
-
-    # ---- extras on the same configuration: PCG iteration time and the implicit bioheat step
-    if not args.no_extras:
-        dinv = form.jacobi()
-        lf = sp.domain_lf(ctx.coeff_eval(1, nq, PHYS["wbcb"] * PHYS["Ta"], 0.0, 0.0))
-        if comm is not None:
-            comm.exchange_sum(lf)      # local partial sums -> consistent L-vector
-        rhs = ctx.add(lf, 1.0, form.mult(T0))
+    # ---- e2e of what an application calls: one PCG solve through the host-buffer entry point (b, x cross PCIe once per solve)
+    if legs:
+        rhs0 = P.rhs(form)
+        bp = rhs0.cpu().pin_memory()
+        xs = torch.empty(nd, dtype=torch.float64).pin_memory()
+        dinv0 = form.jacobi()
         its = 20
-        T1 = T0.clone()
-        form.pcg(dinv, rhs, T1, 0.0, 0.0, 3, want_norms=False)
-        T1.copy_(T0)
-        ms_pcg = timed(lambda: form.pcg(dinv, rhs, T1, 0.0, 0.0, its, want_norms=False), 1)
-        T1.copy_(T0)
-        ms_pcg3 = timed(lambda: form.pcg(dinv, rhs, T1, 0.0, 0.0, 3 * its, want_norms=False), 1)
-        marginal = (ms_pcg3 - ms_pcg) / (2 * its)       # without the two set-up applies and the final read-back
-        line["pcg"] = {"ms_per_iter": ms_pcg / its, "iters": its, "gdof_per_s": global_dofs * its / (ms_pcg * 1e-3) / 1e9,
-                       "ms_per_iter_marginal": marginal, "gdof_per_s_marginal": global_dofs / (marginal * 1e-3) / 1e9}
 
-        def implicit_step():
-            k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, T0, out=kq)
-            form.assemble_diffusion(k2)
-            if args.ops == "both":
-                form.assemble_mass(mq)
-            d2 = form.jacobi()
-            T1.copy_(T0)
-            return form.pcg(d2, rhs, T1, 1e-8, 0.0, 500, want_norms=False)[0]
+        xs.zero_()
+        form.pcg(dinv0, bp, xs, 0.0, 0.0, its, want_norms=False, host=True)
+        xs.zero_()
+        ms_sh = env.timed(lambda: form.pcg(dinv0, bp, xs, 0.0, 0.0, its, want_norms=False, host=True), 1)
+        line["e2e_pcg"] = {"value": global_dofs * its / (ms_sh * 1e-3) / 1e9, "unit": "GDOF/s (dofs x PCG iterations / s)", "iters": its,
+                           "ms_per_solve": ms_sh, "h2d_bytes_per_solve": 16 * nd, "d2h_bytes_per_solve": 8 * nd,
+                           "api": "b200pa_pcg_solve_host (pinned host b, x -> H2D -> 20 Jacobi-PCG iterations -> D2H x)"}
+        del bp, xs, rhs0, dinv0
 
-        implicit_step()
-        res = [None]
-        ms_step = timed(lambda: res.__setitem__(0, implicit_step()), 1)
-        line["bioheat_step"] = {"ms": ms_step, "pcg_iters": res[0].final_iter, "converged": bool(res[0].converged),
-                                "what": "k(T) q-data + PA setup + Jacobi diagonal + PCG to rel 1e-8"}
+    # ---- multi-GPU: the same per-GPU work with the exchange switched off (every rank alone) = the weak-scaling reference
+    if world > 1 and legs:
+        fs = P.make_form(fact, comm=None)
+        t_solo = P.apply_times(fs, K, W, phases=False, collective=False)
+        line["weak_efficiency"] = {"what": "this rank's box as a one-GPU problem (no exchange, no all-reduce), max over ranks, against the "
+                                           "partitioned run of the same command", "ms_apply_no_exchange": t_solo["ms_apply"],
+                                   "apply": t_solo["ms_apply"] / (ms_total / K)}
+        if "bioheat" in legs:
+            solo = leg_bioheat(P, fs, collective=False)
+            line_extra["_solo"] = solo
+        fs.close()
+        # global ||Ax|| against a one-GPU run of the SAME global mesh and the same global input vector (where it fits)
+        if "parity" in legs and GN[0] * GN[1] * GN[2] <= 8_200_000:
+            def serial_norm():
+                r = {"what": "||A x||_2 over the global mesh: partitioned (owned dofs, all ranks) vs the same mesh on ONE GPU (rank 0)"}
+                if rank == 0:
+                    S = Problem(env, GN, p, args.ops, args.qdata, x_kind="hash", grid=(1, 1, 1))
+                    S.form.mult(S.x, S.y)
+                    s2 = S.global_sqnorm(S.y)
+                    S.close()
+                    r.update(partitioned=float(np.sqrt(ynorm2)), one_gpu=float(np.sqrt(s2)),
+                             rel_diff=abs(np.sqrt(ynorm2) - np.sqrt(s2)) / np.sqrt(s2), tolerance=1e-12)
+                env.barrier()
+                return r
+            guarded("parity_global_norm", serial_norm)
 
-        # the whole RF-ablation coupled step (electrostatics + Joule + bioheat), fixed 20 + 20 PCG iterations
+    # ---- the same operator with the factorised diffusion q-data (the mesh is affine): what a caller who opts in gets
+    if not fact and P.sp.affine and "factorised" in legs:
+        def leg_fact():
+            f2 = P.make_form(True)
+            t2 = P.apply_times(f2, K, W, phases=True)
+            bt2, _ = algorithmic_bytes_per_dof(p, 7 if args.ops == "both" else 6, True)
+            y2 = ctx.empty(nd)
+            f2.mult(x, y2)
+            form.mult(x, y)
+            diff = float((y2 - y).abs().max().item() / y.abs().max().item())
+            bh = leg_bioheat(P, f2)
+            out = {"what": "same operator, diffusion q-data stored as w_q k_q per q-point + adj(J)adj(J)^T/detJ per element "
+                           "(b200pa_form_set_factorised; the mesh is affine)",
+                   "value": global_dofs / (t2["ms_apply"] * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": t2["ms_apply"],
+                   "ms_element_kernel": t2["ms_elem"], "bytes_per_dof": bt2,
+                   "hbm_frac_own_bytes": bt2 * nd / (t2["ms_apply"] * 1e-3) / 1e9 / peak, "max_rel_diff_vs_stored": diff,
+                   "pcg_ms_per_iter_marginal": bh["pcg"]["ms_per_iter_marginal"], "bioheat_step_ms": bh["bioheat_step"]["ms"],
+                   "bioheat_step_pcg_iters": bh["bioheat_step"]["pcg_iters"], "bioheat_step_fixed_ms": bh["bioheat_step_fixed"]["ms"]}
+            f2.close()
+            return out
+        guarded("factorised_qdata", leg_fact)
+
+    # ---- PCG iteration time and the implicit bioheat step on the headline configuration
+    if "bioheat" in legs:
+        bh = leg_bioheat(P, form)
+        line.update(bh)
+        solo = line_extra.pop("_solo", None)
+        if solo is not None:
+            we = line["weak_efficiency"]
+            we["pcg_iteration"] = solo["pcg"]["ms_per_iter_marginal"] / bh["pcg"]["ms_per_iter_marginal"]
+            we["bioheat_step_fixed"] = solo["bioheat_step_fixed"]["ms"] / bh["bioheat_step_fixed"]["ms"]
+            we["ms_no_exchange"] = {"pcg_iteration": solo["pcg"]["ms_per_iter_marginal"], "bioheat_step_fixed": solo["bioheat_step_fixed"]["ms"]}
+
+    # ---- the whole RF-ablation coupled step (electrostatics + Joule + bioheat), fixed 20 + 20 PCG iterations
+    def rf_leg(PP, GNN):
         from b200pa.bioheat import CoupledStep
-        cs = CoupledStep(ctx, sp, m, GN, comm=comm)
-        cs.step(T0, 2, 2)
+        cs = CoupledStep(ctx, PP.sp, PP.m, GNN, comm=PP.comm)
+        cs.step(PP.T0, 2, 2)
         out = [None]
-        ms_rf = timed(lambda: out.__setitem__(0, cs.step(T0, 20, 20)), 1)
+        ms_rf = env.timed(lambda: out.__setitem__(0, cs.step(PP.T0, 20, 20)), 1)
         o = out[0]
-        line["rf_step"] = {"ms": ms_rf, "pcg_iters": [20, 20], "what": "sigma(T),k(T) q-data + 2 PA set-ups + 2 Jacobi diagonals + "
-                           "EliminateRHS + 20 PCG its (phi) + Joule q-data + RHS + 20 PCG its (T)"}
+        r = {"ms": ms_rf, "pcg_iters": [20, 20], "what": "sigma(T),k(T) q-data + 2 PA set-ups + 2 Jacobi diagonals + "
+             "EliminateRHS + 20 PCG its (phi) + Joule q-data + RHS + 20 PCG its (T)"}
         if world == 1:
-            line["rf_step"].update(phi_norm=float(np.sqrt(ctx.dot(o["phi"], o["phi"]))), T1_norm=float(np.sqrt(ctx.dot(o["T1"], o["T1"]))),
-                                   src_sum=float(o["src"].sum().item()))
+            r.update(phi_norm=float(np.sqrt(ctx.dot(o["phi"], o["phi"]))), T1_norm=float(np.sqrt(ctx.dot(o["T1"], o["T1"]))),
+                     src_sum=float(o["src"].sum().item()))
         cs.close()
+        return r
+    if "rf" in legs and args.ops == "both":
+        line["rf_step"] = rf_leg(P, GN)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on the host cores
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -477,15 +742,107 @@ def main():
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {e}"}
+    del form, x, y, xp, yp
+    P.close()
+
+    # ---- configs[3]: order sweep on one GPU, ~8 M dofs per order, diffusion+mass and diffusion only
+    if world == 1 and "sweep" in legs:
+        def sweep():
+            rows = []
+            for pp in range(1, 7):
+                nn = SWEEP_N[pp]
+                for ops in ("both", "diff"):
+                    if ops == "both":
+                        S = Problem(env, (nn, nn, nn), pp, "both")
+                        f = S.form
+                    else:
+                        S.ops = "diff"
+                        f = S.make_form(False)
+                    with ClockSampler(env.local) as ck:
+                        t = S.apply_times(f, 20, 3)
+                    r = S.roofline(t)
+                    r.update(order=pp, ops=ops, elems=nn, dofs=S.nd, clocks=ck.summary())
+                    rows.append(r)
+                    if ops == "diff":
+                        f.close()
+                        S.close()
+            return {"what": "configs[3]: PA apply roofline sweep on one B200, ~8 M dofs per order; apply_frac = SURVEY §8(d) bytes / "
+                            "time / measured HBM peak for the whole L->L apply, kernel_frac = the element kernel's share alone",
+                    "rows": rows}
+        guarded("order_sweep", sweep)
+
+    # ---- configs[2]: the coupled RF step at ~30 M dofs on one GPU
+    if world == 1 and "c3" in legs and args.ops == "both":
+        def c3():
+            nn = 155
+            S = Problem(env, (nn, nn, nn), 2, "both")
+            t = S.apply_times(S.form, 10, 3)
+            r = {"what": "configs[2]: RF-ablation coupled step, order 2, hex 155^3, 30,080,231 dofs, one GPU", "dofs": S.nd,
+                 "apply": S.roofline(t), "setup_s": S.setup_s}
+            r.update(leg_bioheat(S, S.form))
+            r["rf_step"] = rf_leg(S, (nn, nn, nn))
+            S.close()
+            return r
+        guarded("c3", c3)
+
+    # ---- configs[4]: N=199 per GPU (398^3 elements, 506 M dofs at 8 GPUs): weak leg at any N, incl. the one-GPU base
+    c5n = args.c5_elems
+    if "c5" in legs and args.ops == "both":
+        def c5():
+            GN5 = (c5n * grid[0], c5n * grid[1], c5n * grid[2])
+            S = Problem(env, GN5, 2, "both")
+            t = S.apply_times(S.form, 10, 3)
+            r = {"what": f"configs[4] weak: N={c5n}^3 elements per GPU, order 2, global hex {GN5[0]}x{GN5[1]}x{GN5[2]}, "
+                         f"{S.global_dofs} dofs on {world} GPU(s)", "global_dofs": S.global_dofs, "dofs_per_gpu": S.nd,
+                 "apply": S.roofline(t), "setup_s": S.setup_s}
+            r.update(leg_bioheat(S, S.form))
+            if world > 1:
+                fs = S.make_form(False, comm=None)
+                ts = S.apply_times(fs, 10, 3, phases=False, collective=False)
+                solo = leg_bioheat(S, fs, collective=False)
+                fs.close()
+                r["one_gpu_same_size"] = {"what": "this rank's box as a one-GPU problem (no exchange), max over ranks",
+                                          "ms_apply": ts["ms_apply"], "pcg_ms_per_iter_marginal": solo["pcg"]["ms_per_iter_marginal"],
+                                          "bioheat_step_fixed_ms": solo["bioheat_step_fixed"]["ms"], "bioheat_step_ms": solo["bioheat_step"]["ms"],
+                                          "bioheat_step_pcg_iters": solo["bioheat_step"]["pcg_iters"]}
+                r["parallel_efficiency"] = {"apply": ts["ms_apply"] / t["ms_apply"],
+                                            "pcg_iteration": solo["pcg"]["ms_per_iter_marginal"] / r["pcg"]["ms_per_iter_marginal"],
+                                            "bioheat_step_fixed": solo["bioheat_step_fixed"]["ms"] / r["bioheat_step_fixed"]["ms"],
+                                            "bioheat_step_to_tolerance": solo["bioheat_step"]["ms"] / r["bioheat_step"]["ms"]}
+            S.close()
+            return r
+        guarded("c5", c5)
+
+    # ---- configs[4] strong: the 398^3 mesh split over 2 / 4 / 8 GPUs (at 8 it is the weak leg's problem)
+    if world in (2, 4) and "strong" in legs and args.ops == "both":
+        def strong():
+            GNs = (2 * c5n, 2 * c5n, 2 * c5n)
+            S = Problem(env, GNs, 2, "both")
+            t = S.apply_times(S.form, 5, 3)
+            r = {"what": f"configs[4] strong: global hex {GNs[0]}^3, order 2, {S.global_dofs} dofs split over {world} GPUs "
+                         "(compare the same key across the --gpus 2 / 4 lines and c5 of the --gpus 8 line)",
+                 "global_dofs": S.global_dofs, "dofs_per_gpu": S.nd, "apply": S.roofline(t), "setup_s": S.setup_s}
+            rhs = S.rhs(S.form)
+            r["pcg"] = S.pcg_times(S.form, rhs, 10)
+            ms, res = S.implicit_step(S.form, rhs, 0.0, 10)
+            r["bioheat_step_fixed"] = {"ms": ms, "pcg_iters": res.final_iter}
+            S.close()
+            return r
+        guarded("strong", strong)
+    if world == 8 and "strong" in legs and isinstance(line_extra.get("c5"), dict) and "apply" in line_extra["c5"]:
+        c = line_extra["c5"]
+        line_extra["strong"] = {"what": "configs[4] strong at 8 GPUs = the c5 problem (398^3 elements over 2x2x2)", "global_dofs": c["global_dofs"],
+                                "dofs_per_gpu": c["dofs_per_gpu"], "apply": c["apply"], "pcg": c["pcg"], "bioheat_step_fixed": c["bioheat_step_fixed"]}
+
+    line.update(line_extra)
+    line["bench_wall_s"] = env.elapsed()
     if rank == 0:
         print(json.dumps(line), file=_JSON_OUT, flush=True)
-    form.close()
-    sp.close()
-    if comm is not None:
-        comm.close()
+    if env.comm is not None:
+        env.comm.close()
     ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
     return 0
 
 

@@ -520,7 +520,8 @@ class Comm:
     def __init__(self, ctx, nccl_id, rank, nranks):
         self.ctx, self.rank, self.nranks = ctx, rank, nranks
         self.h = vp()
-        idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
+        # nccl_id=None: peer-memory transport only (ranks that share one GPU; NCCL refuses those)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id)) if nccl_id is not None else None
         check(lib().b200pa_comm_create(ctx.h, idbuf, rank, nranks, C.byref(self.h)))
 
     @staticmethod

@@ -100,8 +100,14 @@ static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const do
    constexpr int NEB = (72 * 1024 / PER_E) < 1 ? 1 : ((72 * 1024 / PER_E) > 8 ? 8 : (72 * 1024 / PER_E));
    using C = DiagSfCfg<D1, Q1, NEB>;
    auto kern = k_diag_sf<D1, Q1, NEB>;
-   static bool attr_set = false;
-   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES); attr_set = true; }
+   // the opt-in is per device (a process may hold contexts on several): remembered per device, set-once races are benign
+   static std::atomic<bool> attr_set[MAX_DEVICES];
+   const int dev = ctx->device < MAX_DEVICES ? ctx->device : MAX_DEVICES - 1;
+   if (ctx->device >= MAX_DEVICES || !attr_set[dev].load(std::memory_order_acquire))
+   {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+      attr_set[dev].store(true, std::memory_order_release);
+   }
    DiagParams<D1, Q1> P;
    for (int i = 0; i < Q1 * D1; ++i)
    {
@@ -1096,7 +1102,7 @@ extern "C" int b200pa_form_mult_host(b200pa_form f, int constrained, const doubl
    if (form_apply(f, f->w1.as<double>(), f->w2.as<double>(), constrained != 0, nullptr, nullptr)) { return 1; }
    B200PA_CK(cudaMemcpyAsync(y_host, f->w2.p, b, cudaMemcpyDeviceToHost, ctx->stream));
    B200PA_CK(cudaStreamSynchronize(ctx->stream));
-   return 0;
+   return comm_px_check(f->comm, "form_mult_host");
 }
 
 extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
@@ -1215,8 +1221,9 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
 
    // the loop (:952-1027).  Scalars stay on the device; the host only polls `done` every few
    // iterations (kernels after convergence return immediately on the flag).
-   int *h_done = (int *)(ctx->h_result + 4);
-   *h_done = 0;
+   int *h_done = (int *)(ctx->h_result + 4); // [0] done, [1] peer-memory time-out word
+   h_done[0] = h_done[1] = 0;
+   const int *px_err = f->comm ? comm_px_err_ptr(f->comm) : nullptr;
    const int poll = 8;
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
@@ -1230,13 +1237,15 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
       if (it % poll == 0)
       {
          B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+         if (px_err) { B200PA_CK(cudaMemcpyAsync(h_done + 1, px_err, sizeof(int), cudaMemcpyDeviceToHost, s)); }
          B200PA_CK(cudaStreamSynchronize(s));
-         if (*h_done) { break; }
+         if (*h_done || h_done[1]) { break; }
       }
    }
    PcgState hs;
    B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
    B200PA_CK(cudaStreamSynchronize(s));
+   if (comm_px_check(f->comm, "pcg_solve")) { return 1; } // a timed-out peer wait: converged / final_norm would come from stale data
    B200PA_REQUIRE(!hs.nonfinite, "pcg_solve: non-finite (B r, r) or (A d, d) (MFEM_VERIFY(IsFinite(...)), linalg/solvers.cpp:897,932,969,1011)");
    B200PA_REQUIRE(hs.done, "pcg_solve: internal error (loop ended without a terminal state)");
    res->final_iter = hs.final_iter;
@@ -1429,8 +1438,9 @@ extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev,
    B200PA_CK(cudaMemcpyAsync(d, z, vb, cudaMemcpyDeviceToDevice, s));
    if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
    if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
-   int *h_done = (int *)(ctx->h_result + 4);
-   *h_done = 0;
+   int *h_done = (int *)(ctx->h_result + 4); // [0] done, [1] peer-memory time-out word
+   h_done[0] = h_done[1] = 0;
+   const int *px_err = f->comm ? comm_px_err_ptr(f->comm) : nullptr;
    const int poll = 4;
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
@@ -1443,13 +1453,15 @@ extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev,
       if (it % poll == 0)
       {
          B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+         if (px_err) { B200PA_CK(cudaMemcpyAsync(h_done + 1, px_err, sizeof(int), cudaMemcpyDeviceToHost, s)); }
          B200PA_CK(cudaStreamSynchronize(s));
-         if (*h_done) { break; }
+         if (*h_done || h_done[1]) { break; }
       }
    }
    PcgState hs;
    B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
    B200PA_CK(cudaStreamSynchronize(s));
+   if (comm_px_check(f->comm, "pcg_solve_chebyshev")) { return 1; }
    B200PA_REQUIRE(!hs.nonfinite, "pcg_solve_chebyshev: non-finite (B r, r) or (A d, d)");
    B200PA_REQUIRE(hs.done, "pcg_solve_chebyshev: internal error (loop ended without a terminal state)");
    res->final_iter = hs.final_iter;
@@ -1483,6 +1495,7 @@ extern "C" int b200pa_pcg_solve_host(b200pa_form f, const double *dinv_dev, cons
 extern "C" int b200pa_form_set_comm(b200pa_form f, b200pa_comm c)
 {
    B200PA_REQUIRE(f, "form is NULL");
+   if (c && comm_validate(c, f->sp->ndofs)) { return 1; }
    f->comm = c;
    return 0;
 }

@@ -201,7 +201,7 @@ __global__ void k_px_recv(int ns, const int *__restrict__ sh_ldof, const int *__
                           const unsigned char *__restrict__ own_mask, double *partials, unsigned int *ticket, double *dot_out)
 {
    if (done && *done) { return; }
-   if (threadIdx.x < P.n_nbr) { spin_until(my_flags + P.nbr_rank[threadIdx.x], epoch, err); }
+   if (threadIdx.x < P.n_nbr && !*(volatile int *)err) { spin_until(my_flags + P.nbr_rank[threadIdx.x], epoch, err); }
    __syncthreads();
    double acc = 0.0;
    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x)
@@ -249,7 +249,7 @@ __global__ void k_px_allreduce(double *vals, int n, const __grid_constant__ PxAl
       for (int k = 0; k < n; ++k) { dst[k] = vals[k]; }
       __threadfence_system();
       st_release_sys(P.flag[t] + P.rank, epoch);
-      spin_until(my_flags + t, epoch, err);
+      if (!*(volatile int *)err) { spin_until(my_flags + t, epoch, err); }
    }
    __syncthreads();
    if (t < n)
@@ -288,6 +288,19 @@ struct b200pa_comm_s
 
 using namespace b200pa;
 
+// closes the peer mappings and frees the mailbox (the peers must not be inside an exchange: collective call sites only)
+static void px_teardown(b200pa_comm c)
+{
+   c->px = false;
+   for (size_t r = 0; r < c->peer_mb.size(); ++r)
+   {
+      if (c->peer_mb[r] && (int)r != c->rank) { cudaIpcCloseMemHandle(c->peer_mb[r]); }
+   }
+   c->peer_mb.clear();
+   if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+   c->epoch_x = c->epoch_ar = 0;
+}
+
 extern "C" int b200pa_comm_unique_id(unsigned char id_out[128])
 {
    if (!g_nccl.load()) { return fail("b200pa: " + g_nccl.err); }
@@ -299,16 +312,21 @@ extern "C" int b200pa_comm_unique_id(unsigned char id_out[128])
 
 extern "C" int b200pa_comm_create(b200pa_ctx ctx, const unsigned char nccl_id[128], int rank, int nranks, b200pa_comm *out)
 {
-   B200PA_REQUIRE(ctx && nccl_id && out, "comm_create: NULL argument");
+   B200PA_REQUIRE(ctx && out, "comm_create: NULL argument");
    B200PA_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "comm_create: bad rank / nranks");
-   if (!g_nccl.load()) { return fail("b200pa: " + g_nccl.err); }
    B200PA_CK(cudaSetDevice(ctx->device));
    b200pa_comm c = new b200pa_comm_s;
    c->ctx = ctx; c->rank = rank; c->nranks = nranks;
-   ncclUniqueId id;
-   std::memcpy(id.internal, nccl_id, 128);
-   ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
-   if (r != ncclSuccess) { delete c; return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+   // nccl_id == NULL: no NCCL communicator - the peer-memory transport (b200pa_comm_px_prepare / _connect) is then the
+   // only one and every exchange before it is connected fails.  (Ranks that share one GPU need this: NCCL refuses them.)
+   if (nccl_id)
+   {
+      if (!g_nccl.load()) { delete c; return fail("b200pa: " + g_nccl.err); }
+      ncclUniqueId id;
+      std::memcpy(id.internal, nccl_id, 128);
+      ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
+      if (r != ncclSuccess) { delete c; return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+   }
    *out = c;
    return 0;
 }
@@ -318,11 +336,7 @@ extern "C" int b200pa_comm_destroy(b200pa_comm c)
    if (!c) { return 0; }
    cudaSetDevice(c->ctx->device);
    cudaStreamSynchronize(c->ctx->stream);
-   for (size_t r = 0; r < c->peer_mb.size(); ++r)
-   {
-      if (c->peer_mb[r] && (int)r != c->rank) { cudaIpcCloseMemHandle(c->peer_mb[r]); }
-   }
-   if (c->mailbox) { cudaFree(c->mailbox); }
+   px_teardown(c);
    c->send_nbr.release(); c->px_err.release(); c->px_ticket.release(); c->shared_mask.release();
    if (c->nccl) { g_nccl.CommDestroy(c->nccl); }
    for (DevBuf *b : {&c->send_ldof, &c->sendbuf, &c->recvbuf, &c->sh_ldof, &c->sh_off, &c->sh_src, &c->owner_mask}) { b->release(); }
@@ -402,6 +416,10 @@ extern "C" int b200pa_comm_set_tables(b200pa_comm c, int ndofs, int n_nbr, const
    B200PA_REQUIRE(c, "comm is NULL");
    b200pa_ctx ctx = c->ctx;
    B200PA_CK(cudaSetDevice(ctx->device));
+   // new tables invalidate the peer-memory set-up (mailbox size and the peers' offsets came from the old ones):
+   // back to the NCCL transport until b200pa_comm_px_prepare / _connect run again (collectively)
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   px_teardown(c);
    int ns = 0;
    if (b200pa_comm_build_tables(c->rank, ndofs, n_nbr, nbr_rank, shared_offsets, shared_ldofs, &ns, nullptr, nullptr, nullptr, nullptr)) { return 1; }
    const int n_send = n_nbr ? shared_offsets[n_nbr] : 0;
@@ -469,6 +487,7 @@ static int exchange(b200pa_comm c, double *y, int owner_only, const int *done, c
       B200PA_LAUNCHED();
       return 0;
    }
+   B200PA_REQUIRE(c->nccl, "shared-dof exchange: this communicator was created without NCCL and its peer-memory path is not connected");
    k_pack<<<g, bs, 0, ctx->stream>>>(c->n_send, c->send_ldof.as<int>(), y, c->sendbuf.as<double>(), done);
    B200PA_LAUNCHED();
    NCCL_CK(g_nccl.GroupStart());
@@ -498,6 +517,23 @@ int comm_exchange_sum_apply(b200pa_comm c, double *y, const int *done, const dou
    return exchange(c, y, 0, done, ep);
 }
 int comm_exchange_owner(b200pa_comm c, double *x) { return exchange(c, x, 1, nullptr); }
+const int *comm_px_err_ptr(b200pa_comm c) { return (c && c->px) ? c->px_err.as<int>() : nullptr; }
+int comm_px_check(b200pa_comm c, const char *where)
+{
+   if (!c || !c->px) { return 0; }
+   if (b200pa_comm_px_error(c))
+   {
+      return fail(std::string(where) + ": a peer-memory wait timed out (a rank did not take part in the shared-dof exchange / "
+                  "all-reduce); the result is invalid");
+   }
+   return 0;
+}
+int comm_validate(b200pa_comm c, int ndofs)
+{
+   B200PA_REQUIRE(c->nranks == 1 || c->owner_mask.p, "form_set_comm: the communicator has no neighbour tables (call b200pa_comm_set_tables first)");
+   B200PA_REQUIRE(c->nranks == 1 || c->ndofs == ndofs, "form_set_comm: the communicator's tables were built for a different number of L-dofs");
+   return 0;
+}
 
 // all-reduce of one PCG dot + the scalar step that follows it, in one launch (peer-memory path only;
 // returns 0 and does nothing when that path is off, the caller then uses the NCCL all-reduce + a scalar kernel)
@@ -529,6 +565,7 @@ int comm_allreduce_sum_dev(b200pa_comm c, double *vals, int n)
       B200PA_LAUNCHED();
       return 0;
    }
+   B200PA_REQUIRE(c->nccl, "all-reduce: this communicator was created without NCCL and its peer-memory path is not connected (or n > 4)");
    NCCL_CK(g_nccl.AllReduce(vals, vals, (size_t)n, ncclFloat64, ncclSum, c->nccl, c->ctx->stream));
    return 0;
 }
@@ -569,13 +606,22 @@ extern "C" int b200pa_comm_px_connect(b200pa_comm c, const unsigned char *handle
    B200PA_REQUIRE(c->mailbox, "comm_px_connect: call b200pa_comm_px_prepare first");
    b200pa_ctx ctx = c->ctx;
    B200PA_CK(cudaSetDevice(ctx->device));
+   B200PA_REQUIRE(!c->px && c->peer_mb.empty(), "comm_px_connect: already connected (b200pa_comm_set_tables resets the peer path)");
    c->peer_mb.assign(c->nranks, nullptr);
    for (int r = 0; r < c->nranks; ++r)
    {
       if (r == c->rank) { c->peer_mb[r] = c->mailbox; continue; }
       cudaIpcMemHandle_t h;
       std::memcpy(&h, handles + 64 * (size_t)r, 64);
-      B200PA_CK(cudaIpcOpenMemHandle(&c->peer_mb[r], h, cudaIpcMemLazyEnablePeerAccess));
+      const cudaError_t e = cudaIpcOpenMemHandle(&c->peer_mb[r], h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+      {
+         c->peer_mb[r] = nullptr;
+         for (int q = 0; q < r; ++q) { if (q != c->rank && c->peer_mb[q]) { cudaIpcCloseMemHandle(c->peer_mb[q]); } }
+         c->peer_mb.clear();
+         cudaGetLastError();
+         return fail(std::string("comm_px_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+      }
    }
    // layout is the same function of (nranks, n_send) on every rank; only the recv offset depends on the peer's n_send,
    // and that offset (mb_recv) depends on nranks only

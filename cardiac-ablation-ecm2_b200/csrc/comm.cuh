@@ -18,4 +18,10 @@ bool comm_px(b200pa_comm c);
 const unsigned char *comm_shared_mask(b200pa_comm c);
 int comm_exchange_sum_apply(b200pa_comm c, double *yL_dev, const int *done, const double *x_dev, const unsigned char *ess_mask,
                             double *dot_out);
+// peer-memory path: device error word raised by a timed-out wait (nullptr when the path is off) and the check the
+// host-synchronous entry points run after their final stream synchronisation (nonzero + message when it was raised)
+const int *comm_px_err_ptr(b200pa_comm c);
+int comm_px_check(b200pa_comm c, const char *where);
+// tables set and sized for an L-vector of `ndofs` entries (b200pa_form_set_comm)
+int comm_validate(b200pa_comm c, int ndofs);
 } // namespace b200pa

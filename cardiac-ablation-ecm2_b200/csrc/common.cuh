@@ -79,6 +79,7 @@ struct b200pa_ctx_s
 namespace b200pa
 {
 constexpr int MAX_RED_BLOCKS = 2048;
+constexpr int MAX_DEVICES = 64; // per-device caches of kernel attributes / occupancy
 
 // Returns a device pointer for `src` (host or device).  Host data is copied into `buf`.
 int to_device(b200pa_ctx ctx, const void *src, size_t bytes, DevBuf &buf, const void **out);

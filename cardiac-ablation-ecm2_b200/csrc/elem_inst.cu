@@ -1,5 +1,8 @@
 // One (D1D,Q1D) instantiation set of the element kernel.  Compiled six times:
 //   nvcc ... -DB200PA_D=3 -DB200PA_Q=4 -c elem_inst.cu -o elem_3_4.o
+#include <atomic>
+
+#include "common.cuh"
 #include "elem_launch.cuh"
 #include "pa_element_kernel.cuh"
 #include "pa_apply_kernel.cuh"
@@ -14,6 +17,32 @@ namespace b200pa
 namespace
 {
 constexpr int D = B200PA_D, Q = B200PA_Q;
+
+// Dynamic shared-memory opt-in + resident CTAs per SM of one kernel instantiation.  Both are PER DEVICE (a process
+// may hold contexts on several GPUs), so they are cached per (instantiation, device); the cache entries are atomics and a
+// set-once race between threads only repeats the same two idempotent runtime calls.
+// Tag: a type unique to the kernel instantiation (kernels of one signature share the function-pointer type K).
+template <typename Tag, typename K>
+int kernel_setup(K kern, int threads, size_t smem, int *blocks_per_sm)
+{
+   static std::atomic<int> cache[MAX_DEVICES];
+   int dev = 0;
+   cudaError_t e = cudaGetDevice(&dev);
+   if (e != cudaSuccess) { return (int)e; }
+   const bool cached = dev >= 0 && dev < MAX_DEVICES;
+   int n = cached ? cache[dev].load(std::memory_order_acquire) : 0;
+   if (n == 0)
+   {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { return (int)e; }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+      if (e != cudaSuccess) { return (int)e; }
+      n = n > 0 ? n : 1;
+      if (cached) { cache[dev].store(n, std::memory_order_release); }
+   }
+   *blocks_per_sm = n;
+   return 0;
+}
 
 template <int DD, int QQ>
 void fill_params(ElemParams<DD, QQ> &P, const ElemArgs &a)
@@ -33,15 +62,11 @@ int run(const ElemArgs &a, int num_sms, cudaStream_t stream)
 {
    using L = ElemLayout<D, Q>;
    auto kern = pa_element_kernel<D, Q, DIFF, MASS, INMODE, OUTMODE, QOP>;
-   static int blocks_per_sm = 0; // per instantiation
-   if (blocks_per_sm == 0)
+   int blocks_per_sm = 0;
    {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES);
-      if (e != cudaSuccess) { return (int)e; }
-      int n = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, L::NT, L::SMEM_BYTES);
-      if (e != cudaSuccess) { return (int)e; }
-      blocks_per_sm = n > 0 ? n : 1;
+      struct ThisKernel {}; // local to this instantiation of run<>
+      const int e = kernel_setup<ThisKernel>(kern, L::NT, L::SMEM_BYTES, &blocks_per_sm);
+      if (e) { return e; }
    }
    ElemParams<D, Q> P;
    fill_params(P, a);
@@ -58,15 +83,11 @@ int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
 {
    using C = ApplyCfg<D, Q, AFF>;
    auto kern = pa_apply_kernel<D, Q, DIFF, MASS, AFF>;
-   static int blocks_per_sm = 0;
-   if (blocks_per_sm == 0)
+   int blocks_per_sm = 0;
    {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-      if (e != cudaSuccess) { return (int)e; }
-      int n = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::NT, C::SMEM_BYTES);
-      if (e != cudaSuccess) { return (int)e; }
-      blocks_per_sm = n > 0 ? n : 1;
+      struct ThisKernel {}; // local to this instantiation of run_fused<>
+      const int e = kernel_setup<ThisKernel>(kern, C::NT, C::SMEM_BYTES, &blocks_per_sm);
+      if (e) { return e; }
    }
    if (a.NE <= 0) { return 0; }
    // TMA bulk copies need 16-byte aligned sources (cudaMalloc gives 256)

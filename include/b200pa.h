@@ -253,7 +253,9 @@ int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev, int order,
  * that dots count.  P^T followed by P collapses into one symmetric neighbour exchange whose
  * per-dof summation order is ascending rank on every rank (bit-identical copies).
  * nccl_id: the 128-byte ncclUniqueId created on rank 0 (b200pa_comm_unique_id) and broadcast
- * by the host application (torch.distributed / MPI). */
+ * by the host application (torch.distributed / MPI).  nccl_id == NULL creates a communicator
+ * WITHOUT NCCL: the peer-memory path below is then its only transport (every exchange before
+ * b200pa_comm_px_connect fails); this is what ranks sharing one GPU use - NCCL refuses them. */
 int b200pa_comm_unique_id(unsigned char id_out[128]);
 int b200pa_comm_create(b200pa_ctx ctx, const unsigned char nccl_id[128], int rank, int nranks, b200pa_comm *out);
 int b200pa_comm_destroy(b200pa_comm c);
@@ -278,13 +280,19 @@ const unsigned char *b200pa_comm_owner_mask(b200pa_comm c);   /* device pointer 
  *   3. every rank: b200pa_comm_px_connect(handles[nranks*64], remote_off[n_nbr], remote_nsend[n_nbr]) where,
  *      for neighbour k = rank q, remote_off[k] = q's shared_offsets[index of this rank in q's nbr_rank] and
  *      remote_nsend[k] = q's shared_offsets[q's n_nbr]
- * Waits are bounded; b200pa_comm_px_error() returns nonzero (and clears it) if one timed out. */
+ * Waits are bounded: a time-out raises a device error word, the kernels that follow skip their waits, and the
+ * host-synchronous entry points (b200pa_pcg_solve*, b200pa_form_mult_host) fail with a message instead of
+ * returning results computed from stale mailbox data; after the asynchronous ones (b200pa_form_mult, ...)
+ * b200pa_comm_px_error() returns nonzero (and clears the word) if a wait timed out since the last query.
+ * b200pa_comm_set_tables on a connected communicator tears the peer path down (mailbox sizes and peer
+ * offsets came from the old tables): prepare / connect again, collectively. */
 int b200pa_comm_px_prepare(b200pa_comm c, unsigned char handle_out[64]);
 int b200pa_comm_px_connect(b200pa_comm c, const unsigned char *handles, const long long *remote_off,
                            const long long *remote_nsend);
 int b200pa_comm_px_error(b200pa_comm c);
 int b200pa_comm_px_enabled(b200pa_comm c);
 int b200pa_comm_px_disable(b200pa_comm c);   /* back to NCCL; must be called on every rank */
+/* fails unless c's tables are set (nranks > 1) and were built for the form's number of L-dofs */
 int b200pa_form_set_comm(b200pa_form f, b200pa_comm c);
 /* (P P^T) y: every copy of a shared dof <- sum of all copies.  (P R) x: <- the owner's value. */
 int b200pa_comm_exchange_sum(b200pa_comm c, double *yL_dev);
