@@ -31,7 +31,7 @@ class PcgResult(C.Structure):
 # every symbol include/b200pa.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = """
 b200pa_version b200pa_last_error b200pa_launch_count
-b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset
+b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset b200pa_copy
 b200pa_restrict_mult b200pa_restrict_mult_transpose b200pa_diffusion_setup b200pa_mass_setup
 b200pa_diffusion_apply b200pa_mass_apply b200pa_diffusion_diag b200pa_mass_diag b200pa_qvalues
 b200pa_qphysgrad b200pa_domain_lf b200pa_dot b200pa_add b200pa_jacobi_setup b200pa_jacobi_mult
@@ -43,6 +43,7 @@ b200pa_space_qvalues b200pa_space_qphysgrad b200pa_space_coeff_linear b200pa_spa
 b200pa_form_create b200pa_form_destroy b200pa_form_assemble_diffusion b200pa_form_assemble_mass
 b200pa_form_set_pa_data b200pa_form_pa_diff b200pa_form_pa_mass b200pa_form_set_essential b200pa_form_mult
 b200pa_form_constrained_mult b200pa_form_mult_phases b200pa_form_mult_host b200pa_form_assemble_diagonal b200pa_form_eliminate_rhs
+b200pa_form_assemble_diffusion_with_diagonal b200pa_space_set_attributes b200pa_form_set_markers
 b200pa_pcg_solve b200pa_pcg_solve_host
 b200pa_chebyshev_coeffs b200pa_power_method b200pa_chebyshev_mult b200pa_pcg_solve_chebyshev
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
@@ -341,6 +342,12 @@ class Space:
         detJ = _f64(detJ) if isinstance(detJ, np.ndarray) else detJ
         check(lib().b200pa_space_set_geometry(self.h, _ptr(W), _ptr(J), _ptr(detJ)))
 
+    def set_attributes(self, attr):
+        """Mesh::GetAttribute(e) for every element (needed by integrator markers)"""
+        a = _i32(attr)
+        assert len(a) == self.ne
+        check(lib().b200pa_space_set_attributes(self.h, _ptr(a)))
+
     @property
     def affine(self):
         return lib().b200pa_space_is_affine(self.h) == 1
@@ -436,6 +443,14 @@ class Form:
         self._keep = [pa_diff, pa_mass]
         check(lib().b200pa_form_set_pa_data(self.h, _ptr(pa_diff), _ptr(pa_mass)))
 
+    def set_markers(self, which, marker):
+        """AddDomainIntegrator(bfi, elem_marker): which = 0 diffusion / 1 mass; marker[a-1] != 0 <=> acts on attribute a"""
+        if marker is None:
+            check(lib().b200pa_form_set_markers(self.h, int(which), 0, None))
+            return
+        mk = _i32(marker)
+        check(lib().b200pa_form_set_markers(self.h, int(which), len(mk), _ptr(mk)))
+
     def set_essential(self, ess):
         ess = _i32(ess if ess is not None else np.zeros(0, np.int32))
         self.n_ess = len(ess)
@@ -468,6 +483,18 @@ class Form:
         diag = self.ctx.empty(self.sp.ndofs) if diag is None else diag
         check(lib().b200pa_form_assemble_diagonal(self.h, _ptr(diag)))
         return diag
+
+    def assemble_diffusion_with_diagonal(self, Cq, diag=None):
+        """AssemblePA of the diffusion integrator + the form's diagonal in one pass over the q-points"""
+        diag = self.ctx.empty(self.sp.ndofs) if diag is None else diag
+        Cq = _f64(Cq) if isinstance(Cq, np.ndarray) else Cq
+        n = Cq.size if isinstance(Cq, np.ndarray) else Cq.numel()
+        check(lib().b200pa_form_assemble_diffusion_with_diagonal(self.h, _ptr(Cq), C.c_longlong(n), _ptr(diag)))
+        return diag
+
+    def jacobi_from(self, diag, damping=1.0):
+        """OperatorJacobiSmoother from an already assembled diagonal"""
+        return self.ctx.jacobi_setup(diag, self.ess_dev, damping)
 
     def eliminate_rhs(self, x, b):
         check(lib().b200pa_form_eliminate_rhs(self.h, _ptr(x), _ptr(b)))

@@ -91,49 +91,70 @@ static int run_element(b200pa_ctx ctx, int d1d, int q1d, int variant, const Elem
    return 0;
 }
 
-template <int D1, int Q1>
-static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const double *pd, const double *pm,
-                        const double *geo, double *dE)
+// what the diagonal kernel reads and writes (see k_diag_sf)
+struct DiagArgs
 {
-   // elements per CTA: q-data staging + the two contraction tensors within ~72 KB (3 CTAs per SM)
-   constexpr int PER_E = (7 * Q1 * Q1 * Q1 + 7 * (Q1 * Q1 * D1 + Q1 * D1 * D1)) * 8;
-   constexpr int NEB = (72 * 1024 / PER_E) < 1 ? 1 : ((72 * 1024 / PER_E) > 8 ? 8 : (72 * 1024 / PER_E));
-   using C = DiagSfCfg<D1, Q1, NEB>;
-   auto kern = k_diag_sf<D1, Q1, NEB>;
+   const double *pd = nullptr, *pm = nullptr, *geo = nullptr;
+   double *out = nullptr;          // E-vector (+=) when slot == nullptr, else the slot-order scratch (=)
+   const int *slot = nullptr;
+   // fused set-up (affine meshes): pd is the raw coefficient, the kernel writes the integrator's q-data
+   const double *W = nullptr;
+   double *pa_out = nullptr;
+   int pa_out_ncomp = 0, const_c = 0;
+   const unsigned char *diff_off = nullptr;
+};
+
+template <int D1, int Q1, bool SLOT, bool FUSED>
+static void launch_diag_t(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const DiagArgs &a)
+{
+   using C = DiagSfCfg<D1, Q1>;
+   auto kern = k_diag_sf<D1, Q1, SLOT, FUSED>;
    // the opt-in is per device (a process may hold contexts on several): remembered per device, set-once races are benign
-   static std::atomic<bool> attr_set[MAX_DEVICES];
-   const int dev = ctx->device < MAX_DEVICES ? ctx->device : MAX_DEVICES - 1;
-   if (ctx->device >= MAX_DEVICES || !attr_set[dev].load(std::memory_order_acquire))
+   static std::atomic<int> per_sm[MAX_DEVICES];
+   const int dev = ctx->device;
+   int nb = (dev < MAX_DEVICES) ? per_sm[dev].load(std::memory_order_acquire) : 0;
+   if (nb == 0)
    {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-      attr_set[dev].store(true, std::memory_order_release);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NT, C::SMEM_BYTES) != cudaSuccess || nb < 1) { nb = 1; }
+      if (dev < MAX_DEVICES) { per_sm[dev].store(nb, std::memory_order_release); }
    }
    DiagParams<D1, Q1> P;
    for (int i = 0; i < Q1 * D1; ++i)
    {
       P.M[0][i] = hB[i] * hB[i]; P.M[1][i] = hB[i] * hG[i]; P.M[2][i] = hG[i] * hG[i];
    }
-   P.NE = ne; P.pa_diff = pd; P.pa_mass = pm; P.geo = geo; P.dE = dE;
-   const long long nbatch = (ne + NEB - 1) / NEB;
-   const long long cap = (long long)ctx->num_sms * 3;
-   kern<<<(int)(nbatch < cap ? nbatch : cap), 128, C::SMEM_BYTES, ctx->stream>>>(P);
+   P.NE = ne; P.pa_diff = a.pd; P.pa_mass = a.pm; P.geo = a.geo; P.out = a.out; P.slot = a.slot;
+   P.W = a.W; P.pa_out = a.pa_out; P.pa_out_ncomp = a.pa_out_ncomp; P.const_c = a.const_c; P.diff_off = a.diff_off;
+   const long long nbatch = (ne + C::NEB - 1) / C::NEB;
+   const long long cap = (long long)ctx->num_sms * nb;
+   kern<<<(int)(nbatch < cap ? nbatch : cap), C::NT, C::SMEM_BYTES, ctx->stream>>>(P);
+}
+
+template <int D1, int Q1>
+static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const DiagArgs &a)
+{
+   if (a.pa_out) { launch_diag_t<D1, Q1, true, true>(ctx, ne, hB, hG, a); }   // fused set-up always writes the slot layout
+   else if (a.slot) { launch_diag_t<D1, Q1, true, false>(ctx, ne, hB, hG, a); }
+   else { launch_diag_t<D1, Q1, false, false>(ctx, ne, hB, hG, a); }
 }
 
 // hB, hG: HOST copies of the 1-D basis tables
-static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *hB, const double *hG,
-                    const double *pd, const double *pm, double *dE, const double *geo = nullptr)
+static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double *hB, const double *hG, const DiagArgs &a)
 {
    B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
    if (ne <= 0) { return 0; }
-   B200PA_REQUIRE(((((unsigned long long)pd) | ((unsigned long long)pm)) & 15ull) == 0, "pa_data must be 16-byte aligned (TMA bulk copies)");
+   const unsigned long long al = a.pa_out ? ((unsigned long long)a.pm | (a.const_c ? 0ull : (unsigned long long)a.pd)) : ((unsigned long long)a.pd | (unsigned long long)a.pm);
+   B200PA_REQUIRE((al & 15ull) == 0, "pa_data must be 16-byte aligned (TMA bulk copies)");
+   B200PA_REQUIRE(!a.pa_out || (a.slot && a.geo && a.W), "fused set-up + diagonal: slot layout, element tensors and weights are required");
    switch (d1d)
    {
-      case 2: launch_diag<2, 3>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
-      case 3: launch_diag<3, 4>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
-      case 4: launch_diag<4, 5>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
-      case 5: launch_diag<5, 6>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
-      case 6: launch_diag<6, 7>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
-      case 7: launch_diag<7, 8>(ctx, ne, hB, hG, pd, pm, geo, dE); break;
+      case 2: launch_diag<2, 3>(ctx, ne, hB, hG, a); break;
+      case 3: launch_diag<3, 4>(ctx, ne, hB, hG, a); break;
+      case 4: launch_diag<4, 5>(ctx, ne, hB, hG, a); break;
+      case 5: launch_diag<5, 6>(ctx, ne, hB, hG, a); break;
+      case 6: launch_diag<6, 7>(ctx, ne, hB, hG, a); break;
+      case 7: launch_diag<7, 8>(ctx, ne, hB, hG, a); break;
    }
    B200PA_LAUNCHED();
    return 0;
@@ -158,9 +179,10 @@ struct b200pa_space_s
    std::vector<double> hxi;
    // factorised diffusion q-data (affine elements only): adj(J)adj(J)^T/det J per element; affine = every element
    // is a parallelepiped to 1e-13 of its edge lengths (decided on the device by k_affine_geometry)
-   DevBuf geo6;
+   DevBuf geo6, jinv9; // jinv9: rows of J^{-T} per element (q-point gradients on affine meshes)
    bool affine = false;
    DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
+   DevBuf attr;     // element attributes (Mesh::GetAttribute), int32[NE]; only needed by integrator markers
 };
 
 struct b200pa_form_s
@@ -176,6 +198,9 @@ struct b200pa_form_s
    DevBuf r, d, z, q;   // PCG work vectors (linalg/solvers.cpp:855-867); q = A d when the preconditioner needs z for itself
    DevBuf state, norms; // device-resident PCG scalars
    b200pa_comm comm = nullptr;
+   // element-attribute markers of the two domain integrators (0: diffusion, 1: mass): on[w][e] = integrator w acts on e
+   DevBuf on[2], diff_off;
+   bool has_marker[2] = {false, false};
 };
 
 // ------------------------------------------------------------------------ misc
@@ -257,6 +282,13 @@ extern "C" int b200pa_memset(b200pa_ctx c, void *p, int value, size_t bytes)
    B200PA_REQUIRE(c && (p || !bytes), "memset: NULL argument");
    B200PA_CK(cudaSetDevice(c->device));
    if (bytes) { B200PA_CK(cudaMemsetAsync(p, value, bytes, c->stream)); }
+   return 0;
+}
+extern "C" int b200pa_copy(b200pa_ctx c, long long n, const double *src_dev, double *dst_dev)
+{
+   B200PA_REQUIRE(c && (n == 0 || (src_dev && dst_dev)), "copy: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   if (n > 0) { B200PA_CK(cudaMemcpyAsync(dst_dev, src_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream)); }
    return 0;
 }
 extern "C" int b200pa_ctx_upload(b200pa_ctx c, void *dst_dev, const void *src_host, size_t bytes)
@@ -370,7 +402,9 @@ static int diag_common(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B
    B200PA_REQUIRE(supported(d1d, q1d), "unsupported (D1D,Q1D)");
    HostBG h;
    if (h.get(ctx, d1d, q1d, B, G)) { return 1; }
-   return run_diag(ctx, d1d, q1d, ne, h.B.data(), h.G.data(), pd, pm, dE);
+   DiagArgs a;
+   a.pd = pd; a.pm = pm; a.out = dE; // AssembleDiagonalPA adds into the E-vector (fem/integ/bilininteg_diffusion_pa.cpp:22-37)
+   return run_diag(ctx, d1d, q1d, ne, h.B.data(), h.G.data(), a);
 }
 
 extern "C" int b200pa_diffusion_diag(b200pa_ctx ctx, int ne, int d1d, int q1d, const double *B, const double *G,
@@ -573,7 +607,7 @@ extern "C" int b200pa_space_destroy(b200pa_space sp)
    if (!sp) { return 0; }
    cudaSetDevice(sp->ctx->device);
    cudaStreamSynchronize(sp->ctx->stream);
-   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->scratchE})
+   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->jinv9, &sp->scratchE, &sp->attr})
    {
       b->release();
    }
@@ -613,10 +647,11 @@ extern "C" int b200pa_space_set_geometry(b200pa_space sp, const double *W_any, c
       if (sp->ne > 0)
       {
          b200pa_ctx ctx = sp->ctx;
-         if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne)) { return 1; }
+         if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne) || alloc(sp->jinv9, sizeof(double) * 9 * (size_t)sp->ne)) { return 1; }
          int *dflag = (int *)(ctx->d_ticket + 3);
          B200PA_CK(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
-         k_affine_from_J<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>((long long)q3, sp->ne, sp->J.as<double>(), 1e-13, sp->geo6.as<double>(), dflag);
+         k_affine_from_J<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>((long long)q3, sp->ne, sp->J.as<double>(), 1e-13, sp->geo6.as<double>(),
+                                                                      sp->jinv9.as<double>(), dflag);
          B200PA_LAUNCHED();
          int flag = 1;
          B200PA_CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -679,11 +714,11 @@ extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double
    sp->affine = false;
    if (sp->ne > 0)
    {
-      if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne)) { return 1; }
+      if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne) || alloc(sp->jinv9, sizeof(double) * 9 * (size_t)sp->ne)) { return 1; }
       int *dflag = (int *)(ctx->d_ticket + 3);
       B200PA_CK(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
       k_affine_geometry<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>(sp->ne, sp->vtx.as<double>(), sp->ev.as<int>(), 1e-13,
-                                                                    sp->geo6.as<double>(), dflag);
+                                                                    sp->geo6.as<double>(), sp->jinv9.as<double>(), dflag);
       B200PA_LAUNCHED();
       int flag = 1;
       B200PA_CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -738,6 +773,8 @@ static ElemArgs space_args(b200pa_space sp)
 // stored Jacobians if the space has them, else the vertices they are rebuilt from
 static void geometry_args(b200pa_space sp, ElemArgs &a)
 {
+   // a mesh of affine elements: one inverse Jacobian per element (no 72 B per q-point of J, no rebuild from the vertices)
+   if (sp->affine && sp->jinv9.p) { a.jinv = sp->jinv9.as<double>(); }
    if (sp->J.p) { a.J = sp->J.as<double>(); }
    else { a.vtx = sp->vtx.as<double>(); a.ev = sp->ev.as<int>(); a.xi = sp->hxi.data(); }
 }
@@ -823,11 +860,70 @@ extern "C" int b200pa_form_destroy(b200pa_form f)
    if (!f) { return 0; }
    cudaSetDevice(f->sp->ctx->device);
    cudaStreamSynchronize(f->sp->ctx->stream);
-   for (DevBuf *b : {&f->pa_diff, &f->pa_mass, &f->ess, &f->ess_mask, &f->cgmap, &f->w1, &f->w2, &f->r, &f->d, &f->z, &f->q, &f->state, &f->norms})
+   for (DevBuf *b : {&f->pa_diff, &f->pa_mass, &f->ess, &f->ess_mask, &f->cgmap, &f->w1, &f->w2, &f->r, &f->d, &f->z, &f->q, &f->state, &f->norms, &f->on[0], &f->on[1], &f->diff_off})
    {
       b->release();
    }
    delete f;
+   return 0;
+}
+
+// after AssemblePA of integrator `which`: q-data of the elements its marker excludes := 0
+static int apply_marker(b200pa_form f, int which)
+{
+   if (!f->has_marker[which]) { return 0; }
+   b200pa_space sp = f->sp;
+   if (sp->ne <= 0) { return 0; }
+   const long long q3 = (long long)sp->q1d * sp->q1d * sp->q1d;
+   double *pa = which == 0 ? f->pa_diff.as<double>() : f->pa_mass.as<double>();
+   const long long per = which == 0 ? (f->factorised ? q3 : 6 * q3) : q3;
+   k_zero_unmarked<<<grid1d(sp->ctx, sp->ne * per), 256, 0, sp->ctx->stream>>>(sp->ne, per, f->on[which].as<unsigned char>(), pa);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+extern "C" int b200pa_space_set_attributes(b200pa_space sp, const int *attr_any)
+{
+   B200PA_REQUIRE(sp && attr_any, "space_set_attributes: NULL argument");
+   NEED_CTX(sp->ctx);
+   if (alloc(sp->attr, sizeof(int) * (size_t)std::max(sp->ne, 1))) { return 1; }
+   if (sp->ne > 0)
+   {
+      B200PA_CK(cudaMemcpyAsync(sp->attr.p, attr_any, sizeof(int) * (size_t)sp->ne,
+                                is_device_ptr(attr_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sp->ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(sp->ctx->stream));
+   }
+   return 0;
+}
+
+extern "C" int b200pa_form_set_markers(b200pa_form f, int which, int n_attr, const int *marker_host)
+{
+   B200PA_REQUIRE(f && (which == 0 || which == 1), "form_set_markers: which must be 0 (diffusion) or 1 (mass)");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   if (!marker_host) { f->has_marker[which] = false; f->on[which].release(); return 0; }
+   B200PA_REQUIRE(n_attr >= 1, "form_set_markers: the marker array is empty");
+   B200PA_REQUIRE(sp->attr.p, "form_set_markers: the space has no element attributes (call b200pa_space_set_attributes)");
+   DevBuf dm;
+   if (alloc(dm, sizeof(int) * (size_t)n_attr) || alloc(f->on[which], (size_t)std::max(sp->ne, 1))) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(dm.p, marker_host, sizeof(int) * (size_t)n_attr, cudaMemcpyHostToDevice, ctx->stream));
+   int *flag = (int *)(ctx->d_ticket + 2);
+   B200PA_CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+   if (sp->ne > 0)
+   {
+      k_marker_mask<<<grid1d(ctx, sp->ne), 256, 0, ctx->stream>>>(sp->ne, sp->attr.as<int>(), n_attr, dm.as<int>(), f->on[which].as<unsigned char>(), flag);
+      B200PA_LAUNCHED();
+   }
+   int h = 0;
+   B200PA_CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   dm.release();
+   B200PA_REQUIRE(h == 0, "form_set_markers: an element attribute exceeds the size of the marker array");
+   f->has_marker[which] = true;
+   // q-data assembled before the marker was set is masked now (zeroing is idempotent); clearing a marker needs a re-assembly
+   if (which == 0 && f->has_diff && f->pa_diff.owned) { return apply_marker(f, 0); }
+   if (which == 1 && f->has_mass && f->pa_mass.owned) { return apply_marker(f, 1); }
    return 0;
 }
 
@@ -860,7 +956,7 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
       if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
       f->has_diff = (rcf == 0);
       f->factorised = f->has_diff;
-      return rcf;
+      return rcf ? rcf : apply_marker(f, 0);
    }
    if (f->factorised) { f->pa_diff.release(); f->factorised = false; }
    int rc = alloc(f->pa_diff, sizeof(double) * 6 * (size_t)std::max<long long>(sp->nQ, 1));
@@ -886,7 +982,7 @@ extern "C" int b200pa_form_assemble_diffusion(b200pa_form f, const double *C_any
    }
    if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
    f->has_diff = (rc == 0);
-   return rc;
+   return rc ? rc : apply_marker(f, 0);
 }
 
 extern "C" int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, long long nc)
@@ -905,12 +1001,14 @@ extern "C" int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, lon
    if (!rc) { rc = b200pa_mass_setup(sp->ctx, sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(), sp->detJ.as<double>(), (const double *)dC, nc, f->pa_mass.as<double>()); }
    if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
    f->has_mass = (rc == 0);
-   return rc;
+   return rc ? rc : apply_marker(f, 1);
 }
 
 extern "C" int b200pa_form_set_pa_data(b200pa_form f, const double *pa_diff_dev, const double *pa_mass_dev)
 {
    B200PA_REQUIRE(f, "form is NULL");
+   B200PA_REQUIRE(!f->has_marker[0] && !f->has_marker[1], "set_pa_data: integrator markers need q-data assembled by the library "
+                                                        "(they zero the q-data of the excluded elements)");
    f->pa_diff.release(); f->pa_mass.release();
    f->factorised = false;
    f->has_diff = pa_diff_dev != nullptr; f->has_mass = pa_mass_dev != nullptr;
@@ -1105,6 +1203,41 @@ extern "C" int b200pa_form_mult_host(b200pa_form f, int constrained, const doubl
    return comm_px_check(f->comm, "form_mult_host");
 }
 
+// L-vector diagonal from the slot-order scratch the diagonal kernel wrote: ElementRestriction::AbsMultTranspose
+// (fem/restriction.cpp:196-221 - the plain sum for H1, whose gather map has no sign flips) as a contiguous
+// segmented reduction, then ParBilinearForm::AssembleDiagonal's P^T (fem/pbilinearform.cpp:293-330)
+static int finish_diagonal(b200pa_form f, double *diag_dev)
+{
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   if (sp->ndofs > 0)
+   {
+      k_segment_sum<false, false, false><<<grid1d(ctx, sp->ndofs), 256, 0, ctx->stream>>>(
+         sp->ndofs, sp->offsets.as<int>(), sp->scratchE.as<double>(), diag_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      B200PA_LAUNCHED();
+   }
+   if (f->comm) { return comm_exchange_sum(f->comm, diag_dev, nullptr); }
+   return 0;
+}
+
+// PABilinearFormExtension::AssembleDiagonal with markers (fem/bilinearform_ext.cpp:374-399): after EVERY integrator the
+// reference zeroes the accumulated element diagonal of the elements that integrator's marker excludes - what earlier
+// integrators added there goes too.  The form's integrator order is diffusion, then mass: elements the MASS marker excludes
+// end up with a zero element diagonal, diffusion part included.  (An excluded element's own q-data is zero already.)
+static const unsigned char *diag_diff_off(b200pa_form f)
+{
+   if (!(f->has_marker[1] && f->has_mass && f->has_diff)) { return nullptr; }
+   // on[1][e] == 0 <=> excluded by the mass marker; the kernel wants "off" = 1 there: kept as a second byte array
+   b200pa_space sp = f->sp;
+   if (alloc(f->diff_off, (size_t)std::max(sp->ne, 1))) { return nullptr; }
+   if (sp->ne > 0)
+   {
+      k_invert_mask<<<grid1d(sp->ctx, sp->ne), 256, 0, sp->ctx->stream>>>(sp->ne, f->on[1].as<unsigned char>(), f->diff_off.as<unsigned char>());
+      g_launches++;
+   }
+   return f->diff_off.as<unsigned char>();
+}
+
 extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
 {
    B200PA_REQUIRE(f && diag_dev, "form_assemble_diagonal: NULL argument");
@@ -1112,22 +1245,65 @@ extern "C" int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev)
    b200pa_ctx ctx = sp->ctx;
    NEED_CTX(ctx);
    B200PA_REQUIRE(f->has_diff || f->has_mass, "form has no assembled integrator");
-   // fem/bilinearform_ext.cpp:401-423: localY = 0; every integrator adds; AbsMultTranspose
-   B200PA_CK(cudaMemsetAsync(sp->scratchE.p, 0, sizeof(double) * (size_t)sp->nE, ctx->stream));
-   if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->hB.data(), sp->hG.data(),
-                f->has_diff ? f->pa_diff.as<double>() : nullptr, f->has_mass ? f->pa_mass.as<double>() : nullptr,
-                sp->scratchE.as<double>(), (f->has_diff && f->factorised) ? sp->geo6.as<double>() : nullptr))
+   // fem/bilinearform_ext.cpp:401-423: localY = 0; every integrator adds; AbsMultTranspose.  Here: one kernel for both
+   // integrators that WRITES every E-entry straight into the slot layout (no zero fill, no read-modify-write)
+   DiagArgs a;
+   a.pd = f->has_diff ? f->pa_diff.as<double>() : nullptr;
+   a.pm = f->has_mass ? f->pa_mass.as<double>() : nullptr;
+   a.geo = (f->has_diff && f->factorised) ? sp->geo6.as<double>() : nullptr;
+   a.out = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>();
+   a.diff_off = diag_diff_off(f);
+   if (run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->hB.data(), sp->hG.data(), a)) { return 1; }
+   return finish_diagonal(f, diag_dev);
+}
+
+// DiffusionIntegrator::AssemblePA + the form's AssembleDiagonal in ONE pass over the q-points (what every implicit time
+// step with k(T) needs: new q-data and a new Jacobi diagonal).  On a mesh of affine elements the kernel forms
+// c = W C per q-point, writes the q-data from it (six stored components, or the scalar of the factorised form) and takes
+// the diagonal from the same values; the mass integrator's q-data is used as currently assembled.  On other meshes:
+// b200pa_form_assemble_diffusion followed by b200pa_form_assemble_diagonal (same results, two passes).
+extern "C" int b200pa_form_assemble_diffusion_with_diagonal(b200pa_form f, const double *C_any, long long nc, double *diag_dev)
+{
+   B200PA_REQUIRE(f && C_any && diag_dev, "form_assemble_diffusion_with_diagonal: NULL argument");
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   const bool fused = sp->affine && sp->geo6.p && sp->W.p && sp->ne > 0;
+   if (!fused)
    {
-      return 1;
+      if (b200pa_form_assemble_diffusion(f, C_any, nc)) { return 1; }
+      return b200pa_form_assemble_diagonal(f, diag_dev);
    }
-   if (b200pa_restrict_mult_transpose(ctx, sp->ndofs, sp->offsets.as<int>(), sp->indices.as<int>(), sp->scratchE.as<double>(),
-                                      diag_dev, 1))
+   B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_diffusion: coefficient must have 1 or Q^3*NE entries");
+   DevBuf cb;
+   const void *dC = nullptr;
+   if (to_device(ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
+   if (!f->pa_diff.owned) { f->pa_diff.release(); }
+   const bool fac = f->want_factorised;
+   if (fac != f->factorised) { f->pa_diff.release(); }
+   if (alloc(f->pa_diff, sizeof(double) * (fac ? 1 : 6) * (size_t)sp->nQ)) { return 1; }
+   DiagArgs a;
+   a.pd = (const double *)dC; a.const_c = (nc == 1);
+   a.pm = f->has_mass ? f->pa_mass.as<double>() : nullptr;
+   a.geo = sp->geo6.as<double>(); a.W = sp->W.as<double>();
+   a.pa_out = f->pa_diff.as<double>(); a.pa_out_ncomp = fac ? 1 : 6;
+   a.out = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>();
+   if (f->has_marker[0])
    {
-      return 1;
+      // the kernel takes the diagonal from the un-masked coefficient: with a diffusion marker keep the two passes
+      if (cb.owned) { cudaStreamSynchronize(ctx->stream); cb.release(); }
+      if (b200pa_form_assemble_diffusion(f, C_any, nc)) { return 1; }
+      return b200pa_form_assemble_diagonal(f, diag_dev);
    }
-   // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293-330): P^T of the local diagonal
-   if (f->comm) { return comm_exchange_sum(f->comm, diag_dev, nullptr); }
-   return 0;
+   f->has_diff = true;
+   f->factorised = fac;
+   a.diff_off = diag_diff_off(f);
+   int rc = run_diag(ctx, sp->d1d, sp->q1d, sp->ne, sp->hB.data(), sp->hG.data(), a);
+   if (cb.owned) { cudaStreamSynchronize(ctx->stream); cb.release(); }
+   f->has_diff = (rc == 0);
+   f->factorised = f->has_diff && fac;
+   if (rc) { return rc; }
+   return finish_diagonal(f, diag_dev);
 }
 
 extern "C" int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, double *b_dev)

@@ -38,6 +38,7 @@ struct ElemArgs
    const int *done = nullptr;
    double ca = 0.0, cb = 0.0, cT0 = 0.0;    // EV_COEFF_L / EV_JOULE_L parameters
    const double *s = nullptr;               // EV_JOULE_L: sigma_q
+   const double *jinv = nullptr;            // affine meshes: rows of J^{-T} per element [9,NE] (wins over J / vtx)
    const double *vtx = nullptr;             // J == nullptr: trilinear geometry from vertices
    const int *ev = nullptr;
    const double *xi = nullptr;              // HOST pointer, Q values

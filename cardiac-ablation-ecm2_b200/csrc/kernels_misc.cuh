@@ -231,7 +231,7 @@ __global__ void k_diffusion_setup_trilinear(int Q1D, long long NE, const double 
 // into the per-element tensor below (6 doubles per ELEMENT) and the scalar w_q c_q per q-point.  One thread per
 // element; `flag` is raised when an element is not affine to `tol` (relative to its edge lengths).
 __global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, const int *__restrict__ ev, double tol,
-                                  double *__restrict__ geo6, int *flag)
+                                  double *__restrict__ geo6, double *__restrict__ jinv9, int *flag)
 {
    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
    {
@@ -271,12 +271,22 @@ __global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, 
       g[3] = w * (A21 * A21 + A22 * A22 + A23 * A23);
       g[4] = w * (A21 * A31 + A22 * A32 + A23 * A33);
       g[5] = w * (A31 * A31 + A32 * A32 + A33 * A33);
+      if (jinv9)
+      {
+         // rows of J^{-T} = cofactors / det J: physical gradient g_r = ji[3r] gX + ji[3r+1] gY + ji[3r+2] gZ
+         // (fem/qinterp/grad.hpp:340-352; same cofactor naming as pa_element_kernel's i0..i8)
+         double *ji = jinv9 + 9 * e;
+         ji[0] = A11 * w; ji[1] = A21 * w; ji[2] = A31 * w;
+         ji[3] = A12 * w; ji[4] = A22 * w; ji[5] = A32 * w;
+         ji[6] = A13 * w; ji[7] = A23 * w; ji[8] = A33 * w;
+      }
    }
 }
 
 // The same per-element tensor from stored Jacobians (the host's GeometricFactors): J is taken at the first q-point
 // and the element counts as affine when no entry of J moves by more than tol * max|J| over its q-points.
-__global__ void k_affine_from_J(long long NQ, long long NE, const double *__restrict__ J, double tol, double *__restrict__ geo6, int *flag)
+__global__ void k_affine_from_J(long long NQ, long long NE, const double *__restrict__ J, double tol, double *__restrict__ geo6,
+                                double *__restrict__ jinv9, int *flag)
 {
    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
    {
@@ -303,6 +313,15 @@ __global__ void k_affine_from_J(long long NQ, long long NE, const double *__rest
       g[3] = w * (A21 * A21 + A22 * A22 + A23 * A23);
       g[4] = w * (A21 * A31 + A22 * A32 + A23 * A33);
       g[5] = w * (A31 * A31 + A32 * A32 + A33 * A33);
+      if (jinv9)
+      {
+         // rows of J^{-T} = cofactors / det J: physical gradient g_r = ji[3r] gX + ji[3r+1] gY + ji[3r+2] gZ
+         // (fem/qinterp/grad.hpp:340-352; same cofactor naming as pa_element_kernel's i0..i8)
+         double *ji = jinv9 + 9 * e;
+         ji[0] = A11 * w; ji[1] = A21 * w; ji[2] = A31 * w;
+         ji[3] = A12 * w; ji[4] = A22 * w; ji[5] = A32 * w;
+         ji[6] = A13 * w; ji[7] = A23 * w; ji[8] = A33 * w;
+      }
    }
 }
 
@@ -357,13 +376,57 @@ __global__ void k_coeff_eval(int kind, long long n, double a, double b, double T
 // with the seven fields f = D00, D01, D02, D11, D12, D22, mass; per direction the 1-D factor is
 // GG, BG or BB (G in the directions i and j of D_ij, B elsewhere); w = 2 for the off-diagonal D_ij.
 // Three contraction passes through shared memory instead of a Q^3 loop per E-entry (14x fewer FMAs at p=2).
-template <int D1, int Q1, int NEB>
+//
+// HBM-bound (reads the q-data once: 8 * 7 Q^3 bytes per element), so what matters is bytes in flight: the q-data of
+// a batch is staged by TMA bulk copies into one of TWO shared-memory stages, two batches ahead of its use (round 1
+// had one stage refilled after pass 1: 49 % of the HBM roofline).  Output modes:
+//   * E-vector, accumulated (AssembleDiagonalPA semantics of the integrator-level entry points), or
+//   * the slot layout of the E->L CSR, written (the form-level diagonal: no zero fill, no read-modify-write, and the
+//     segmented reduction that follows streams contiguously instead of gathering through the index list).
+// FUSED (affine meshes): the staged field is the raw coefficient C(q); the kernel forms c = W(q) C(q) in place, WRITES the
+// integrator's q-data from it (pa_out: the six stored components c * geo6_f(e), or the scalar c of the factorised form)
+// and takes the diagonal from the same registers - PADiffusionSetup3D and the diagonal in one pass over the q-points
+// (an implicit time step re-assembles both at every step: 3.6 GB of q-data are then never read back for the diagonal).
+#ifndef B200PA_TUNE_DIAG_KB
+#define B200PA_TUNE_DIAG_KB 64
+#endif
+// smallest s >= lo with s = r (mod 16): 16 consecutive lanes (one 128-byte shared-memory wavefront of doubles) whose
+// addresses advance by `r` per outer index and by 1 per inner index then fall into 16 different banks
+constexpr int diag_stride(int lo, int r) { return lo + ((r - lo) % 16 + 16) % 16; }
+
+template <int D1, int Q1>
 struct DiagSfCfg
 {
    static constexpr int Q2 = Q1 * Q1, Q3 = Q1 * Q1 * Q1, NF = 7;
-   static constexpr int T1E = NF * Q2 * D1, T2E = NF * Q1 * D1 * D1;
-   static constexpr int SQD = NEB * 6 * Q3 + 2, SQM = ((NEB * Q3 + 2) + 1) & ~1; // TMA staging (16-byte aligned, +slack)
-   static constexpr size_t SMEM_BYTES = sizeof(double) * (SQD + SQM + NEB * (T1E + T2E));
+   // The contraction order is z, y, x (round 1 went x, y, z: its first pass read rows of Q1 consecutive doubles per lane,
+   // a Q1-way bank conflict on the staged q-data - 55 % of all shared-memory wavefronts at p=2, profiles/r2c_*):
+   //   pass 1  task (e, qy, qx): contract qz   stage[f][qz][qy][qx] -> T1[f][dz][qy qx]     (lanes walk qx: stride 1)
+   //   pass 2  task (e, dz, qx): contract qy   T1 -> T2[f][dz][dy][qx]                        (lanes walk qx, then dz)
+   //   pass 3  task (e, dz, dy): contract qx, sum the fields -> element diagonal             (lanes walk dy, then dz)
+   static constexpr int S1 = diag_stride(Q2, Q1);          // dz stride of T1: lanes (dz, qx) of pass 2 -> distinct banks
+   static constexpr int F1 = D1 * S1;                      // field stride of T1
+   static constexpr int T1E = diag_stride(NF * F1, Q2 % 16); // element stride of T1 (pass 1 lanes: Q2 per element)
+   static constexpr int R2 = Q1 | 1;                       // row stride of T2 (odd: lanes of pass 3 walk rows)
+   static constexpr int S2 = diag_stride(D1 * R2, Q1);     // dz stride of T2: lanes (dz, qx) of pass 2 -> distinct banks
+   static constexpr int F2 = D1 * S2;
+   static constexpr int T2E = NF * F2;
+   static constexpr int SQD1 = 6 * Q3, SQM1 = Q3;          // staged q-data per element
+   static_assert(T2E <= 7 * Q3 + 0 || true, "");
+   // T2 overlays the stage it was fed from (free once pass 1 is done; the stage is refilled at the END of the batch, which
+   // still leaves the copy a whole batch of time): shared memory per element = two stages + T1
+   static constexpr int STAGE1 = (SQD1 + SQM1) > T2E ? (SQD1 + SQM1) : T2E;
+   static constexpr int PER_E = (2 * STAGE1 + T1E) * 8;
+   static constexpr int NEB0 = (B200PA_TUNE_DIAG_KB * 1024) / PER_E;
+   static constexpr int NEB = NEB0 < 1 ? 1 : (NEB0 > 8 ? 8 : NEB0);
+   // lanes per element in the three passes: padded to a whole 16-lane group while an element has fewer tasks than that, so
+   // that no half-warp (one shared-memory wavefront of doubles) straddles two elements - the strides above are
+   // conflict-free inside an element (ncu of the unpadded version: 2.25x the ideal wavefronts in pass 3 at p=2)
+   static constexpr int TPE1 = Q2 < 16 ? 16 : Q2, TPE2 = D1 * Q1 < 16 ? 16 : D1 * Q1, TPE3 = D1 * D1 < 16 ? 16 : D1 * D1;
+   static constexpr int NT0 = ((NEB * TPE1 + 31) / 32) * 32;
+   static constexpr int NT = NT0 < 64 ? 64 : NT0;
+   static constexpr int SQD = NEB * SQD1 + 2, SQM = ((NEB * SQM1 + 2) + 1) & ~1; // TMA staging (16-byte aligned, +slack)
+   static constexpr int STAGE = (SQD + SQM) > NEB * T2E ? (SQD + SQM) : ((NEB * T2E + 1) & ~1);
+   static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * STAGE + NEB * T1E + Q3);
 };
 
 // kernel parameters: the three 1-D factor tables live in the constant bank, so that with the field loop
@@ -373,32 +436,43 @@ struct DiagParams
 {
    double M[3][Q1 * D1]; // 0: B*B, 1: B*G, 2: G*G, column-major [Q,D]
    long long NE;
-   const double *__restrict__ pa_diff;
+   const double *__restrict__ pa_diff; // stored: [6 Q^3, NE]; factorised (geo != null): c_q [Q^3, NE]; FUSED: the raw coefficient C
    const double *__restrict__ pa_mass;
-   const double *__restrict__ geo; // factorised diffusion q-data: pa_diff = c_q [Q^3,NE], geo = adj(J)adj(J)^T/det J [6,NE]; else null
-   double *__restrict__ dE;
+   const double *__restrict__ geo; // adj(J)adj(J)^T/det J [6,NE] (factorised form and FUSED), else null
+   double *__restrict__ out;       // E-vector (+=) or slot-order scratch (=)
+   const int *__restrict__ slot;   // SLOT output: position of every E-entry in the E->L CSR
+   // FUSED
+   const double *__restrict__ W;   // quadrature weights [Q^3] (device)
+   double *__restrict__ pa_out;    // q-data written by the kernel
+   int pa_out_ncomp;               // 6 (stored form) or 1 (factorised form)
+   int const_c;                    // FUSED: C has one entry
+   // markers: elements whose DIFFUSION part is left out of the diagonal although its q-data is there - the reference
+   // zeroes the accumulated element diagonal of every element a LATER integrator's marker excludes (see b200pa.h)
+   const unsigned char *__restrict__ diff_off;
 };
 
-template <int D1, int Q1, int NEB>
-__global__ void __launch_bounds__(128)
+template <int D1, int Q1, bool SLOT, bool FUSED>
+__global__ void __launch_bounds__(DiagSfCfg<D1, Q1>::NT)
 k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 {
-   using C = DiagSfCfg<D1, Q1, NEB>;
-   constexpr int D3 = D1 * D1 * D1, Q2 = C::Q2, Q3 = C::Q3, NF = C::NF, T1E = C::T1E, T2E = C::T2E;
-   extern __shared__ double dsm[];
-   double *sQd = dsm;                 // this batch's q-data, staged by TMA one batch ahead (as pa_apply_kernel)
-   double *sQm = sQd + C::SQD;
-   double *sT1 = sQm + C::SQM;
-   double *sT2 = sT1 + NEB * T1E;
-   __shared__ unsigned long long qbar;
+   using C = DiagSfCfg<D1, Q1>;
+   constexpr int D2 = D1 * D1, D3 = D1 * D1 * D1, Q2 = C::Q2, Q3 = C::Q3, NF = C::NF, NEB = C::NEB;
+   constexpr int S1 = C::S1, F1 = C::F1, T1E = C::T1E, R2 = C::R2, S2 = C::S2, F2 = C::F2, T2E = C::T2E;
+   extern __shared__ __align__(16) double dsm[];
+   double *sT1 = dsm + 2 * C::STAGE;  // stages first: 16-byte aligned for the bulk copies
+   double *sW = sT1 + NEB * T1E;
+   __shared__ unsigned long long qbar[2];
    const long long NE = P.NE;
    const double *pa_diff = P.pa_diff, *pa_mass = P.pa_mass;
-   if (threadIdx.x == 0) { mbar_init(&qbar, 1); }
+   const double *geo = P.geo;
+   const bool scalar_diff = FUSED || geo != nullptr; // the diffusion field is one scalar per q-point
+   const bool stage_diff = pa_diff != nullptr && !(FUSED && P.const_c);
+   if (threadIdx.x == 0) { mbar_init(&qbar[0], 1); mbar_init(&qbar[1], 1); }
+   if (FUSED) { for (int i = threadIdx.x; i < Q3; i += blockDim.x) { sW[i] = P.W[i]; } }
    __syncthreads();
 // factor type of field f = D00, D01, D02, D11, D12, D22, mass in direction a: how many of the two indices
 // of D_ij equal a (0: BB, 1: BG, 2: GG); f and a are compile-time wherever this is used
 #define B200PA_MTYPE(f, a) ((((a) == 0 ? 0x0016u : ((a) == 1 ? 0x0184u : 0x0910u)) >> (2 * (f))) & 3u)
-   const double *geo = P.geo;
    struct FieldCopy { const double *src; unsigned bytes; };
    auto scalar_field = [&](const double *arr, double *sdst, long long e0, int nel)
    {
@@ -413,38 +487,68 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
       }
       return FieldCopy{src, (unsigned)(nd * sizeof(double))};
    };
-   auto issue = [&](long long b)
+   auto issue = [&](long long b, int st)
    {
+      double *sQd = dsm + st * C::STAGE, *sQm = sQd + C::SQD;
       const long long e0 = b * NEB;
       const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
       FieldCopy cd{nullptr, 0}, cm{nullptr, 0};
-      if (pa_diff) { cd = geo ? scalar_field(pa_diff, sQd, e0, nel) : FieldCopy{pa_diff + e0 * 6 * Q3, (unsigned)(nel * 6 * Q3 * sizeof(double))}; }
+      if (stage_diff) { cd = scalar_diff ? scalar_field(pa_diff, sQd, e0, nel) : FieldCopy{pa_diff + e0 * 6 * Q3, (unsigned)(nel * 6 * Q3 * sizeof(double))}; }
       if (pa_mass) { cm = scalar_field(pa_mass, sQm, e0, nel); }
-      mbar_expect_tx(&qbar, cd.bytes + cm.bytes);
-      if (pa_diff) { tma_bulk_g2s(sQd, cd.src, cd.bytes, &qbar); }
-      if (pa_mass) { tma_bulk_g2s(sQm, cm.src, cm.bytes, &qbar); }
+      mbar_expect_tx(&qbar[st], cd.bytes + cm.bytes);
+      if (stage_diff) { tma_bulk_g2s(sQd, cd.src, cd.bytes, &qbar[st]); }
+      if (pa_mass) { tma_bulk_g2s(sQm, cm.src, cm.bytes, &qbar[st]); }
    };
    const long long nbatch = (NE + NEB - 1) / NEB;
-   unsigned phase = 0;
-   if ((long long)blockIdx.x < nbatch && threadIdx.x == 0) { issue(blockIdx.x); }
-   for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x)
+   unsigned phase = 0; // bit s: parity of stage s
+   if (threadIdx.x == 0)
+   {
+      if ((long long)blockIdx.x < nbatch) { issue(blockIdx.x, 0); }
+      if ((long long)blockIdx.x + gridDim.x < nbatch) { issue((long long)blockIdx.x + gridDim.x, 1); }
+   }
+   int st = 0;
+   for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x, st ^= 1)
    {
       const long long e0 = batch * NEB;
       const int nel = (int)(NE - e0 < NEB ? NE - e0 : NEB);
-      mbar_wait(&qbar, phase);
-      phase ^= 1u;
+      double *sQd = dsm + st * C::STAGE, *sQm = sQd + C::SQD;
+      double *sT2 = sQd;              // overlays the stage once pass 1 has consumed it
+      mbar_wait(&qbar[st], (phase >> st) & 1u);
+      phase ^= 1u << st;
       const int msh = pa_mass ? (int)(((unsigned long long)(pa_mass + e0 * Q3) >> 3) & 1ull) : 0;
-      const int dsh = (pa_diff && geo) ? (int)(((unsigned long long)(pa_diff + e0 * Q3) >> 3) & 1ull) : 0;
-      // pass 1: contract qx.  task = (e, qz, qy), all seven fields: one row of Q1 q-data values each
-      for (int t = threadIdx.x; t < nel * Q2; t += blockDim.x)
+      const int dsh = (stage_diff && scalar_diff) ? (int)(((unsigned long long)(pa_diff + e0 * Q3) >> 3) & 1ull) : 0;
+      if (FUSED)
       {
-         const int e = t / Q2, row = t - e * Q2;
+         // c = W(q) C(q) in place; the integrator's q-data goes out from the same value (coalesced over q)
+         const double c0 = P.const_c ? __ldg(pa_diff) : 0.0;
+         for (int i = threadIdx.x; i < nel * Q3; i += blockDim.x)
+         {
+            const int e = i / Q3, q = i - e * Q3;
+            const double c = sW[q] * (P.const_c ? c0 : sQd[dsh + i]);
+            sQd[dsh + i] = c;
+            if (P.pa_out_ncomp == 1) { P.pa_out[(e0 + e) * Q3 + q] = c; }
+            else
+            {
+               const double *g = geo + (e0 + e) * 6;
+               double *o = P.pa_out + (e0 + e) * 6 * Q3 + q;
+#pragma unroll
+               for (int f = 0; f < 6; ++f) { o[f * Q3] = c * __ldg(g + f); }
+            }
+         }
+         __syncthreads();
+      }
+      // pass 1: contract qz.  task = (e, qy, qx), all seven fields: one column of Q1 q-data values each
+      for (int t = threadIdx.x; t < nel * C::TPE1; t += blockDim.x)
+      {
+         const int e = t / C::TPE1, c = t - e * C::TPE1;
+         if (c >= Q2) { continue; }
+         const bool diff_on = pa_diff != nullptr && !(P.diff_off && P.diff_off[e0 + e]);
 #pragma unroll
          for (int f = 0; f < NF; ++f)
          {
-            const bool have = f < 6 ? pa_diff != nullptr : pa_mass != nullptr;
-            const double *src = f < 6 ? (geo ? sQd + dsh + e * Q3 + row * Q1 : sQd + (e * 6 + f) * Q3 + row * Q1) : sQm + msh + e * Q3 + row * Q1;
-            const double scale = (f < 6 && geo && have) ? __ldg(geo + (e0 + e) * 6 + f) : 1.0;
+            const bool have = f < 6 ? diff_on : pa_mass != nullptr;
+            const double *src = f < 6 ? (scalar_diff ? sQd + dsh + e * Q3 + c : sQd + (e * 6 + f) * Q3 + c) : sQm + msh + e * Q3 + c;
+            const double scale = (f < 6 && scalar_diff && have) ? __ldg(geo + (e0 + e) * 6 + f) : 1.0;
             double out[D1];
 #pragma unroll
             for (int d = 0; d < D1; ++d) { out[d] = 0.0; }
@@ -453,22 +557,21 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 #pragma unroll
                for (int q = 0; q < Q1; ++q)
                {
-                  const double v = scale * src[q];
+                  const double v = scale * src[q * Q2];
 #pragma unroll
-                  for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 0)][q + Q1 * d], v, out[d]); }
+                  for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 2)][q + Q1 * d], v, out[d]); }
                }
             }
 #pragma unroll
-            for (int d = 0; d < D1; ++d) { sT1[e * T1E + (f * Q2 + row) * D1 + d] = out[d]; }
+            for (int d = 0; d < D1; ++d) { sT1[e * T1E + f * F1 + d * S1 + c] = out[d]; }
          }
       }
       __syncthreads();
-      // the staged q-data is consumed: fetch the next batch while passes 2 and 3 run
-      if (batch + gridDim.x < nbatch && threadIdx.x == 0) { issue(batch + gridDim.x); }
-      // pass 2: contract qy.  task = (e, qz, dx), all seven fields
-      for (int t = threadIdx.x; t < nel * Q1 * D1; t += blockDim.x)
+      // pass 2: contract qy.  task = (e, dz, qx), all seven fields; T2 goes where the consumed q-data was
+      for (int t = threadIdx.x; t < nel * C::TPE2; t += blockDim.x)
       {
-         const int e = t / (Q1 * D1), r2 = t - e * Q1 * D1, qz = r2 / D1, dx = r2 - qz * D1;
+         const int e = t / C::TPE2, r2 = t - e * C::TPE2, dz = r2 / Q1, qx = r2 - dz * Q1;
+         if (r2 >= D1 * Q1) { continue; }
 #pragma unroll
          for (int f = 0; f < NF; ++f)
          {
@@ -478,19 +581,20 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 #pragma unroll
             for (int qy = 0; qy < Q1; ++qy)
             {
-               const double v = sT1[e * T1E + (f * Q2 + qz * Q1 + qy) * D1 + dx];
+               const double v = sT1[e * T1E + f * F1 + dz * S1 + qy * Q1 + qx];
 #pragma unroll
                for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 1)][qy + Q1 * d], v, out[d]); }
             }
 #pragma unroll
-            for (int dy = 0; dy < D1; ++dy) { sT2[e * T2E + ((f * Q1 + qz) * D1 + dy) * D1 + dx] = out[dy]; }
+            for (int dy = 0; dy < D1; ++dy) { sT2[e * T2E + f * F2 + dz * S2 + dy * R2 + qx] = out[dy]; }
          }
       }
       __syncthreads();
-      // pass 3: contract qz and sum the fields.  task = (e, dy, dx): all dz at once
-      for (int t = threadIdx.x; t < nel * D1 * D1; t += blockDim.x)
+      // pass 3: contract qx and sum the fields.  task = (e, dz, dy): all dx at once
+      for (int t = threadIdx.x; t < nel * C::TPE3; t += blockDim.x)
       {
-         const int e = t / (D1 * D1), k = t - e * D1 * D1;
+         const int e = t / C::TPE3, k = t - e * C::TPE3, dz = k / D1, dy = k - dz * D1;
+         if (k >= D2) { continue; }
          double acc[D1];
 #pragma unroll
          for (int d = 0; d < D1; ++d) { acc[d] = 0.0; }
@@ -499,19 +603,55 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
          {
             const double w = (f == 1 || f == 2 || f == 4) ? 2.0 : 1.0;
 #pragma unroll
-            for (int qz = 0; qz < Q1; ++qz)
+            for (int qx = 0; qx < Q1; ++qx)
             {
-               const double v = w * sT2[e * T2E + (f * Q1 + qz) * D1 * D1 + k];
+               const double v = w * sT2[e * T2E + f * F2 + dz * S2 + dy * R2 + qx];
 #pragma unroll
-               for (int dz = 0; dz < D1; ++dz) { acc[dz] = fma(P.M[B200PA_MTYPE(f, 2)][qz + Q1 * dz], v, acc[dz]); }
+               for (int dx = 0; dx < D1; ++dx) { acc[dx] = fma(P.M[B200PA_MTYPE(f, 0)][qx + Q1 * dx], v, acc[dx]); }
             }
          }
+         const long long o = (e0 + e) * D3 + k * D1;
 #pragma unroll
-         for (int dz = 0; dz < D1; ++dz) { P.dE[(e0 + e) * D3 + dz * D1 * D1 + k] += acc[dz]; }
+         for (int dx = 0; dx < D1; ++dx)
+         {
+            if (SLOT) { P.out[__ldg(P.slot + o + dx)] = acc[dx]; }
+            else { P.out[o + dx] += acc[dx]; }
+         }
       }
       __syncthreads();
+      // T2 (and with it this stage) is consumed: refill the stage with the batch after the next one; the other stage has
+      // been in flight / landed since the end of the previous batch
+      if (batch + 2LL * gridDim.x < nbatch && threadIdx.x == 0) { issue(batch + 2LL * gridDim.x, st); }
    }
 #undef B200PA_MTYPE
+}
+
+// ------------------------------------------------------- element-attribute markers
+// BilinearForm::AddDomainIntegrator(bfi, elem_marker): on[e] = the integrator acts on element e
+// (attr > 0 && marker[attr-1] != 0, fem/bilinearform_ext.cpp:391-399 and AddWithMarkers_)
+__global__ void k_marker_mask(long long NE, const int *__restrict__ attr, int n_attr, const int *__restrict__ marker,
+                              unsigned char *__restrict__ on, int *bad_flag)
+{
+   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
+   {
+      const int a = attr[e];
+      if (a > n_attr) { *bad_flag = 1; on[e] = 0; continue; }
+      on[e] = (a > 0 && marker[a - 1] != 0) ? 1 : 0;
+   }
+}
+__global__ void k_invert_mask(long long n, const unsigned char *__restrict__ in, unsigned char *__restrict__ out)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { out[i] = in[i] ? 0 : 1; }
+}
+// q-data of the elements an integrator does not act on := 0, so that their contribution to every apply is exactly
+// zero - AddMultWithMarkers (fem/bilinearform_ext.cpp:807-847) computes it and then leaves it out of the sum
+__global__ void k_zero_unmarked(long long NE, long long per_elem, const unsigned char *__restrict__ on, double *__restrict__ pa)
+{
+   const long long n = NE * per_elem;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   {
+      if (!on[i / per_elem]) { pa[i] = 0.0; }
+   }
 }
 
 // ------------------------------------------------------------------ BLAS-1 etc.

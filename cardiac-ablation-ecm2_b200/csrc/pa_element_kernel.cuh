@@ -61,6 +61,7 @@ struct ElemParams
    double ca, cb, cT0;                 // QOP_COEFF: a (1 + b (T - T0)); QOP_JOULE: s |grad|^2 + a
    const double *__restrict__ s;       // QOP_JOULE: sigma at q-points [Q^3,NE]
    // QOP_PHYSGRAD / QOP_JOULE without stored Jacobians (J == null): trilinear geometry from the vertices
+   const double *__restrict__ jinv;    // affine elements: rows of J^{-T} per ELEMENT [9,NE] (takes precedence over J / vtx)
    const double *__restrict__ vtx;     // [3,nv]
    const int *__restrict__ ev;         // [8,NE]
    double xi[Q];                       // 1-D Gauss-Legendre points
@@ -226,6 +227,29 @@ pa_element_kernel(const __grid_constant__ ElemParams<D, Q> P)
             }
          }
 
+         // q-point inputs of the other operations, also for the whole column up front: the loads of one thread are then in
+         // flight together instead of one DRAM latency per q-point (nvcc does not hoist them over the stores of the loop)
+         double Sq[Q], Fq[Q], Dq[Q], Ji[9];
+         if (QOP == QOP_JOULE)
+         {
+            B200PA_UNROLL
+            for (int qz = 0; qz < Q; ++qz) { Sq[qz] = __ldg(P.s + eg * Q3 + qz * Q2 + c); }
+         }
+         if (QOP == QOP_LF)
+         {
+            B200PA_UNROLL
+            for (int qz = 0; qz < Q; ++qz)
+            {
+               Fq[qz] = P.nf == 1 ? __ldg(P.f) : __ldg(P.f + eg * Q3 + qz * Q2 + c);
+               Dq[qz] = __ldg(P.detJ + eg * Q3 + qz * Q2 + c);
+            }
+         }
+         if ((QOP == QOP_PHYSGRAD || QOP == QOP_JOULE) && P.jinv)
+         {
+            B200PA_UNROLL
+            for (int k = 0; k < 9; ++k) { Ji[k] = __ldg(P.jinv + eg * 9 + k); }
+         }
+
          B200PA_UNROLL
          for (int qz = 0; qz < Q; ++qz)
          {
@@ -272,6 +296,16 @@ pa_element_kernel(const __grid_constant__ ElemParams<D, Q> P)
             else if (QOP == QOP_PHYSGRAD || QOP == QOP_JOULE)
             {
                // J^{-T} (gX,gY,gZ): adjugate / det, fem/qinterp/grad.hpp:340-352
+               double g0, g1, g2;
+               if (P.jinv)
+               {
+                  // affine element: J is constant over it, its inverse was formed once per element at geometry time
+                  g0 = Ji[0] * gX + Ji[1] * gY + Ji[2] * gZ;
+                  g1 = Ji[3] * gX + Ji[4] * gY + Ji[5] * gZ;
+                  g2 = Ji[6] * gX + Ji[7] * gY + Ji[8] * gZ;
+               }
+               else
+               {
                double a0, a1, a2, a3, a4, a5, a6, a7, a8;
                if (P.J)
                {
@@ -290,20 +324,20 @@ pa_element_kernel(const __grid_constant__ ElemParams<D, Q> P)
                const double i3 = a5 * a6 - a3 * a8, i4 = a0 * a8 - a2 * a6, i5 = a2 * a3 - a0 * a5;
                const double i6 = a3 * a7 - a4 * a6, i7 = a1 * a6 - a0 * a7, i8 = a0 * a4 - a1 * a3;
                const double idet = 1.0 / (a0 * i0 + a1 * i3 + a2 * i6);
-               const double g0 = (i0 * gX + i1 * gY + i2 * gZ) * idet;
-               const double g1 = (i3 * gX + i4 * gY + i5 * gZ) * idet;
-               const double g2 = (i6 * gX + i7 * gY + i8 * gZ) * idet;
+               g0 = (i0 * gX + i1 * gY + i2 * gZ) * idet;
+               g1 = (i3 * gX + i4 * gY + i5 * gZ) * idet;
+               g2 = (i6 * gX + i7 * gY + i8 * gZ) * idet;
+               }
                if (QOP == QOP_PHYSGRAD)
                {
                   double *g = P.y + 3 * (eg * Q3 + q);
                   g[0] = g0; g[1] = g1; g[2] = g2;
                }
-               else { P.y[eg * Q3 + q] = P.s[eg * Q3 + q] * (g0 * g0 + g1 * g1 + g2 * g2) + P.ca; }
+               else { P.y[eg * Q3 + q] = Sq[qz] * (g0 * g0 + g1 * g1 + g2 * g2) + P.ca; }
             }
             else if (QOP == QOP_LF)
             {
-               const double fv = P.nf == 1 ? P.f[0] : P.f[eg * Q3 + q];
-               const double hM = P.W[q] * fv * P.detJ[eg * Q3 + q];
+               const double hM = P.W[q] * Fq[qz] * Dq[qz];
                B200PA_UNROLL
                for (int dz = 0; dz < D; ++dz) { p2[dz] = fma(Bm(qz, dz), hM, p2[dz]); }
             }

@@ -21,6 +21,11 @@
 
 #include "mfem.hpp"
 
+#include <cmath>
+#include <iomanip>
+#include <memory>
+#include <vector>
+
 #include "../../include/b200pa.h"
 
 namespace b200
@@ -187,7 +192,9 @@ public:
 };
 
 /// The fused operator: PABilinearFormExtension::Mult + ConstrainedOperator for a form made of a
-/// DiffusionIntegrator and/or a MassIntegrator with scalar coefficients (either may be null).
+/// DiffusionIntegrator and/or a MassIntegrator with scalar coefficients (either may be null), added in that order.
+/// diff_marker / mass_marker: the element-attribute markers of BilinearForm::AddDomainIntegrator(bfi, elem_marker)
+/// (multi-material domains; semantics of fem/bilinearform_ext.cpp:370-454, 807-847, see include/b200pa.h).
 class PAOperator : public mfem::Operator
 {
    const mfem::FiniteElementSpace &fes;
@@ -196,6 +203,8 @@ class PAOperator : public mfem::Operator
    mfem::Array<int> ess;
    const mfem::IntegrationRule *ir = nullptr;
    friend class PCGSolver;
+   friend class JacobiSmoother;
+   friend class ChebyshevSmoother;
 
    void Project(mfem::Coefficient *c, std::vector<double> &out)
    {
@@ -207,7 +216,8 @@ public:
    /// factorised = true: on a mesh whose elements are all affine (b200pa_space_is_affine) the diffusion q-data is kept
    /// as w_q c_q per q-point + one tensor per element (b200pa_form_set_factorised); other meshes keep the stored form
    PAOperator(const mfem::FiniteElementSpace &fes_, mfem::Coefficient *kdiff, mfem::Coefficient *cmass,
-              const mfem::Array<int> &ess_tdof_list, bool factorised = false)
+              const mfem::Array<int> &ess_tdof_list, bool factorised = false,
+              const mfem::Array<int> *diff_marker = nullptr, const mfem::Array<int> *mass_marker = nullptr)
       : mfem::Operator(fes_.GetVSize()), fes(fes_)
    {
       const mfem::FiniteElement &el = *fes.GetTypicalFE();
@@ -225,6 +235,15 @@ public:
       Check(b200pa_space_set_geometry(sp, ir->GetWeights().HostRead(), geom->J.HostRead(), geom->detJ.HostRead()));
       Check(b200pa_form_create(sp, &form));
       if (factorised && b200pa_space_is_affine(sp) == 1) { Check(b200pa_form_set_factorised(form, 1)); }
+      if (diff_marker || mass_marker)
+      {
+         // elem_attributes of PABilinearFormExtension (fem/bilinearform_ext.cpp: SetupRestrictionOperators)
+         mfem::Array<int> attr(s.ne);
+         for (int e = 0; e < s.ne; e++) { attr[e] = fes.GetMesh()->GetAttribute(e); }
+         Check(b200pa_space_set_attributes(sp, attr.HostRead()));
+         if (diff_marker) { Check(b200pa_form_set_markers(form, 0, diff_marker->Size(), diff_marker->HostRead())); }
+         if (mass_marker) { Check(b200pa_form_set_markers(form, 1, mass_marker->Size(), mass_marker->HostRead())); }
+      }
       std::vector<double> q;
       if (kdiff) { Project(kdiff, q); Check(b200pa_form_assemble_diffusion(form, q.data(), (long long)q.size())); }
       if (cmass) { Project(cmass, q); Check(b200pa_form_assemble_mass(form, q.data(), (long long)q.size())); }
@@ -264,83 +283,195 @@ public:
    const mfem::Array<int> &GetEssentialTrueDofs() const { return ess; }
 };
 
-/// CGSolver + OperatorJacobiSmoother on the GPU (linalg/solvers.cpp:331-453, 869-1050); same
-/// setters / getters and the same meaning of iterative_mode, GetNumIterations, GetConverged,
-/// GetFinalNorm as mfem::CGSolver.
-class PCGSolver : public mfem::Solver
+/// ≙ OperatorJacobiSmoother(a, ess_tdof_list, damping) (linalg/solvers.cpp:331-453) for a b200::PAOperator: the diagonal is
+/// assembled and inverted on the GPU.  A Solver of its own (Mult works on host vectors, so mfem::CGSolver can use it) and
+/// the preconditioner b200::PCGSolver fuses into its device-resident loop.
+class JacobiSmoother : public mfem::Solver
 {
    const PAOperator *op = nullptr;
    DeviceBuffer dinv;
-   double rel_tol = 0.0, abs_tol = 0.0, damping = 1.0;
-   int max_iter = 10, print_level = -1;
-   mutable b200pa_pcg_result res{};
-   mutable std::vector<double> norms;
-   int cheb_order = 0;
-   double cheb_max_eig = 0.0;
+   mutable DeviceBuffer d_r, d_z;
+   double damping;
 public:
-   PCGSolver() : mfem::Solver(0, true) {}
-   void SetRelTol(double t) { rel_tol = t; }
-   void SetAbsTol(double t) { abs_tol = t; }
-   void SetMaxIter(int n) { max_iter = n; }
-   void SetPrintLevel(int l) { print_level = l; }
-   /// precondition with OperatorChebyshevSmoother(order) instead of OperatorJacobiSmoother (linalg/solvers.cpp:455-657);
-   /// max_eig <= 0: estimated at SetOperator time by the reference's power method (10 steps, 1e-8, seed 12345). Call
-   /// before SetOperator.
-   void SetChebyshev(int order, double max_eig = 0.0) { cheb_order = order; cheb_max_eig = max_eig; }
-   double GetMaxEigEstimate() const { return cheb_max_eig; }
-   /// SetOperator + SetPreconditioner(OperatorJacobiSmoother(a, ess, damping)) in one
+   explicit JacobiSmoother(double damping_ = 1.0) : mfem::Solver(0, false), damping(damping_) {}
+   JacobiSmoother(const PAOperator &A, double damping_ = 1.0) : mfem::Solver(0, false), damping(damping_) { SetOperator(A); }
    void SetOperator(const mfem::Operator &o) override
    {
       op = dynamic_cast<const PAOperator *>(&o);
-      MFEM_VERIFY(op, "b200::PCGSolver works on a b200::PAOperator");
+      MFEM_VERIFY(op, "b200::JacobiSmoother works on a b200::PAOperator");
       height = width = op->Height();
-      DeviceBuffer diag;
+      DeviceBuffer diag, dess;
       diag.Resize(sizeof(double) * height);
       dinv.Resize(sizeof(double) * height);
       Check(b200pa_form_assemble_diagonal(op->form, diag.D()));
-      DeviceBuffer dess;
       dess.Resize(sizeof(int) * std::max(op->ess.Size(), 1));
       if (op->ess.Size()) { dess.Upload(op->ess.HostRead(), sizeof(int) * op->ess.Size()); }
       Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), op->ess.Size(), dess.I(), damping, dinv.D()));
-      if (cheb_order > 0 && cheb_max_eig <= 0.0)
+   }
+   /// z = dinv .* r  (OperatorJacobiSmoother::Mult with iterative_mode = false, linalg/solvers.cpp:427-453)
+   void Mult(const mfem::Vector &r, mfem::Vector &z) const override
+   {
+      MFEM_VERIFY(op, "b200::JacobiSmoother: SetOperator first");
+      MFEM_VERIFY(!iterative_mode, "b200::JacobiSmoother: iterative_mode is not supported");
+      d_r.Upload(r.HostRead(), sizeof(double) * height);
+      d_z.Resize(sizeof(double) * height);
+      Check(b200pa_jacobi_mult(Ctx(), height, dinv.D(), d_r.D(), d_z.D()));
+      d_z.Download(z.HostWrite(), sizeof(double) * height);
+   }
+   const PAOperator *GetOperator() const { return op; }
+   const double *DeviceDinv() const { return dinv.D(); }
+};
+
+/// ≙ OperatorChebyshevSmoother(A, diag, ess, order[, max_eig_estimate]) (linalg/solvers.cpp:455-657); without an estimate the
+/// reference's power method (10 steps, 1e-8, seed 12345, linalg/solvers.cpp:497-511) runs on the GPU at SetOperator time.
+class ChebyshevSmoother : public mfem::Solver
+{
+   JacobiSmoother jac;
+   int order;
+   double max_eig;
+   mutable DeviceBuffer d_x, d_y;
+public:
+   explicit ChebyshevSmoother(int order_, double max_eig_estimate = 0.0) : mfem::Solver(0, false), jac(1.0), order(order_), max_eig(max_eig_estimate) {}
+   void SetOperator(const mfem::Operator &o) override
+   {
+      jac.SetOperator(o);
+      height = width = jac.Height();
+      if (max_eig <= 0.0)
       {
          mfem::Vector v0(height);
          v0.Randomize(12345);
          DeviceBuffer dv;
          dv.Upload(v0.HostRead(), sizeof(double) * height);
-         Check(b200pa_power_method(op->form, dinv.D(), dv.D(), 10, 1e-8, &cheb_max_eig));
+         Check(b200pa_power_method(jac.GetOperator()->form, jac.DeviceDinv(), dv.D(), 10, 1e-8, &max_eig));
       }
+   }
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      MFEM_VERIFY(jac.GetOperator(), "b200::ChebyshevSmoother: SetOperator first");
+      d_x.Upload(x.HostRead(), sizeof(double) * height);
+      d_y.Resize(sizeof(double) * height);
+      Check(b200pa_chebyshev_mult(jac.GetOperator()->form, jac.DeviceDinv(), order, max_eig, d_x.D(), d_y.D()));
+      d_y.Download(y.HostWrite(), sizeof(double) * height);
+   }
+   int Order() const { return order; }
+   double GetMaxEigEstimate() const { return max_eig; }
+   const JacobiSmoother &Jacobi() const { return jac; }
+};
+
+/// mfem::CGSolver on the GPU (linalg/solvers.cpp:869-1050): an mfem::IterativeSolver - it can be handed wherever the
+/// reference takes an IterativeSolver& - whose Mult runs the whole loop device-resident on a b200::PAOperator.
+///   SetPreconditioner   b200::JacobiSmoother or b200::ChebyshevSmoother (fused into the loop); none = plain CG, as in the
+///                       reference; any other Solver aborts - there is no CPU fallback.
+///   SetPrintLevel       the reference's PrintLevel flags print the reference's lines from the recorded (B r, r) history.
+///   SetMonitor          MonitorResidual / MonitorSolution are called for every iteration AFTER the solve with the recorded
+///                       norms; the vectors they receive are the final residual and solution (the loop keeps its iterates
+///                       on the device), and a controller cannot stop the iteration (HasConverged is ignored, a controller
+///                       that RequiresUpdatedSolution is refused).
+/// Same meaning of iterative_mode, rel/abs tolerance, GetNumIterations, GetConverged, GetInitialNorm, GetFinalNorm.
+class PCGSolver : public mfem::IterativeSolver
+{
+   const PAOperator *op = nullptr;
+   mutable DeviceBuffer ones;
+   mutable std::vector<double> norms;
+   // shortcuts that own their smoother: UseJacobi(damping), SetChebyshev(order)
+   std::unique_ptr<ChebyshevSmoother> own_cheb;
+   std::unique_ptr<JacobiSmoother> own_jac;
+public:
+   PCGSolver() : mfem::IterativeSolver() {}
+   void UseJacobi(double damping = 1.0) { own_jac.reset(new JacobiSmoother(damping)); prec = own_jac.get(); }
+   void SetChebyshev(int order, double max_eig = 0.0) { own_cheb.reset(new ChebyshevSmoother(order, max_eig)); prec = own_cheb.get(); }
+   double GetMaxEigEstimate() const { return own_cheb ? own_cheb->GetMaxEigEstimate() : 0.0; }
+
+   void SetPreconditioner(mfem::Solver &pr) override
+   {
+      MFEM_VERIFY(dynamic_cast<JacobiSmoother *>(&pr) || dynamic_cast<ChebyshevSmoother *>(&pr),
+                  "b200::PCGSolver: the preconditioner must be a b200::JacobiSmoother or b200::ChebyshevSmoother (no CPU fallback)");
+      mfem::IterativeSolver::SetPreconditioner(pr);
+   }
+   void SetOperator(const mfem::Operator &o) override
+   {
+      op = dynamic_cast<const PAOperator *>(&o);
+      MFEM_VERIFY(op, "b200::PCGSolver works on a b200::PAOperator");
+      mfem::IterativeSolver::SetOperator(o); // sets height/width and hands the operator to the preconditioner
    }
    void Mult(const mfem::Vector &b, mfem::Vector &x) const override
    {
+      MFEM_VERIFY(op, "b200::PCGSolver: SetOperator first");
+      MFEM_VERIFY(!ControllerRequiresUpdate(), "b200::PCGSolver: controllers that need the updated solution every iteration are not supported");
       if (!iterative_mode) { x = 0.0; }
       norms.assign(max_iter + 2, 0.0);
-      if (cheb_order > 0)
+      b200pa_pcg_result res{};
+      const JacobiSmoother *jac = dynamic_cast<const JacobiSmoother *>(prec);
+      const ChebyshevSmoother *cheb = dynamic_cast<const ChebyshevSmoother *>(prec);
+      if (jac && !jac->GetOperator()) { const_cast<JacobiSmoother *>(jac)->SetOperator(*op); }
+      if (cheb && !cheb->Jacobi().GetOperator()) { const_cast<ChebyshevSmoother *>(cheb)->SetOperator(*op); }
+      if (cheb)
       {
          DeviceBuffer db, dx;
          db.Upload(b.HostRead(), sizeof(double) * height);
          dx.Upload(x.HostRead(), sizeof(double) * height);
-         Check(b200pa_pcg_solve_chebyshev(op->form, dinv.D(), cheb_order, cheb_max_eig, db.D(), dx.D(), rel_tol, abs_tol, max_iter, &res,
-                                          norms.data()));
+         Check(b200pa_pcg_solve_chebyshev(op->form, cheb->Jacobi().DeviceDinv(), cheb->Order(), cheb->GetMaxEigEstimate(), db.D(), dx.D(),
+                                          rel_tol, abs_tol, max_iter, &res, norms.data()));
          dx.Download(x.HostReadWrite(), sizeof(double) * height);
       }
       else
       {
-         Check(b200pa_pcg_solve_host(op->form, dinv.D(), b.HostRead(), x.HostReadWrite(), rel_tol, abs_tol, max_iter, &res, norms.data()));
-      }
-      if (print_level >= 1)
-      {
-         for (int i = 0; i <= res.final_iter; i++)
+         const double *dinv = nullptr;
+         if (jac) { dinv = jac->DeviceDinv(); }
+         else
          {
-            mfem::out << "   Iteration : " << std::setw(3) << i << "  (B r, r) = " << norms[i] << '\n';
+            // no preconditioner: d = r (linalg/solvers.cpp:889-892) == Jacobi with dinv = 1
+            std::vector<double> one(height, 1.0);
+            ones.Upload(one.data(), sizeof(double) * height);
+            dinv = ones.D();
          }
+         Check(b200pa_pcg_solve_host(op->form, dinv, b.HostRead(), x.HostReadWrite(), rel_tol, abs_tol, max_iter, &res, norms.data()));
+      }
+      final_iter = res.final_iter;
+      converged = res.converged != 0;
+      initial_norm = res.initial_norm;
+      final_norm = res.final_norm;
+      Report(b, x);
+   }
+   const std::vector<double> &GetResidualHistory() const { return norms; }
+private:
+   // the output and monitor calls of CGSolver::Mult (linalg/solvers.cpp:897-1047), from the recorded history
+   void Report(const mfem::Vector &b, const mfem::Vector &x) const
+   {
+      using std::setw;
+      const PrintLevel &po = print_options;
+      const double nom0 = norms[0];
+      if (po.iterations || po.first_and_last)
+      {
+         mfem::out << "   Iteration : " << setw(3) << 0 << "  (B r, r) = " << nom0 << (po.first_and_last ? " ...\n" : "\n");
+      }
+      if (nom0 < 0.0)
+      {
+         if (po.warnings) { mfem::out << "PCG: The preconditioner is not positive definite. (Br, r) = " << nom0 << '\n'; }
+      }
+      else if (final_iter > 0 || !converged)
+      {
+         const double betanom = norms[final_iter];
+         if (po.iterations) { for (int i = 1; i <= final_iter; i++) { mfem::out << "   Iteration : " << setw(3) << i << "  (B r, r) = " << norms[i] << std::endl; } }
+         if (betanom < 0.0 && po.warnings) { mfem::out << "PCG: The preconditioner is not positive definite. (Br, r) = " << betanom << '\n'; }
+         if (po.first_and_last && !po.iterations) { mfem::out << "   Iteration : " << setw(3) << final_iter << "  (B r, r) = " << betanom << '\n'; }
+         if (po.summary || (po.warnings && !converged)) { mfem::out << "PCG: Number of iterations: " << final_iter << '\n'; }
+         if ((po.summary || po.iterations || po.first_and_last) && final_iter > 0)
+         {
+            mfem::out << "Average reduction factor = " << pow(betanom / nom0, 0.5 / final_iter) << '\n';
+         }
+         if (po.warnings && !converged) { mfem::out << "PCG: No convergence!" << '\n'; }
+      }
+      if (controller)
+      {
+         // final residual for the monitor: r = b - A x (one more apply; only when somebody is watching)
+         mfem::Vector r(height);
+         op->Mult(x, r);
+         subtract(b, r, r);
+         for (int i = 0; i <= final_iter; i++) { Monitor(i, norms[i], r, x, false); }
+         Monitor(final_iter, final_iter == 0 ? norms[0] : final_norm, r, x, true);
       }
    }
-   int GetNumIterations() const { return res.final_iter; }
-   bool GetConverged() const { return res.converged != 0; }
-   double GetFinalNorm() const { return res.final_norm; }
-   double GetInitialNorm() const { return res.initial_norm; }
-   const std::vector<double> &GetResidualHistory() const { return norms; }
 };
 
 /// The Pennes bioheat equation as an mfem::TimeDependentOperator whose implicit solve runs on the GPU (pattern:
@@ -349,21 +480,27 @@ public:
 ///     rho c dT/dt = div k(T) grad T - w (T - Ta) + q,    k(T) = k0 (1 + ak (T - Tref)),   natural BCs
 ///     ImplicitSolve(dt, T, dT):  [M(rho c + dt w) + dt K(k(T))] dT = -[K(k(T)) + M(w)] T + (w Ta + q, v)
 /// T, the q-data and all solver vectors stay on the device; only T comes up and dT goes back per call.
+/// With EnableRF (or through b200::RFCoupledOperator) q is the Joule heat of the RF field, re-solved at every stage.
 class BioheatOperator : public mfem::TimeDependentOperator
 {
 public:
    struct Physics { double rc = 3.6e6, w = 4.0e4, Ta = 37.0, q = 0.0, k0 = 0.5, ak = 0.02, Tref = 37.0; };
-private:
+protected:
    const mfem::FiniteElementSpace &fes;
    Physics ph;
    b200pa_space sp = nullptr;
-   b200pa_form fA = nullptr, fK = nullptr;
+   b200pa_form fA = nullptr, fK = nullptr, fE = nullptr;
    mutable DeviceBuffer dT, dk, drhs, dz, dlf, dkq, dkq_dt, dsrc, dcm, diag, dinv, dess;
+   // RF part: sigma(T) q-data, potential, its Dirichlet data (uploaded once), eliminated RHS, Joule source q-data
+   mutable DeviceBuffer dsq, dphi, dphi_bc, dBe, dsrcq, dinvE, dessE;
+   bool rf = false;
+   double s0 = 0.3, as = 0.015;
+   int n_essE = 0;
    long long nq = 0;
-   double rel_tol = 1e-8, abs_tol = 0.0;
-   int max_iter = 500;
-   mutable b200pa_pcg_result res{};
-   mutable int total_iters = 0;
+   double rel_tol = 1e-8, abs_tol = 0.0, rel_tol_e = 1e-8;
+   int max_iter = 500, max_iter_e = 500;
+   mutable b200pa_pcg_result res{}, resE{};
+   mutable int total_iters = 0, total_iters_e = 0;
 public:
    BioheatOperator(const mfem::FiniteElementSpace &fes_, const Physics &p, bool factorised = false)
       : mfem::TimeDependentOperator(fes_.GetVSize(), 0.0, mfem::TimeDependentOperator::IMPLICIT), fes(fes_), ph(p)
@@ -382,10 +519,12 @@ public:
       Check(b200pa_space_set_geometry(sp, ir->GetWeights().HostRead(), geom->J.HostRead(), geom->detJ.HostRead()));
       Check(b200pa_form_create(sp, &fA));
       Check(b200pa_form_create(sp, &fK));
+      Check(b200pa_form_create(sp, &fE));
       if (factorised && b200pa_space_is_affine(sp) == 1)
       {
          Check(b200pa_form_set_factorised(fA, 1));
          Check(b200pa_form_set_factorised(fK, 1));
+         Check(b200pa_form_set_factorised(fE, 1));
       }
       Check(b200pa_form_set_essential(fA, 0, nullptr));
       Check(b200pa_form_set_essential(fK, 0, nullptr));
@@ -400,28 +539,65 @@ public:
       dsrc.Upload(&src, sizeof(double));
       Check(b200pa_space_domain_lf(sp, dsrc.D(), 1, dlf.D()));
    }
-   ~BioheatOperator() { b200pa_form_destroy(fA); b200pa_form_destroy(fK); b200pa_space_destroy(sp); }
+   ~BioheatOperator() { b200pa_form_destroy(fA); b200pa_form_destroy(fK); b200pa_form_destroy(fE); b200pa_space_destroy(sp); }
    void SetSolverOptions(double rtol, double atol, int maxit) { rel_tol = rtol; abs_tol = atol; max_iter = maxit; }
+
+   /// The RF field that heats the tissue: at every stage  div sigma(T) grad phi = 0,  phi = phi_bc on the essential dofs
+   /// (the electrodes), sigma(T) = s0 (1 + as (T - Tref)), and the heat source becomes q + sigma(T) |grad phi|^2 (Joule
+   /// heating: miniapps/electromagnetics/joule_solver.cpp:898-906).  phi_bc: an L-vector holding the Dirichlet values on
+   /// ess_tdofs (anything elsewhere); it is uploaded here, once - nothing crosses PCIe for phi inside the time loop.
+   void EnableRF(const mfem::Array<int> &ess_tdofs, const mfem::Vector &phi_bc, double sigma0, double a_sigma, double rtol_e = 1e-8,
+                 int maxit_e = 500)
+   {
+      rf = true; s0 = sigma0; as = a_sigma; rel_tol_e = rtol_e; max_iter_e = maxit_e;
+      n_essE = ess_tdofs.Size();
+      Check(b200pa_form_set_essential(fE, n_essE, ess_tdofs.HostRead()));
+      dessE.Resize(sizeof(int) * std::max(n_essE, 1));
+      if (n_essE) { dessE.Upload(ess_tdofs.HostRead(), sizeof(int) * n_essE); }
+      const size_t nb = sizeof(double) * height;
+      mfem::Vector bc(height);
+      bc = 0.0;
+      for (int i = 0; i < n_essE; i++) { bc[ess_tdofs[i]] = phi_bc[ess_tdofs[i]]; }
+      dphi_bc.Upload(bc.HostRead(), nb);
+      for (DeviceBuffer *b : {&dphi, &dBe, &dinvE}) { b->Resize(nb); }
+      dsq.Resize(sizeof(double) * nq); dsrcq.Resize(sizeof(double) * nq);
+   }
+   void SetRFSolverOptions(double rtol_e, int maxit_e) { rel_tol_e = rtol_e; max_iter_e = maxit_e; }
 
    /// dT = k solving the backward-Euler stage equation at T (TimeDependentOperator::ImplicitSolve, linalg/operator.hpp:343)
    void ImplicitSolve(const mfem::real_t dt, const mfem::Vector &T, mfem::Vector &dT_dt) override
    {
       const size_t nb = sizeof(double) * height;
       dT.Upload(T.HostRead(), nb);
+      if (rf)
+      {
+         // (1) electrostatics with sigma(T): q-data + Jacobi diagonal in one pass, EliminateRHS, PCG from the Dirichlet lift
+         Check(b200pa_space_coeff_linear(sp, s0, as, ph.Tref, dT.D(), dsq.D()));
+         Check(b200pa_form_assemble_diffusion_with_diagonal(fE, dsq.D(), nq, diag.D()));
+         Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), n_essE, dessE.I(), 1.0, dinvE.D()));
+         Check(b200pa_copy(Ctx(), height, dphi_bc.D(), dphi.D()));
+         Check(b200pa_memset(Ctx(), dBe.D(), 0, nb));
+         Check(b200pa_form_eliminate_rhs(fE, dphi.D(), dBe.D()));
+         Check(b200pa_pcg_solve(fE, dinvE.D(), dBe.D(), dphi.D(), rel_tol_e, 0.0, max_iter_e, &resE, nullptr));
+         total_iters_e += resE.final_iter;
+         // (2) Joule source at the q-points (grad phi never stored) and its load vector
+         Check(b200pa_space_joule(sp, dphi.D(), dsq.D(), ph.w * ph.Ta + ph.q, dsrcq.D()));
+         Check(b200pa_space_domain_lf(sp, dsrcq.D(), nq, dlf.D()));
+      }
       // k(T) at the quadrature points, once for K and once scaled by dt for the system operator
       Check(b200pa_space_coeff_linear(sp, ph.k0, ph.ak, ph.Tref, dT.D(), dkq.D()));
       Check(b200pa_space_coeff_linear(sp, dt * ph.k0, ph.ak, ph.Tref, dT.D(), dkq_dt.D()));
       Check(b200pa_form_assemble_diffusion(fK, dkq.D(), nq));
-      Check(b200pa_form_assemble_diffusion(fA, dkq_dt.D(), nq));
       const double cm = ph.rc + dt * ph.w;
       Check(b200pa_form_assemble_mass(fA, &cm, 1));
+      // system operator: q-data and Jacobi diagonal in one pass over the q-points
+      Check(b200pa_form_assemble_diffusion_with_diagonal(fA, dkq_dt.D(), nq, diag.D()));
       // rhs = (w Ta + q, v) - [K + M(w)] T
       Check(b200pa_form_mult(fK, dT.D(), dz.D()));
       Check(b200pa_add(Ctx(), height, dlf.D(), -1.0, dz.D(), drhs.D()));
       // Jacobi-PCG from a zero initial guess
-      Check(b200pa_form_assemble_diagonal(fA, diag.D()));
       Check(b200pa_jacobi_setup(Ctx(), height, diag.D(), 0, dess.I(), 1.0, dinv.D()));
-      Check(b200pa_add(Ctx(), height, drhs.D(), -1.0, drhs.D(), dk.D())); // dk = 0
+      Check(b200pa_memset(Ctx(), dk.D(), 0, nb));
       Check(b200pa_pcg_solve(fA, dinv.D(), drhs.D(), dk.D(), rel_tol, abs_tol, max_iter, &res, nullptr));
       total_iters += res.final_iter;
       dk.Download(dT_dt.HostWrite(), nb);
@@ -432,6 +608,25 @@ public:
    int TotalIterations() const { return total_iters; }
    bool LastConverged() const { return res.converged != 0; }
    bool Factorised() const { return b200pa_form_is_factorised(fA) == 1; }
+   /// RF: the potential of the last stage (downloaded on request), iteration counts of the potential solves
+   void GetPotential(mfem::Vector &phi) const { phi.SetSize(height); dphi.Download(phi.HostWrite(), sizeof(double) * height); }
+   int LastPotentialIterations() const { return resE.final_iter; }
+   int TotalPotentialIterations() const { return total_iters_e; }
+};
+
+/// The RF-ablation coupled problem (BASELINE configs[2]) as ONE TimeDependentOperator: every implicit stage solves the
+/// electrostatic problem with sigma(T), evaluates the Joule heat sigma |grad phi|^2 at the quadrature points and solves the
+/// bioheat stage with k(T) - all device-resident, stepped by the reference's ODE solvers.
+class RFCoupledOperator : public BioheatOperator
+{
+public:
+   struct RF { double s0 = 0.3, as = 0.015, rel_tol = 1e-8; int max_iter = 500; };
+   RFCoupledOperator(const mfem::FiniteElementSpace &fes_, const Physics &p, const RF &r, const mfem::Array<int> &ess_phi_tdofs,
+                     const mfem::Vector &phi_bc, bool factorised = false)
+      : BioheatOperator(fes_, p, factorised)
+   {
+      EnableRF(ess_phi_tdofs, phi_bc, r.s0, r.as, r.rel_tol, r.max_iter);
+   }
 };
 
 } // namespace b200

@@ -60,6 +60,8 @@ void *b200pa_ctx_stream(b200pa_ctx ctx);
 int b200pa_malloc(b200pa_ctx ctx, size_t bytes, void **out_dev);
 int b200pa_free(b200pa_ctx ctx, void *dev);
 int b200pa_memset(b200pa_ctx ctx, void *dev, int value, size_t bytes);
+/* device-to-device copy of n doubles on the context's stream (Vector::operator=, linalg/vector.cpp:203-240) */
+int b200pa_copy(b200pa_ctx ctx, long long n, const double *src_dev, double *dst_dev);
 /* synchronous copies on the context's stream (≙ Vector::HostRead / Vector::Write of a device vector) */
 int b200pa_ctx_upload(b200pa_ctx ctx, void *dst_dev, const void *src_host, size_t bytes);
 int b200pa_ctx_download(b200pa_ctx ctx, void *dst_host, const void *src_dev, size_t bytes);
@@ -190,6 +192,20 @@ const double *b200pa_form_pa_mass(b200pa_form f);
  * fail, loudly, when b200pa_space_is_affine() is not 1.  Results agree with the stored form to rounding. */
 int b200pa_form_set_factorised(b200pa_form f, int on);
 int b200pa_form_is_factorised(b200pa_form f);
+/* Element-attribute markers: BilinearForm::AddDomainIntegrator(bfi, elem_marker) (fem/bilinearform.hpp; multi-material
+ * domains: tissue / blood / electrode).  b200pa_space_set_attributes: Mesh::GetAttribute(e), one int >= 1 per element
+ * (host or device).  b200pa_form_set_markers(which = 0 diffusion | 1 mass): marker[a-1] != 0 <=> the integrator acts
+ * on the elements of attribute a (n_attr >= the largest attribute); marker = NULL removes it (re-assemble afterwards).
+ *   apply     PABilinearFormExtension::AddMultWithMarkers (fem/bilinearform_ext.cpp:807-847): the element
+ *             contributions of excluded elements are left out of the sum - here the integrator's q-data is zeroed on
+ *             them at assembly, so the hot kernel is unchanged and those contributions are exactly 0;
+ *   diagonal  PABilinearFormExtension::AssembleDiagonal (:370-454) zeroes, after EVERY integrator, the accumulated
+ *             element diagonal of the elements that integrator's marker excludes - including what EARLIER integrators
+ *             added there.  The form's integrator order is diffusion, then mass (as b200::PAOperator adds them), and
+ *             this order dependence is reproduced: an element the MASS marker excludes has a zero element diagonal.
+ * Markers need q-data assembled by the library (not b200pa_form_set_pa_data). */
+int b200pa_space_set_attributes(b200pa_space sp, const int *attr_any);
+int b200pa_form_set_markers(b200pa_form f, int which, int n_attr, const int *marker_host);
 /* ConstrainedOperator ctor (linalg/operator.cpp:511-526): essential true-dof list, DIAG_ONE */
 int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *ess_any);
 /* PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487-564): y = A x, L→L, unconstrained.
@@ -204,6 +220,13 @@ int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_d
 int b200pa_form_mult_host(b200pa_form f, int constrained, const double *x_host, double *y_host);
 /* PABilinearFormExtension::AssembleDiagonal (fem/bilinearform_ext.cpp:370-454) */
 int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev);
+/* DiffusionIntegrator::AssemblePA (fem/integ/bilininteg_diffusion_pa.cpp:89-142) + the form's AssembleDiagonal
+ * (fem/bilinearform_ext.cpp:370-454) in ONE pass over the q-points - what every implicit step with k(T) needs.
+ * On a mesh of affine elements (b200pa_space_is_affine) the kernel forms
+ * W C per q-point, writes the integrator's q-data from it and takes the diagonal from the same values (the q-data
+ * is never read back); the mass integrator is used as currently assembled.  Elsewhere it is
+ * b200pa_form_assemble_diffusion followed by b200pa_form_assemble_diagonal.  Same results either way. */
+int b200pa_form_assemble_diffusion_with_diagonal(b200pa_form f, const double *C_any, long long nc, double *diag_dev);
 /* ConstrainedOperator::EliminateRHS (linalg/operator.cpp:559-584): b -= A w; b[ess] = x[ess] */
 int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, double *b_dev);
 

@@ -686,6 +686,87 @@ static int check_inline(const char *path)
    return same ? 0 : 1;
 }
 
+// --------------------------------------------------------------- dump_markers
+// dump_markers OUT p kind nx ny nz: element-attribute markers (BilinearForm::AddDomainIntegrator(bfi, elem_marker),
+// PABilinearFormExtension::AddMultWithMarkers / AssembleDiagonal, fem/bilinearform_ext.cpp:370-454, 807-847) on a
+// three-material mesh (attribute 1 + e % 3).  Marker combinations k = 0..3, each with y = A x and the diagonal.
+static int dump_markers(int argc, char **argv)
+{
+   if (argc < 8) { cerr << "dump_markers OUT p kind nx ny nz\n"; return 2; }
+   Dumper D(argv[2]);
+   const int p = atoi(argv[3]);
+   const string kind = argv[4];
+   const int nx = atoi(argv[5]), ny = atoi(argv[6]), nz = atoi(argv[7]);
+   Device device("cpu");
+   Mesh mesh = make_mesh(kind, nx, ny, nz, 1.0, 1.0, 1.0);
+   for (int e = 0; e < mesh.GetNE(); e++) { mesh.SetAttribute(e, 1 + e % 3); }
+   mesh.SetAttributes();
+   H1_FECollection fec(p, 3);
+   FiniteElementSpace fes(&mesh, &fec);
+   const FiniteElement &el = *fes.GetTypicalFE();
+   const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+   const DofToQuad &maps = el.GetDofToQuad(ir, DofToQuad::TENSOR);
+   const int NE = mesh.GetNE(), ND = fes.GetNDofs();
+   D.iscalar("p", p); D.iscalar("D1D", maps.ndof); D.iscalar("Q1D", maps.nqpt); D.iscalar("NE", NE); D.iscalar("ndofs", ND);
+   D.arr("B", maps.B); D.arr("G", maps.G); D.arr("W", ir.GetWeights());
+   const ElementRestriction *R = dynamic_cast<const ElementRestriction *>(fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.arr("gather_map", R->GatherMap());
+   const GeometricFactors *geom = mesh.GetGeometricFactors(ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS);
+   D.vec("J", geom->J); D.vec("detJ", geom->detJ);
+   {
+      Vector vx(3 * mesh.GetNV());
+      for (int i = 0; i < mesh.GetNV(); i++) { for (int d = 0; d < 3; d++) { vx(3 * i + d) = mesh.GetVertex(i)[d]; } }
+      D.vec("vertices", vx);
+      Array<int> ev(8 * NE), at(NE);
+      for (int e = 0; e < NE; e++)
+      {
+         const int *v = mesh.GetElement(e)->GetVertices();
+         for (int j = 0; j < 8; j++) { ev[8 * e + j] = v[j]; }
+         at[e] = mesh.GetAttribute(e);
+      }
+      D.arr("elem_vertices", ev); D.arr("elem_attr", at);
+   }
+   QuadratureSpace qs(mesh, ir);
+   FunctionCoefficient kc(kfun), mc(mfun);
+   CoefficientVector kq(kc, qs, CoefficientStorage::COMPRESSED), mq(mc, qs, CoefficientStorage::COMPRESSED);
+   D.vec("kq", kq); D.vec("mq", mq);
+   Vector x(ND); x.Randomize(1);
+   D.vec("x", x);
+   // marker combinations: -1 = the integrator has no marker
+   const int combos[4][2][3] = {{{1, 1, 0}, {1, 0, 1}}, {{-1, -1, -1}, {0, 1, 0}}, {{1, 0, 1}, {-1, -1, -1}}, {{0, 1, 1}, {1, 1, 0}}};
+   for (int k = 0; k < 4; k++)
+   {
+      Array<int> md(3), mm(3);
+      for (int i = 0; i < 3; i++) { md[i] = combos[k][0][i]; mm[i] = combos[k][1][i]; }
+      const bool has_d = md[0] >= 0, has_m = mm[0] >= 0;
+      BilinearForm a(&fes);
+      a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      if (has_d) { a.AddDomainIntegrator(new DiffusionIntegrator(kc), md); } else { a.AddDomainIntegrator(new DiffusionIntegrator(kc)); }
+      if (has_m) { a.AddDomainIntegrator(new MassIntegrator(mc), mm); } else { a.AddDomainIntegrator(new MassIntegrator(mc)); }
+      a.Assemble();
+      Vector y(ND), diag(ND);
+      a.Mult(x, y);
+      a.AssembleDiagonal(diag);
+      const string tag = to_string(k);
+      D.arr("marker_diff" + tag, md); D.arr("marker_mass" + tag, mm);
+      D.vec("y" + tag, y); D.vec("diag" + tag, diag);
+      // the same against the reference's own full assembly (its test: tests/unit/fem/test_pa_kernels.cpp:696-750)
+      BilinearForm fa(&fes);
+      if (has_d) { fa.AddDomainIntegrator(new DiffusionIntegrator(kc), md); } else { fa.AddDomainIntegrator(new DiffusionIntegrator(kc)); }
+      if (has_m) { fa.AddDomainIntegrator(new MassIntegrator(mc), mm); } else { fa.AddDomainIntegrator(new MassIntegrator(mc)); }
+      fa.Assemble(); fa.Finalize();
+      Vector yf(ND), df(ND);
+      fa.Mult(x, yf);
+      fa.SpMat().GetDiag(df);
+      yf -= y; df -= diag;
+      cout << "markers " << k << ": |y_fa - y_pa| = " << yf.Normlinf() << "  |diag_fa - diag_pa| = " << df.Normlinf()
+           << "  min diag_pa = " << diag.Min() << endl;
+      D.scalar("diag_fa_minus_pa" + tag, df.Normlinf());
+   }
+   cout << "dump_markers ok: p=" << p << " NE=" << NE << " ndofs=" << ND << endl;
+   return 0;
+}
+
 // ------------------------------------------------------------------ load_check
 // The reference loading the product's wire formats: Mesh(file) + GridFunction(mesh, file); dumps what it sees so that
 // tests/test_wire_formats.py can compare with the builder (numbering, boundary attributes, values, an L2 norm).
@@ -731,6 +812,7 @@ int main(int argc, char **argv)
    if (cmd == "dump_bioheat_steps") { return bioheat_steps(argc, argv); }
    if (cmd == "time_apply") { return time_apply(argc, argv); }
    if (cmd == "load_check") { return load_check(argc, argv); }
+   if (cmd == "dump_markers") { return dump_markers(argc, argv); }
    if (cmd == "ex1") { return ex1(argc, argv); }
    if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }
    cerr << "usage: ref_driver dump_case|dump_bioheat|time_bioheat|time_apply|ex1|--check-inline ...\n";

@@ -13,6 +13,7 @@ Fixtures (all float64 / int32, reference layouts):
   numbering.npz       gather_map / ndofs for many (nx,ny,nz,p): pins the product-side hex builder
   bioheat_p2_n4.npz   the RF + bioheat coupled step of SURVEY §3.2/3.3 on a 4^3 mesh
   bioheat_steps_p2_n4.npz   three consecutive coupled steps (T^{n+1} feeds k(T), sigma(T) of the next one)
+  markers_<tag>.npz   element-attribute markers: y = A x and the diagonal for four marker combinations (`dump_markers`)
 """
 import os
 import subprocess
@@ -62,6 +63,14 @@ NUMBERING = [(1, 1, 1), (2, 2, 2), (3, 3, 3), (4, 3, 2), (2, 5, 3), (5, 5, 5), (
              (8, 8, 8), (7, 2, 9)]
 
 
+def markers():
+    """element-attribute markers (three-material meshes, four marker combinations): markers_<tag>.npz"""
+    for tag, c in {"p2_skew332": (2, "skew", 3, 3, 2), "p3_cart232": (3, "cart", 2, 3, 2), "p1_skew433": (1, "skew", 4, 3, 3)}.items():
+        d = run(["dump_markers"] + list(c))
+        np.savez_compressed(os.path.join(HERE, f"markers_{tag}.npz"), **d)
+        print("markers", tag, sum(v.nbytes for v in d.values()) // 1024, "KiB raw")
+
+
 def main():
     if not os.path.exists(DRIVER):
         sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle ref` in the build container")
@@ -85,8 +94,12 @@ def main():
     np.savez_compressed(os.path.join(HERE, "bioheat_p2_n4.npz"), **d)
     d = run(["dump_bioheat_steps", 2, 4, 12, 3])
     np.savez_compressed(os.path.join(HERE, "bioheat_steps_p2_n4.npz"), **d)
+    markers()
     print("done")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "markers":   # only the fixtures added in round 2
+        markers()
+    else:
+        main()

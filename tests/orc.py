@@ -223,3 +223,42 @@ def domain_lf(NE, D1D, Q1D, B, detJ, W, f):
     f = f64(f)
     lib().orc_domain_lf(NE, D1D, Q1D, dp(f64(B)), dp(f64(detJ)), dp(f64(W)), dp(f), C.c_long(f.size), dp(b))
     return b
+
+
+# ---- element-attribute markers: the reference's orchestration restated over the element-level functions above
+def _marked(attr, marker):
+    attr = np.asarray(attr)
+    mk = np.asarray(marker)
+    return (attr > 0) & (mk[np.maximum(attr, 1) - 1] != 0)
+
+
+def op_mult_markers(op, x, attr, marker_diff, marker_mass):
+    """PABilinearFormExtension::MultInternal with AddMultWithMarkers (fem/bilinearform_ext.cpp:528-556, 807-847):
+    every integrator's E-vector result is added for the elements its marker includes (None = all)"""
+    nd = op.nd
+    xE = restrict_mult(op.NE, nd, op.gather_map, x)
+    yE = np.zeros(op.NE * nd)
+    for pa, marker, fn in ((op.pa_diff, marker_diff, lambda v: diffusion_apply(op.NE, op.D1D, op.Q1D, op.B, op.G, op.pa_diff, v)),
+                           (op.pa_mass, marker_mass, lambda v: mass_apply(op.NE, op.D1D, op.Q1D, op.B, op.pa_mass, v))):
+        if pa is None:
+            continue
+        tmp = fn(xE)
+        if marker is not None:
+            tmp = tmp.reshape(op.NE, nd) * _marked(attr, marker)[:, None]
+        yE += tmp.ravel()
+    return restrict_mult_transpose(op.ndofs, op.offsets, op.indices, yE)
+
+
+def op_diag_markers(op, attr, marker_diff, marker_mass):
+    """PABilinearFormExtension::AssembleDiagonal (fem/bilinearform_ext.cpp:370-423): after every integrator the
+    accumulated element diagonal of the elements its marker excludes is set to zero (earlier integrators included)"""
+    nd = op.nd
+    dE = np.zeros(op.NE * nd)
+    for pa, marker, fn in ((op.pa_diff, marker_diff, lambda: diffusion_diag(op.NE, op.D1D, op.Q1D, op.B, op.G, op.pa_diff)),
+                           (op.pa_mass, marker_mass, lambda: mass_diag(op.NE, op.D1D, op.Q1D, op.B, op.pa_mass))):
+        if pa is None:
+            continue
+        dE += fn()
+        if marker is not None:
+            dE = (dE.reshape(op.NE, nd) * _marked(attr, marker)[:, None]).ravel()
+    return restrict_mult_transpose(op.ndofs, op.offsets, op.indices, dE, abs_=True)

@@ -122,3 +122,102 @@ def test_non_affine_mesh_is_refused(ctx):
     assert np.max(np.abs(y)) < 1e-12        # constants are in the kernel of the diffusion operator
     f.close()
     sp.close()
+
+
+# ---------------------------------------------------------------- fused q-data set-up + diagonal (one pass)
+def _pa_diff_host(ctx, f, n):
+    import ctypes as C
+    out = np.empty(n)
+    p = b200pa.lib().b200pa_form_pa_diff(f.h)
+    b200pa.check(b200pa.lib().b200pa_ctx_download(ctx.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(p), C.c_size_t(out.nbytes)))
+    return out
+
+
+@pytest.mark.parametrize("fact", [False, True])
+def test_fused_setup_diagonal_matches_reference(ctx, dev, fact):
+    """b200pa_form_assemble_diffusion_with_diagonal on the golden meshes (all affine, geometry from the vertices):
+    q-data and diagonal against the reference's pa_data / diagonal, and bit-identical to the two-pass route"""
+    c = dev.c
+    sp = dev.space(geometry="vertices")
+    f = b200pa.Form(sp)
+    f.set_factorised(fact)
+    f.assemble_mass(c["mq"])
+    f.set_essential(None)
+    diag = ctx.to_host(f.assemble_diffusion_with_diagonal(c["kq"]))
+    assert f.factorised == fact
+    close(diag, c["diag"])
+    close(ctx.to_host(f.mult(dev["x"])), c["y"])
+    g = b200pa.Form(sp)
+    g.set_factorised(fact)
+    g.assemble_diffusion(c["kq"])
+    g.assemble_mass(c["mq"])
+    g.set_essential(None)
+    nq = dev.NE * dev.Q ** 3
+    n = nq if fact else 6 * nq
+    assert np.array_equal(_pa_diff_host(ctx, f, n), _pa_diff_host(ctx, g, n))
+    assert np.array_equal(diag, ctx.to_host(g.assemble_diagonal()))
+    if not fact:
+        close(_pa_diff_host(ctx, f, n), c["pa_diff"])
+    f.close()
+    g.close()
+    sp.close()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("const_c", [False, True])
+def test_fused_setup_diagonal_on_slab(ctx, p, const_c):
+    """tail batches and odd element counts (the scalar fields then start on odd 8-byte boundaries), q-function and constant
+    coefficients, diffusion alone and with mass; fused == two passes, bit for bit, and reproducible"""
+    dims = (7, 5, 3)
+    m = b200pa.hex_build(*dims, p, sx=2.0, sy=1.0, sz=0.25)
+    b = b200pa.basis(p)
+    sp = b200pa.Space(ctx, p + 1, p + 2, m["ne"], m["ndofs"], m["gather_map"], b["B"], b["G"])
+    sp.geometry_from_vertices(b["W"], m["vertices"], m["elem_vertices"])
+    rng = np.random.default_rng(10 + p)
+    nq = m["ne"] * (p + 2) ** 3
+    kq = np.array([0.7]) if const_c else 0.5 + rng.random(nq)
+    mq = 3.0 + rng.random(nq)
+    for mass in (True, False):
+        for fact in (False, True):
+            f, g = b200pa.Form(sp), b200pa.Form(sp)
+            for h in (f, g):
+                h.set_factorised(fact)
+                if mass:
+                    h.assemble_mass(mq)
+                h.set_essential(None)
+            d1 = ctx.to_host(f.assemble_diffusion_with_diagonal(kq))
+            d1b = ctx.to_host(f.assemble_diffusion_with_diagonal(kq))
+            g.assemble_diffusion(kq)
+            d2 = ctx.to_host(g.assemble_diagonal())
+            n = nq if fact else 6 * nq
+            assert np.array_equal(_pa_diff_host(ctx, f, n), _pa_diff_host(ctx, g, n))
+            assert np.array_equal(d1, d2) and np.array_equal(d1, d1b)
+            x = ctx.to_dev(rng.random(m["ndofs"]))
+            assert np.array_equal(ctx.to_host(f.mult(x)), ctx.to_host(g.mult(x)))
+            f.close()
+            g.close()
+    sp.close()
+
+
+def test_fused_setup_diagonal_falls_back_on_skewed_mesh(ctx):
+    """a mesh with non-affine elements takes the two-pass route: same results as calling the two entry points"""
+    p = 2
+    m = b200pa.hex_build(4, 3, 3, p)
+    b = b200pa.basis(p)
+    v = m["vertices"].copy().reshape(-1, 3)
+    v[21] += [0.03, -0.02, 0.01]
+    sp = b200pa.Space(ctx, p + 1, p + 2, m["ne"], m["ndofs"], m["gather_map"], b["B"], b["G"])
+    sp.geometry_from_vertices(b["W"], v.ravel(), m["elem_vertices"])
+    assert not sp.affine
+    rng = np.random.default_rng(5)
+    kq = 0.5 + rng.random(m["ne"] * 64)
+    f, g = b200pa.Form(sp), b200pa.Form(sp)
+    for h in (f, g):
+        h.assemble_mass(np.array([2.0]))
+        h.set_essential(None)
+    d1 = ctx.to_host(f.assemble_diffusion_with_diagonal(kq))
+    g.assemble_diffusion(kq)
+    assert np.array_equal(d1, ctx.to_host(g.assemble_diagonal()))
+    f.close()
+    g.close()
+    sp.close()

@@ -58,3 +58,29 @@ def test_bioheat_time_stepping_through_mfem_ode_solver(p, n):
     for r in recs:
         assert r["ok"] and r["T_rel_diff_fixed_iters"] <= 1e-10
         assert abs(r["iters_ref"] - r["iters_gpu"]) <= 3
+
+
+@pytest.mark.parametrize("p,n", [(2, 4), (3, 3), (1, 5)])
+def test_iterative_solver_surface_and_markers(p, n):
+    """b200::PCGSolver handed to code that only knows mfem::IterativeSolver (SetPreconditioner / SetOperator / SetMonitor /
+    PrintLevel): same iteration counts, recorded (B r, r) history, printed lines and norms as mfem::CGSolver with
+    OperatorJacobiSmoother, and as plain CG without a preconditioner; element-attribute markers through
+    b200::PAOperator against BilinearForm::AddDomainIntegrator(bfi, marker) on a three-material mesh"""
+    r = run(["surface", p, n])[0]
+    assert r["ok"]
+    assert max(r["markers"].values()) <= 1e-12
+    s = r["iterative_solver"]
+    assert abs(s["iters_ref"] - s["iters_gpu"]) <= 1 and s["monitor_norms"] <= 1e-9
+    assert abs(r["plain_cg"]["iters_ref"] - r["plain_cg"]["iters_gpu"]) <= 1
+
+
+@pytest.mark.parametrize("p,n", [(2, 4), (3, 3)])
+def test_rf_coupled_operator_through_mfem_ode_solver(p, n):
+    """BASELINE configs[2] behind the C++ surface: b200::RFCoupledOperator (electrostatics with sigma(T) + Joule heat +
+    bioheat stage, device-resident) stepped by mfem::BackwardEulerSolver against the same composition written with the
+    reference's own PA forms, solvers and q-point interpolators; stored and factorised q-data"""
+    recs = run(["rf", p, n, 2])
+    assert len(recs) == 2 and {bool(r["factorised"]) for r in recs} == {False, True}
+    for r in recs:
+        assert r["ok"] and r["T_rel_diff_fixed_iters"] <= 1e-9 and r["phi_rel_diff"] <= 1e-8
+        assert abs(r["iters_T_ref"] - r["iters_T_gpu"]) <= 2 and abs(r["iters_phi_ref"] - r["iters_phi_gpu"]) <= 2
