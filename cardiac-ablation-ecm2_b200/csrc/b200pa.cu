@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <utility>
 
 #include "common.cuh"
 #include "elem_launch.cuh"
@@ -104,11 +106,11 @@ struct DiagArgs
    const unsigned char *diff_off = nullptr;
 };
 
-template <int D1, int Q1, bool SLOT, bool FUSED>
+template <int D1, int Q1, bool SLOT, int QMODE>
 static void launch_diag_t(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const DiagArgs &a)
 {
    using C = DiagSfCfg<D1, Q1>;
-   auto kern = k_diag_sf<D1, Q1, SLOT, FUSED>;
+   auto kern = k_diag_sf<D1, Q1, SLOT, QMODE>;
    // the opt-in is per device (a process may hold contexts on several): remembered per device, set-once races are benign
    static std::atomic<int> per_sm[MAX_DEVICES];
    const int dev = ctx->device;
@@ -134,9 +136,10 @@ static void launch_diag_t(b200pa_ctx ctx, long long ne, const double *hB, const 
 template <int D1, int Q1>
 static void launch_diag(b200pa_ctx ctx, long long ne, const double *hB, const double *hG, const DiagArgs &a)
 {
-   if (a.pa_out) { launch_diag_t<D1, Q1, true, true>(ctx, ne, hB, hG, a); }   // fused set-up always writes the slot layout
-   else if (a.slot) { launch_diag_t<D1, Q1, true, false>(ctx, ne, hB, hG, a); }
-   else { launch_diag_t<D1, Q1, false, false>(ctx, ne, hB, hG, a); }
+   if (a.pa_out) { launch_diag_t<D1, Q1, true, 2>(ctx, ne, hB, hG, a); }   // fused set-up always writes the slot layout
+   else if (a.slot && a.geo) { launch_diag_t<D1, Q1, true, 1>(ctx, ne, hB, hG, a); }
+   else if (a.slot) { launch_diag_t<D1, Q1, true, 0>(ctx, ne, hB, hG, a); }
+   else { launch_diag_t<D1, Q1, false, 0>(ctx, ne, hB, hG, a); }   // integrator-level entry points: stored q-data, E-vector
 }
 
 // hB, hG: HOST copies of the 1-D basis tables
@@ -147,6 +150,7 @@ static int run_diag(b200pa_ctx ctx, int d1d, int q1d, long long ne, const double
    const unsigned long long al = a.pa_out ? ((unsigned long long)a.pm | (a.const_c ? 0ull : (unsigned long long)a.pd)) : ((unsigned long long)a.pd | (unsigned long long)a.pm);
    B200PA_REQUIRE((al & 15ull) == 0, "pa_data must be 16-byte aligned (TMA bulk copies)");
    B200PA_REQUIRE(!a.pa_out || (a.slot && a.geo && a.W), "fused set-up + diagonal: slot layout, element tensors and weights are required");
+   B200PA_REQUIRE(!a.geo || a.slot, "diagonal of factorised q-data: slot-layout output only");
    switch (d1d)
    {
       case 2: launch_diag<2, 3>(ctx, ne, hB, hG, a); break;
@@ -183,6 +187,30 @@ struct b200pa_space_s
    bool affine = false;
    DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
    DevBuf attr;     // element attributes (Mesh::GetAttribute), int32[NE]; only needed by integrator markers
+   struct HostPipe *pipe = nullptr; // plan + streams of the pipelined host-buffer apply (b200pa_form_mult_host), built on first use
+};
+
+// Plan of the pipelined host-buffer apply.  Elements are cut into C chunks of consecutive elements (compact blobs of the
+// space-filling-curve order), L-dofs into tiles of TS consecutive dofs.  first[t] / last[t] = first / last chunk that
+// touches a dof of tile t: x-tile t must be on the device before chunk first[t] runs, y-tile t is final once chunk last[t]
+// is done.  H2D of the x tiles (in order of first use), the element kernel chunk by chunk, the segmented E->L reduction of
+// the tiles a chunk completes and their D2H run on three streams - PCIe is busy in both directions while the kernels run.
+struct HostPipe
+{
+   int C = 0, T = 0, TS = 0, cs = 0;
+   std::vector<std::vector<std::pair<int, int>>> up, down; // per chunk: merged dof ranges [i0, i1) to upload before / finalise after it
+   cudaStream_t s_up = nullptr, s_down = nullptr;
+   std::vector<cudaEvent_t> ev_up, ev_done;
+   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+   ~HostPipe()
+   {
+      for (cudaEvent_t e : ev_up) { cudaEventDestroy(e); }
+      for (cudaEvent_t e : ev_done) { cudaEventDestroy(e); }
+      if (ev_start) { cudaEventDestroy(ev_start); }
+      if (ev_end) { cudaEventDestroy(ev_end); }
+      if (s_up) { cudaStreamDestroy(s_up); }
+      if (s_down) { cudaStreamDestroy(s_down); }
+   }
 };
 
 struct b200pa_form_s
@@ -607,6 +635,7 @@ extern "C" int b200pa_space_destroy(b200pa_space sp)
    if (!sp) { return 0; }
    cudaSetDevice(sp->ctx->device);
    cudaStreamSynchronize(sp->ctx->stream);
+   delete sp->pipe;
    for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->jinv9, &sp->scratchE, &sp->attr})
    {
       b->release();
@@ -1189,12 +1218,144 @@ static int need_work(b200pa_form f)
    return alloc(f->w1, b) || alloc(f->w2, b);
 }
 
+// ---- pipelined host-buffer apply (one GPU): see HostPipe
+static int build_pipe(b200pa_space sp)
+{
+   if (sp->pipe) { return 0; }
+   b200pa_ctx ctx = sp->ctx;
+   HostPipe *hp = new HostPipe;
+   const long long ne = sp->ne, nd = sp->nd;
+   const int ndofs = sp->ndofs;
+   // chunk size: a multiple of 64 elements (every kernel's batch size divides it; scalar q-data fields stay 16-byte aligned)
+   int C = 16;
+   long long cs = ((ne + C - 1) / C + 63) / 64 * 64;
+   C = (int)((ne + cs - 1) / cs);
+   const int TS = 32768;
+   const int T = (ndofs + TS - 1) / TS;
+   hp->C = C; hp->T = T; hp->TS = TS; hp->cs = (int)cs;
+   std::vector<int> gm((size_t)(ne * nd));
+   B200PA_CK(cudaMemcpyAsync(gm.data(), sp->gmap.p, sizeof(int) * gm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   std::vector<int> first(T, C), last(T, -1);
+   for (long long e = 0; e < ne; ++e)
+   {
+      const int c = (int)(e / cs);
+      const int *g = gm.data() + e * nd;
+      for (int k = 0; k < nd; ++k)
+      {
+         const int t = g[k] / TS;
+         if (c < first[t]) { first[t] = c; }
+         if (c > last[t]) { last[t] = c; }
+      }
+   }
+   hp->up.assign(C, {}); hp->down.assign(C, {});
+   auto add = [&](std::vector<std::pair<int, int>> &v, int t)
+   {
+      const int i0 = t * TS, i1 = std::min(ndofs, (t + 1) * TS);
+      if (!v.empty() && v.back().second == i0) { v.back().second = i1; } else { v.emplace_back(i0, i1); }
+   };
+   for (int t = 0; t < T; ++t)
+   {
+      // a tile no element touches (cannot happen for a conforming space) still has to travel: first / last chunk
+      add(hp->up[first[t] < C ? first[t] : 0], t);
+      add(hp->down[last[t] >= 0 ? last[t] : C - 1], t);
+   }
+   B200PA_CK(cudaStreamCreateWithFlags(&hp->s_up, cudaStreamNonBlocking));
+   B200PA_CK(cudaStreamCreateWithFlags(&hp->s_down, cudaStreamNonBlocking));
+   hp->ev_up.resize(C); hp->ev_done.resize(C);
+   for (int c = 0; c < C; ++c)
+   {
+      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_up[c], cudaEventDisableTiming));
+      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_done[c], cudaEventDisableTiming));
+   }
+   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
+   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_end, cudaEventDisableTiming));
+   sp->pipe = hp;
+   return 0;
+}
+
+static int form_mult_host_pipelined(b200pa_form f, bool constrained, const double *x_host, double *y_host)
+{
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   if (build_pipe(sp)) { return 1; }
+   HostPipe &hp = *sp->pipe;
+   double *x = f->w1.as<double>(), *y = f->w2.as<double>();
+   const long long nd = sp->nd, q3 = (long long)sp->q1d * sp->q1d * sp->q1d;
+   cudaStream_t s = ctx->stream;
+   // the copy streams start after whatever the compute stream still has queued on w1 / w2 / the scratch
+   B200PA_CK(cudaEventRecord(hp.ev_start, s));
+   B200PA_CK(cudaStreamWaitEvent(hp.s_up, hp.ev_start, 0));
+   B200PA_CK(cudaStreamWaitEvent(hp.s_down, hp.ev_start, 0));
+   for (int c = 0; c < hp.C; ++c)
+   {
+      for (const auto &r : hp.up[c])
+      {
+         B200PA_CK(cudaMemcpyAsync(x + r.first, x_host + r.first, sizeof(double) * (size_t)(r.second - r.first), cudaMemcpyHostToDevice, hp.s_up));
+      }
+      B200PA_CK(cudaEventRecord(hp.ev_up[c], hp.s_up));
+   }
+   const int *gmap = constrained ? f->cgmap.as<int>() : sp->gmap.as<int>();
+   const int *off = sp->offsets.as<int>();
+   const double *yS = sp->scratchE.as<double>();
+   const unsigned char *em = f->ess_mask.as<unsigned char>();
+   for (int c = 0; c < hp.C; ++c)
+   {
+      const long long e0 = (long long)c * hp.cs;
+      const int nel = (int)std::min<long long>(hp.cs, sp->ne - e0);
+      B200PA_CK(cudaStreamWaitEvent(s, hp.ev_up[c], 0));
+      ElemArgs a = space_args(sp);
+      a.NE = nel; a.x = x; a.gmap = gmap + e0 * nd; a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>() + e0 * nd;
+      a.pa_diff = f->has_diff ? f->pa_diff.as<double>() + e0 * (f->factorised ? q3 : 6 * q3) : nullptr;
+      a.pa_mass = f->has_mass ? f->pa_mass.as<double>() + e0 * q3 : nullptr;
+      a.geo = (f->has_diff && f->factorised) ? sp->geo6.as<double>() + e0 * 6 : nullptr;
+      if (run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
+      for (const auto &r : hp.down[c])
+      {
+         const int n = r.second - r.first;
+         const int grid = grid1d(ctx, n);
+         if (constrained)
+         {
+            k_segment_sum<true, false, false><<<grid, 256, 0, s>>>(n, off + r.first, yS, y + r.first, em + r.first, x + r.first, nullptr, nullptr, nullptr, nullptr, nullptr);
+         }
+         else
+         {
+            k_segment_sum<false, false, false><<<grid, 256, 0, s>>>(n, off + r.first, yS, y + r.first, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+         }
+         B200PA_LAUNCHED();
+      }
+      B200PA_CK(cudaEventRecord(hp.ev_done[c], s));
+   }
+   for (int c = 0; c < hp.C; ++c)
+   {
+      B200PA_CK(cudaStreamWaitEvent(hp.s_down, hp.ev_done[c], 0));
+      for (const auto &r : hp.down[c])
+      {
+         B200PA_CK(cudaMemcpyAsync(y_host + r.first, y + r.first, sizeof(double) * (size_t)(r.second - r.first), cudaMemcpyDeviceToHost, hp.s_down));
+      }
+   }
+   // the compute stream continues only after the last tile has left (w2 may be reused by the next call)
+   B200PA_CK(cudaEventRecord(hp.ev_end, hp.s_down));
+   B200PA_CK(cudaStreamWaitEvent(s, hp.ev_end, 0));
+   B200PA_CK(cudaStreamSynchronize(hp.s_down));
+   B200PA_CK(cudaStreamSynchronize(s));
+   return 0;
+}
+
 extern "C" int b200pa_form_mult_host(b200pa_form f, int constrained, const double *x_host, double *y_host)
 {
    B200PA_REQUIRE(f && x_host && y_host, "form_mult_host: NULL argument");
    b200pa_ctx ctx = f->sp->ctx;
    NEED_CTX(ctx);
    if (need_work(f)) { return 1; }
+   B200PA_REQUIRE(f->has_diff || f->has_mass, "form has no assembled integrator");
+   if (constrained) { B200PA_REQUIRE(f->cgmap.p, "form has no essential-dof list (call b200pa_form_set_essential, n_ess may be 0)"); }
+   // one GPU and a problem large enough to be worth three streams: H2D, kernels and D2H overlap tile by tile
+   static const bool no_pipe = getenv("B200PA_NO_PIPELINE") != nullptr;
+   if (!f->comm && !no_pipe && f->sp->ndofs >= (1 << 20) && f->sp->ne >= 4096)
+   {
+      return form_mult_host_pipelined(f, constrained != 0, x_host, y_host);
+   }
    const size_t b = sizeof(double) * (size_t)f->sp->ndofs;
    B200PA_CK(cudaMemcpyAsync(f->w1.p, x_host, b, cudaMemcpyHostToDevice, ctx->stream));
    if (form_apply(f, f->w1.as<double>(), f->w2.as<double>(), constrained != 0, nullptr, nullptr)) { return 1; }

@@ -388,7 +388,7 @@ __global__ void k_coeff_eval(int kind, long long n, double a, double b, double T
 // and takes the diagonal from the same registers - PADiffusionSetup3D and the diagonal in one pass over the q-points
 // (an implicit time step re-assembles both at every step: 3.6 GB of q-data are then never read back for the diagonal).
 #ifndef B200PA_TUNE_DIAG_KB
-#define B200PA_TUNE_DIAG_KB 64
+#define B200PA_TUNE_DIAG_KB 44
 #endif
 // smallest s >= lo with s = r (mod 16): 16 consecutive lanes (one 128-byte shared-memory wavefront of doubles) whose
 // addresses advance by `r` per outer index and by 1 per inner index then fall into 16 different banks
@@ -451,10 +451,13 @@ struct DiagParams
    const unsigned char *__restrict__ diff_off;
 };
 
-template <int D1, int Q1, bool SLOT, bool FUSED>
+// QMODE: 0 = stored diffusion q-data (six components per q-point), 1 = factorised (one scalar per q-point + geo),
+//        2 = FUSED (raw coefficient staged, q-data written by the kernel)
+template <int D1, int Q1, bool SLOT, int QMODE>
 __global__ void __launch_bounds__(DiagSfCfg<D1, Q1>::NT)
 k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 {
+   constexpr bool FUSED = (QMODE == 2);
    using C = DiagSfCfg<D1, Q1>;
    constexpr int D2 = D1 * D1, D3 = D1 * D1 * D1, Q2 = C::Q2, Q3 = C::Q3, NF = C::NF, NEB = C::NEB;
    constexpr int S1 = C::S1, F1 = C::F1, T1E = C::T1E, R2 = C::R2, S2 = C::S2, F2 = C::F2, T2E = C::T2E;
@@ -465,7 +468,7 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
    const long long NE = P.NE;
    const double *pa_diff = P.pa_diff, *pa_mass = P.pa_mass;
    const double *geo = P.geo;
-   const bool scalar_diff = FUSED || geo != nullptr; // the diffusion field is one scalar per q-point
+   constexpr bool scalar_diff = (QMODE != 0);        // the diffusion field is one scalar per q-point
    const bool stage_diff = pa_diff != nullptr && !(FUSED && P.const_c);
    if (threadIdx.x == 0) { mbar_init(&qbar[0], 1); mbar_init(&qbar[1], 1); }
    if (FUSED) { for (int i = threadIdx.x; i < Q3; i += blockDim.x) { sW[i] = P.W[i]; } }
@@ -557,7 +560,7 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
 #pragma unroll
                for (int q = 0; q < Q1; ++q)
                {
-                  const double v = scale * src[q * Q2];
+                  const double v = (scalar_diff && f < 6) ? scale * src[q * Q2] : src[q * Q2];
 #pragma unroll
                   for (int d = 0; d < D1; ++d) { out[d] = fma(P.M[B200PA_MTYPE(f, 2)][q + Q1 * d], v, out[d]); }
                }
@@ -595,6 +598,15 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
       {
          const int e = t / C::TPE3, k = t - e * C::TPE3, dz = k / D1, dy = k - dz * D1;
          if (k >= D2) { continue; }
+         // slot indices first: their global-memory latency hides behind the contraction (ncu: 14 % of all stall samples
+         // sat on the address of the first store when they were loaded where they are used)
+         const long long o = (e0 + e) * D3 + k * D1;
+         int sl[D1];
+         if (SLOT)
+         {
+#pragma unroll
+            for (int dx = 0; dx < D1; ++dx) { sl[dx] = __ldg(P.slot + o + dx); }
+         }
          double acc[D1];
 #pragma unroll
          for (int d = 0; d < D1; ++d) { acc[d] = 0.0; }
@@ -610,11 +622,10 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
                for (int dx = 0; dx < D1; ++dx) { acc[dx] = fma(P.M[B200PA_MTYPE(f, 0)][qx + Q1 * dx], v, acc[dx]); }
             }
          }
-         const long long o = (e0 + e) * D3 + k * D1;
 #pragma unroll
          for (int dx = 0; dx < D1; ++dx)
          {
-            if (SLOT) { P.out[__ldg(P.slot + o + dx)] = acc[dx]; }
+            if (SLOT) { P.out[sl[dx]] = acc[dx]; }
             else { P.out[o + dx] += acc[dx]; }
          }
       }

@@ -332,7 +332,8 @@ static int surface_case(int p, int nx)
       mfem::out.SetStream(std::cout);
       double en = 0.0;
       for (size_t i = 0; i < min(r0.norms.size(), r2.norms.size()); i++) { en = max(en, fabs(r0.norms[i] - r2.norms[i]) / r0.norms[0]); }
-      const int l0 = (int)count(o0.str().begin(), o0.str().end(), '\n'), l2 = (int)count(o2.str().begin(), o2.str().end(), '\n');
+      const string s0 = o0.str(), s2 = o2.str();
+      const int l0 = (int)count(s0.begin(), s0.end(), '\n'), l2 = (int)count(s2.begin(), s2.end(), '\n');
       ok = ok && abs(i0 - i2) <= 1 && en <= 1e-9 && rel(Xb, Xa) <= 1e-7 && r2.finals == 1 && fabs(r2.x_norm - Xb.Norml2()) <= 1e-12 * Xb.Norml2() &&
            abs(l0 - l2) <= 1 && cg2.GetConverged() == cg0.GetConverged() && fabs(cg2.GetFinalNorm() - cg0.GetFinalNorm()) <= 1e-6 * cg0.GetInitialNorm() &&
            fabs(cg2.GetInitialNorm() - cg0.GetInitialNorm()) <= 1e-10 * cg0.GetInitialNorm();

@@ -354,3 +354,39 @@ def test_chebyshev_smoother_and_pcg(ctx, dev):
         f.chebyshev_mult(dinv, 6, lam_ref, dev["x"])
     f.close()
     sp.close()
+
+
+@pytest.mark.parametrize("p,n", [(1, 104), (2, 52), (3, 35), (5, 21)])
+def test_mult_host_pipelined_equals_device_apply(ctx, p, n):
+    """b200pa_form_mult_host on a problem large enough for its pipelined route (x tiles up, element chunks, E->L reduction
+    of the tiles a chunk completes, y tiles down - three streams): bit-identical to the device-resident apply, constrained
+    and unconstrained, stored and factorised q-data, repeated calls, and equal to the serial route (B200PA_NO_PIPELINE)"""
+    import torch
+    m = b200pa.hex_build(n, n, n, p, sx=1.0, sy=0.8, sz=0.6)
+    b = b200pa.basis(p)
+    assert m["ndofs"] >= 1 << 20
+    sp = b200pa.Space(ctx, p + 1, p + 2, m["ne"], m["ndofs"], m["gather_map"], b["B"], b["G"])
+    sp.geometry_from_vertices(b["W"], m["vertices"], m["elem_vertices"])
+    rng = np.random.default_rng(p)
+    nq = m["ne"] * (p + 2) ** 3
+    kq, mq = 0.5 + rng.random(nq), 3.0 + rng.random(nq)
+    xh = rng.random(m["ndofs"])
+    xp = torch.from_numpy(xh).pin_memory()
+    x = ctx.to_dev(xh)
+    for fact in (False, True):
+        f = b200pa.Form(sp)
+        f.set_factorised(fact)
+        f.assemble_diffusion(kq)
+        f.assemble_mass(mq)
+        f.set_essential(b200pa.essential_dofs(m["bdr_attr"], [1, 6]))
+        for constrained in (False, True):
+            yd = ctx.to_host(f.constrained_mult(x) if constrained else f.mult(x))
+            for _ in range(2):
+                yp = torch.full((m["ndofs"],), np.nan, dtype=torch.float64).pin_memory()
+                f.mult_host(xp, yp, constrained=constrained)
+                assert np.array_equal(yp.numpy(), yd)
+            yh = np.full(m["ndofs"], np.nan)     # pageable host memory works too (copies just do not overlap)
+            f.mult_host(xh, yh, constrained=constrained)
+            assert np.array_equal(yh, yd)
+        f.close()
+    sp.close()
