@@ -184,6 +184,7 @@ struct b200pa_space_s
    // factorised diffusion q-data (affine elements only): adj(J)adj(J)^T/det J per element; affine = every element
    // is a parallelepiped to 1e-13 of its edge lengths (decided on the device by k_affine_geometry)
    DevBuf geo6, jinv9; // jinv9: rows of J^{-T} per element (q-point gradients on affine meshes)
+   DevBuf detE;        // affine mesh from vertices: det J per element; detJ per q-point is then only built on request
    bool affine = false;
    DevBuf scratchE; // E-sized scratch (slot layout), shared by the forms on this space
    DevBuf attr;     // element attributes (Mesh::GetAttribute), int32[NE]; only needed by integrator markers
@@ -636,7 +637,7 @@ extern "C" int b200pa_space_destroy(b200pa_space sp)
    cudaSetDevice(sp->ctx->device);
    cudaStreamSynchronize(sp->ctx->stream);
    delete sp->pipe;
-   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->jinv9, &sp->scratchE, &sp->attr})
+   for (DevBuf *b : {&sp->dB, &sp->dG, &sp->gmap, &sp->offsets, &sp->indices, &sp->slot, &sp->W, &sp->J, &sp->detJ, &sp->vtx, &sp->ev, &sp->dxi, &sp->geo6, &sp->jinv9, &sp->detE, &sp->scratchE, &sp->attr})
    {
       b->release();
    }
@@ -711,6 +712,22 @@ static void gauss_legendre_01(int n, double *x)
    }
 }
 
+// determinants per q-point, rebuilt from the vertices (trilinear geometry)
+static int ensure_detJ(b200pa_space sp)
+{
+   if (sp->detJ.p) { return 0; }
+   B200PA_REQUIRE(sp->vtx.p, "space has no geometry (call b200pa_space_set_geometry or b200pa_space_geometry_from_vertices)");
+   b200pa_ctx ctx = sp->ctx;
+   if (alloc(sp->detJ, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1))) { return 1; }
+   if (sp->ne > 0)
+   {
+      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, sp->dxi.as<double>(), sp->vtx.as<double>(),
+                                                                       sp->ev.as<int>(), nullptr, sp->detJ.as<double>());
+      B200PA_LAUNCHED();
+   }
+   return 0;
+}
+
 extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double *W_any, int nv, const double *vertices_any,
                                                    const int *elem_vertices_any)
 {
@@ -718,9 +735,9 @@ extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double
    NEED_CTX(sp->ctx);
    b200pa_ctx ctx = sp->ctx;
    if (b200pa_space_set_geometry(sp, W_any, nullptr, nullptr)) { return 1; }
-   sp->J.release(); sp->detJ.release();
+   sp->J.release(); sp->detJ.release(); sp->detE.release();
    if (alloc(sp->vtx, sizeof(double) * 3 * (size_t)std::max(nv, 1)) || alloc(sp->ev, sizeof(int) * 8 * (size_t)std::max(sp->ne, 1)) ||
-       alloc(sp->dxi, sizeof(double) * 16) || alloc(sp->detJ, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1)))
+       alloc(sp->dxi, sizeof(double) * 16))
    {
       return 1;
    }
@@ -734,25 +751,30 @@ extern "C" int b200pa_space_geometry_from_vertices(b200pa_space sp, const double
    sp->hxi.assign(16, 0.0);
    gauss_legendre_01(sp->q1d, sp->hxi.data());
    B200PA_CK(cudaMemcpyAsync(sp->dxi.p, sp->hxi.data(), sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
-   if (sp->ne > 0)
-   {
-      k_geometry_trilinear<<<grid1d(ctx, sp->nQ), 256, 0, ctx->stream>>>(sp->q1d, sp->ne, sp->dxi.as<double>(), sp->vtx.as<double>(),
-                                                                       sp->ev.as<int>(), nullptr, sp->detJ.as<double>());
-      B200PA_LAUNCHED();
-   }
    sp->affine = false;
    if (sp->ne > 0)
    {
-      if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne) || alloc(sp->jinv9, sizeof(double) * 9 * (size_t)sp->ne)) { return 1; }
+      if (alloc(sp->geo6, sizeof(double) * 6 * (size_t)sp->ne) || alloc(sp->jinv9, sizeof(double) * 9 * (size_t)sp->ne) ||
+          alloc(sp->detE, sizeof(double) * (size_t)sp->ne))
+      {
+         return 1;
+      }
       int *dflag = (int *)(ctx->d_ticket + 3);
       B200PA_CK(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
       k_affine_geometry<<<grid1d(ctx, sp->ne), 128, 0, ctx->stream>>>(sp->ne, sp->vtx.as<double>(), sp->ev.as<int>(), 1e-13,
-                                                                    sp->geo6.as<double>(), sp->jinv9.as<double>(), dflag);
+                                                                    sp->geo6.as<double>(), sp->jinv9.as<double>(), sp->detE.as<double>(), dflag);
       B200PA_LAUNCHED();
       int flag = 1;
       B200PA_CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       B200PA_CK(cudaStreamSynchronize(ctx->stream));
       sp->affine = (flag == 0);
+   }
+   // affine mesh: det J is one number per element (detE); the per-q-point array (8 B per q-point: 16 GB on a 31 M-element
+   // rank) is only built when somebody asks for it (b200pa_space_detJ).  Other meshes get it now.
+   if (!sp->affine)
+   {
+      sp->detE.release();
+      if (ensure_detJ(sp)) { return 1; }
    }
    B200PA_CK(cudaStreamSynchronize(ctx->stream));
    return 0;
@@ -784,7 +806,12 @@ extern "C" const double *b200pa_space_J(b200pa_space sp)
    if (!sp || cudaSetDevice(sp->ctx->device) != cudaSuccess || ensure_J(sp)) { return nullptr; }
    return sp->J.as<double>();
 }
-extern "C" const double *b200pa_space_detJ(b200pa_space sp) { return sp ? sp->detJ.as<double>() : nullptr; }
+extern "C" const double *b200pa_space_detJ(b200pa_space sp)
+{
+   if (!sp) { return nullptr; }
+   if (!sp->detJ.p && sp->vtx.p) { if (cudaSetDevice(sp->ctx->device) != cudaSuccess || ensure_detJ(sp)) { return nullptr; } }
+   return sp->detJ.as<double>();
+}
 extern "C" const double *b200pa_space_W(b200pa_space sp) { return sp ? sp->W.as<double>() : nullptr; }
 
 static int need_scratch(b200pa_space sp)
@@ -855,11 +882,11 @@ extern "C" int b200pa_space_domain_lf(b200pa_space sp, const double *f_dev, long
 {
    B200PA_REQUIRE(sp, "space is NULL");
    NEED_CTX(sp->ctx);
-   B200PA_REQUIRE(sp->detJ.p && sp->W.p, "space has no geometry (call b200pa_space_set_geometry)");
+   B200PA_REQUIRE((sp->detJ.p || sp->detE.p) && sp->W.p, "space has no geometry (call b200pa_space_set_geometry)");
    B200PA_REQUIRE(nf == 1 || nf == sp->nQ, "domain_lf: f must have 1 or Q^3*NE entries");
    if (need_scratch(sp)) { return 1; }
    ElemArgs a = space_args(sp);
-   a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>(); a.detJ = sp->detJ.as<double>(); a.W = sp->W.as<double>();
+   a.y = sp->scratchE.as<double>(); a.slot = sp->slot.as<int>(); a.detJ = sp->detJ.as<double>(); a.detE = sp->detE.as<double>(); a.W = sp->W.as<double>();
    a.f = f_dev; a.nf = nf;
    if (run_element(sp->ctx, sp->d1d, sp->q1d, EV_LF_S, a)) { return 1; }
    if (sp->ndofs > 0)
@@ -1020,14 +1047,22 @@ extern "C" int b200pa_form_assemble_mass(b200pa_form f, const double *C_any, lon
    b200pa_space sp = f->sp;
    NEED_CTX(sp->ctx);
    if (!C_any) { f->pa_mass.release(); f->has_mass = false; return 0; }
-   B200PA_REQUIRE(sp->detJ.p && sp->W.p, "assemble_mass: space has no geometry");
+   B200PA_REQUIRE((sp->detJ.p || sp->detE.p) && sp->W.p, "assemble_mass: space has no geometry");
    B200PA_REQUIRE(nc == 1 || nc == sp->nQ, "assemble_mass: coefficient must have 1 or Q^3*NE entries");
    DevBuf cb;
    const void *dC = nullptr;
    if (to_device(sp->ctx, C_any, sizeof(double) * (size_t)nc, cb, &dC)) { return 1; }
    if (!f->pa_mass.owned) { f->pa_mass.release(); }
    int rc = alloc(f->pa_mass, sizeof(double) * (size_t)std::max<long long>(sp->nQ, 1));
-   if (!rc) { rc = b200pa_mass_setup(sp->ctx, sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(), sp->detJ.as<double>(), (const double *)dC, nc, f->pa_mass.as<double>()); }
+   if (!rc && sp->detJ.p) { rc = b200pa_mass_setup(sp->ctx, sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(), sp->detJ.as<double>(), (const double *)dC, nc, f->pa_mass.as<double>()); }
+   else if (!rc && sp->ne > 0)
+   {
+      // affine mesh: one determinant per element (the set-up then reads 8 B per q-point less)
+      k_mass_setup_affine<<<grid1d(sp->ctx, sp->nQ), 256, 0, sp->ctx->stream>>>((long long)sp->q1d * sp->q1d * sp->q1d, sp->ne, sp->W.as<double>(),
+                                                                               sp->detE.as<double>(), (const double *)dC, nc == 1, f->pa_mass.as<double>());
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("mass set-up kernel launch failed"); }
+   }
    if (cb.owned) { cudaStreamSynchronize(sp->ctx->stream); cb.release(); }
    f->has_mass = (rc == 0);
    return rc ? rc : apply_marker(f, 1);
@@ -1094,6 +1129,15 @@ extern "C" int b200pa_form_set_essential(b200pa_form f, int n_ess, const int *es
       k_mask_indexed<<<grid1d(ctx, n_ess), 256, 0, ctx->stream>>>(n_ess, f->ess.as<int>(), f->ess_mask.as<unsigned char>());
       B200PA_LAUNCHED();
    }
+   if (n_ess == 0)
+   {
+      // nothing to constrain: the gather map itself (a borrowed pointer: 4 B per E-entry saved)
+      f->cgmap.release();
+      f->cgmap.p = sp->gmap.p; f->cgmap.bytes = sp->gmap.bytes; f->cgmap.owned = false;
+      B200PA_CK(cudaStreamSynchronize(ctx->stream));
+      return 0;
+   }
+   if (!f->cgmap.owned) { f->cgmap.release(); }
    if (alloc(f->cgmap, sizeof(int) * (size_t)std::max<long long>(sp->nE, 1))) { return 1; }
    if (sp->nE > 0)
    {
@@ -1227,10 +1271,12 @@ static int build_pipe(b200pa_space sp)
    const long long ne = sp->ne, nd = sp->nd;
    const int ndofs = sp->ndofs;
    // chunk size: a multiple of 64 elements (every kernel's batch size divides it; scalar q-data fields stay 16-byte aligned)
-   int C = 16;
+   // tuning knobs (environment, read when the plan is built): number of element chunks, dofs per tile
+   const char *ec = getenv("B200PA_PIPE_CHUNKS"), *et = getenv("B200PA_PIPE_TILE");
+   int C = ec ? std::max(1, atoi(ec)) : 16;
    long long cs = ((ne + C - 1) / C + 63) / 64 * 64;
    C = (int)((ne + cs - 1) / cs);
-   const int TS = 32768;
+   const int TS = et ? std::max(1024, atoi(et)) : 32768;
    const int T = (ndofs + TS - 1) / TS;
    hp->C = C; hp->T = T; hp->TS = TS; hp->cs = (int)cs;
    std::vector<int> gm((size_t)(ne * nd));

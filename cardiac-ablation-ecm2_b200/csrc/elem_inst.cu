@@ -51,7 +51,7 @@ void fill_params(ElemParams<DD, QQ> &P, const ElemArgs &a)
    P.NE = a.NE;
    P.x = a.x; P.gmap = a.gmap; P.y = a.y; P.slot = a.slot;
    P.pa_diff = a.pa_diff; P.pa_mass = a.pa_mass; P.geo = a.geo; P.J = a.J;
-   P.f = a.f; P.detJ = a.detJ; P.W = a.W; P.nf = a.nf; P.done = a.done;
+   P.f = a.f; P.detJ = a.detJ; P.detE = a.detE; P.W = a.W; P.nf = a.nf; P.done = a.done;
    P.ca = a.ca; P.cb = a.cb; P.cT0 = a.cT0; P.s = a.s;
    P.vtx = a.vtx; P.ev = a.ev; P.jinv = a.jinv;
    for (int i = 0; i < QQ; ++i) { P.xi[i] = a.xi ? a.xi[i] : 0.0; }

@@ -33,7 +33,7 @@ struct ElemArgs
    const double *pa_diff = nullptr, *pa_mass = nullptr;
    const double *geo = nullptr;             // EV_APPLY_L2S: factorised diffusion q-data (pa_diff = c_q [Q^3,NE], geo [6,NE])
    const double *J = nullptr;
-   const double *f = nullptr, *detJ = nullptr, *W = nullptr;
+   const double *f = nullptr, *detJ = nullptr, *detE = nullptr, *W = nullptr; // detE: one determinant per element (detJ == nullptr)
    long long nf = 0;
    const int *done = nullptr;
    double ca = 0.0, cb = 0.0, cT0 = 0.0;    // EV_COEFF_L / EV_JOULE_L parameters

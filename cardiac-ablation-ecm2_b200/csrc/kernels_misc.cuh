@@ -159,14 +159,35 @@ __global__ void k_diffusion_setup(long long NQ, long long NE, const double *__re
 }
 
 // fem/integ/bilininteg_mass_pa.cpp:62-78
+// (element, q-point) of a grid-stride loop over NQ * NE entries without a 64-bit division per entry: one division at the
+// start, then the stride is added in (element, q-point) form
+struct EQ
+{
+   long long e; int q, de, dq, NQ;
+   __device__ EQ(long long i0, long long stride, long long NQ_) : e(i0 / NQ_), q((int)(i0 % NQ_)), de((int)(stride / NQ_)), dq((int)(stride % NQ_)), NQ((int)NQ_) {}
+   __device__ void next() { e += de; q += dq; if (q >= NQ) { q -= NQ; ++e; } }
+};
+
 __global__ void k_mass_setup(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ detJ,
                              const double *__restrict__ C, int const_c, double *__restrict__ v)
 {
-   const long long n = NQ * NE;
-   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   const long long n = NQ * NE, i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+   EQ eq(i0, st, NQ);
+   for (long long i = i0; i < n; i += st, eq.next())
    {
-      const long long q = i % NQ;
-      v[i] = W[q] * (const_c ? C[0] : C[i]) * detJ[i];
+      v[i] = W[eq.q] * (const_c ? C[0] : C[i]) * detJ[i];
+   }
+}
+
+// the same on a mesh of affine elements whose determinant is kept per ELEMENT (8 B per element instead of 8 B per q-point)
+__global__ void k_mass_setup_affine(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ detE,
+                                    const double *__restrict__ C, int const_c, double *__restrict__ v)
+{
+   const long long n = NQ * NE, i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+   EQ eq(i0, st, NQ);
+   for (long long i = i0; i < n; i += st, eq.next())
+   {
+      v[i] = W[eq.q] * (const_c ? C[0] : C[i]) * detE[eq.e];
    }
 }
 
@@ -231,7 +252,7 @@ __global__ void k_diffusion_setup_trilinear(int Q1D, long long NE, const double 
 // into the per-element tensor below (6 doubles per ELEMENT) and the scalar w_q c_q per q-point.  One thread per
 // element; `flag` is raised when an element is not affine to `tol` (relative to its edge lengths).
 __global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, const int *__restrict__ ev, double tol,
-                                  double *__restrict__ geo6, double *__restrict__ jinv9, int *flag)
+                                  double *__restrict__ geo6, double *__restrict__ jinv9, double *__restrict__ detE, int *flag)
 {
    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < NE; e += (long long)gridDim.x * blockDim.x)
    {
@@ -260,6 +281,7 @@ __global__ void k_affine_geometry(long long NE, const double *__restrict__ vtx, 
       trilinear_jacobian(vtx, v, 0.5, 0.5, 0.5, Jm);
       const double J11 = Jm[0], J21 = Jm[1], J31 = Jm[2], J12 = Jm[3], J22 = Jm[4], J32 = Jm[5], J13 = Jm[6], J23 = Jm[7], J33 = Jm[8];
       const double detJ = J11 * (J22 * J33 - J32 * J23) - J21 * (J12 * J33 - J32 * J13) + J31 * (J12 * J23 - J22 * J13);
+      if (detE) { detE[e] = detJ; }
       const double w = 1.0 / detJ;
       const double A11 = (J22 * J33) - (J23 * J32), A12 = (J32 * J13) - (J12 * J33), A13 = (J12 * J23) - (J22 * J13);
       const double A21 = (J31 * J23) - (J21 * J33), A22 = (J11 * J33) - (J13 * J31), A23 = (J21 * J13) - (J11 * J23);
@@ -330,13 +352,13 @@ __global__ void k_affine_from_J(long long NQ, long long NE, const double *__rest
 __global__ void k_diffusion_setup_affine(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ geo6,
                                          const double *__restrict__ C, int const_c, double *__restrict__ D)
 {
-   const long long n = NQ * NE;
-   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   const long long n = NQ * NE, i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+   EQ eq(i0, st, NQ);
+   for (long long i = i0; i < n; i += st, eq.next())
    {
-      const long long e = i / NQ, q = i - e * NQ;
-      const double w = W[q] * (const_c ? C[0] : C[i]);
-      const double *g = geo6 + 6 * e;
-      double *De = D + e * 6 * NQ + q;
+      const double w = W[eq.q] * (const_c ? C[0] : C[i]);
+      const double *g = geo6 + 6 * eq.e;
+      double *De = D + eq.e * 6 * NQ + eq.q;
 #pragma unroll
       for (int k = 0; k < 6; ++k) { De[k * NQ] = w * g[k]; }
    }
@@ -346,10 +368,11 @@ __global__ void k_diffusion_setup_affine(long long NQ, long long NE, const doubl
 __global__ void k_coeff_times_w(long long NQ, long long NE, const double *__restrict__ W, const double *__restrict__ C, int const_c,
                                 double *__restrict__ out)
 {
-   const long long n = NQ * NE;
-   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+   const long long n = NQ * NE, i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+   EQ eq(i0, st, NQ);
+   for (long long i = i0; i < n; i += st, eq.next())
    {
-      out[i] = W[i % NQ] * (const_c ? C[0] : C[i]);
+      out[i] = W[eq.q] * (const_c ? C[0] : C[i]);
    }
 }
 
@@ -390,6 +413,19 @@ __global__ void k_coeff_eval(int kind, long long n, double a, double b, double T
 #ifndef B200PA_TUNE_DIAG_KB
 #define B200PA_TUNE_DIAG_KB 44
 #endif
+// field groups: the seven fields of passes 1 and 2 are split over NFG tasks per (element, column) - the kernel is bound by
+// latency at low occupancy (shared memory per element is large, tasks per element few), more threads per element hide it
+#ifndef B200PA_TUNE_DIAG_NFG
+#define B200PA_TUNE_DIAG_NFG 2
+#endif
+__device__ __forceinline__ int diag_group_lo(int g)
+{
+   // first field of group g (and 7 for g = NFG)
+   return B200PA_TUNE_DIAG_NFG == 1 ? (g == 0 ? 0 : 7)
+          : B200PA_TUNE_DIAG_NFG == 2 ? (g == 0 ? 0 : (g == 1 ? 3 : 7))
+          : B200PA_TUNE_DIAG_NFG == 4 ? (g < 3 ? 2 * g : (g == 3 ? 6 : 7))
+          : g;
+}
 // smallest s >= lo with s = r (mod 16): 16 consecutive lanes (one 128-byte shared-memory wavefront of doubles) whose
 // addresses advance by `r` per outer index and by 1 per inner index then fall into 16 different banks
 constexpr int diag_stride(int lo, int r) { return lo + ((r - lo) % 16 + 16) % 16; }
@@ -422,7 +458,9 @@ struct DiagSfCfg
    // that no half-warp (one shared-memory wavefront of doubles) straddles two elements - the strides above are
    // conflict-free inside an element (ncu of the unpadded version: 2.25x the ideal wavefronts in pass 3 at p=2)
    static constexpr int TPE1 = Q2 < 16 ? 16 : Q2, TPE2 = D1 * Q1 < 16 ? 16 : D1 * Q1, TPE3 = D1 * D1 < 16 ? 16 : D1 * D1;
-   static constexpr int NT0 = ((NEB * TPE1 + 31) / 32) * 32;
+   static constexpr int NFG = B200PA_TUNE_DIAG_NFG;
+   static_assert(NFG == 1 || NFG == 2 || NFG == 4 || NFG == 7, "field groups: 1, 2, 4 or 7");
+   static constexpr int NT0 = ((NFG * NEB * TPE1 + 31) / 32) * 32;
    static constexpr int NT = NT0 < 64 ? 64 : NT0;
    static constexpr int SQD = NEB * SQD1 + 2, SQM = ((NEB * SQM1 + 2) + 1) & ~1; // TMA staging (16-byte aligned, +slack)
    static constexpr int STAGE = (SQD + SQM) > NEB * T2E ? (SQD + SQM) : ((NEB * T2E + 1) & ~1);
@@ -541,14 +579,17 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
          __syncthreads();
       }
       // pass 1: contract qz.  task = (e, qy, qx), all seven fields: one column of Q1 q-data values each
-      for (int t = threadIdx.x; t < nel * C::TPE1; t += blockDim.x)
+      for (int t0 = threadIdx.x; t0 < C::NFG * nel * C::TPE1; t0 += blockDim.x)
       {
+         const int fg = t0 / (nel * C::TPE1), t = t0 - fg * nel * C::TPE1;
+         const int flo = diag_group_lo(fg), fhi = diag_group_lo(fg + 1);
          const int e = t / C::TPE1, c = t - e * C::TPE1;
          if (c >= Q2) { continue; }
          const bool diff_on = pa_diff != nullptr && !(P.diff_off && P.diff_off[e0 + e]);
 #pragma unroll
          for (int f = 0; f < NF; ++f)
          {
+            if (C::NFG > 1 && (f < flo || f >= fhi)) { continue; }
             const bool have = f < 6 ? diff_on : pa_mass != nullptr;
             const double *src = f < 6 ? (scalar_diff ? sQd + dsh + e * Q3 + c : sQd + (e * 6 + f) * Q3 + c) : sQm + msh + e * Q3 + c;
             const double scale = (f < 6 && scalar_diff && have) ? __ldg(geo + (e0 + e) * 6 + f) : 1.0;
@@ -571,13 +612,16 @@ k_diag_sf(const __grid_constant__ DiagParams<D1, Q1> P)
       }
       __syncthreads();
       // pass 2: contract qy.  task = (e, dz, qx), all seven fields; T2 goes where the consumed q-data was
-      for (int t = threadIdx.x; t < nel * C::TPE2; t += blockDim.x)
+      for (int t0 = threadIdx.x; t0 < C::NFG * nel * C::TPE2; t0 += blockDim.x)
       {
+         const int fg = t0 / (nel * C::TPE2), t = t0 - fg * nel * C::TPE2;
+         const int flo = diag_group_lo(fg), fhi = diag_group_lo(fg + 1);
          const int e = t / C::TPE2, r2 = t - e * C::TPE2, dz = r2 / Q1, qx = r2 - dz * Q1;
          if (r2 >= D1 * Q1) { continue; }
 #pragma unroll
          for (int f = 0; f < NF; ++f)
          {
+            if (C::NFG > 1 && (f < flo || f >= fhi)) { continue; }
             double out[D1];
 #pragma unroll
             for (int d = 0; d < D1; ++d) { out[d] = 0.0; }

@@ -54,7 +54,8 @@ struct ElemParams
    const double *__restrict__ geo;     // pa_apply_kernel<.., AFF>: adj(J) adj(J)^T / det J per element [6,NE]; pa_diff is then [Q^3,NE]
    const double *__restrict__ J;       // QOP_PHYSGRAD: [Q^3,3,3,NE]
    const double *__restrict__ f;       // QOP_LF: f [Q^3,NE] or 1 value
-   const double *__restrict__ detJ;    // QOP_LF
+   const double *__restrict__ detJ;    // QOP_LF: per q-point [Q^3,NE], or null and
+   const double *__restrict__ detE;    //         one determinant per (affine) element [NE]
    const double *__restrict__ W;       // QOP_LF
    long long nf;
    const int *done;                    // PCG early-exit flag (device) or null
@@ -241,7 +242,7 @@ pa_element_kernel(const __grid_constant__ ElemParams<D, Q> P)
             for (int qz = 0; qz < Q; ++qz)
             {
                Fq[qz] = P.nf == 1 ? __ldg(P.f) : __ldg(P.f + eg * Q3 + qz * Q2 + c);
-               Dq[qz] = __ldg(P.detJ + eg * Q3 + qz * Q2 + c);
+               Dq[qz] = P.detJ ? __ldg(P.detJ + eg * Q3 + qz * Q2 + c) : __ldg(P.detE + eg);
             }
          }
          if ((QOP == QOP_PHYSGRAD || QOP == QOP_JOULE) && P.jinv)
