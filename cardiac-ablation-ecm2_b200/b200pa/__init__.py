@@ -49,7 +49,9 @@ b200pa_chebyshev_coeffs b200pa_power_method b200pa_chebyshev_mult b200pa_pcg_sol
 b200pa_comm_unique_id b200pa_comm_create b200pa_comm_destroy b200pa_comm_set_tables b200pa_comm_build_tables
 b200pa_comm_owner_mask b200pa_comm_px_prepare b200pa_comm_px_connect b200pa_comm_px_error b200pa_comm_px_enabled b200pa_comm_px_disable b200pa_form_set_comm b200pa_comm_exchange_sum b200pa_comm_bcast b200pa_comm_allreduce_sum
 b200pa_hex_sizes b200pa_hex_build b200pa_hex_build_part b200pa_hex_dof_lattice b200pa_basis b200pa_randomize
-b200pa_hex_write_mesh b200pa_write_gridfunction
+b200pa_hex_write_mesh b200pa_write_gridfunction b200pa_basis_transfer
+b200pa_transfer_create b200pa_transfer_destroy b200pa_transfer_mult b200pa_transfer_mult_transpose
+b200pa_mg_create b200pa_mg_destroy b200pa_mg_set_cycle b200pa_mg_set_coarse_solver b200pa_mg_setup b200pa_mg_max_eig b200pa_mg_coarse_iterations b200pa_mg_mult b200pa_pcg_solve_mg
 """.split()
 
 
@@ -136,6 +138,13 @@ def basis(p, q1d=None):
     w1d, W, gll = np.empty(q1d), np.empty(q1d ** 3), np.empty(D)
     check(lib().b200pa_basis(p, q1d, _ptr(B), _ptr(G), _ptr(w1d), _ptr(W), _ptr(gll)))
     return {"B": B, "G": G, "w1d": w1d, "W": W, "gll": gll}
+
+
+def basis_transfer(pc, pf):
+    """[pf+1, pc+1] column-major: coarse GLL-nodal basis at the fine GLL nodes (order-refinement transfer)"""
+    B = np.empty((pf + 1) * (pc + 1))
+    check(lib().b200pa_basis_transfer(int(pc), int(pf), _ptr(B)))
+    return B
 
 
 def randomize(n, seed=1):
@@ -538,6 +547,78 @@ class Form:
     def close(self):
         if self.h:
             lib().b200pa_form_destroy(self.h)
+            self.h = vp()
+
+
+class Transfer:
+    """TensorProductPRefinementTransferOperator between two forms on the same mesh (coarse, fine)"""
+
+    def __init__(self, coarse, fine, B):
+        self.fc, self.ff, self.ctx = coarse, fine, coarse.ctx
+        self.h = vp()
+        check(lib().b200pa_transfer_create(coarse.h, fine.h, _ptr(_f64(B)), C.byref(self.h)))
+
+    def mult(self, xc, yf=None):
+        yf = self.ctx.empty(self.ff.sp.ndofs) if yf is None else yf
+        check(lib().b200pa_transfer_mult(self.h, _ptr(xc), _ptr(yf)))
+        return yf
+
+    def mult_transpose(self, xf, yc=None):
+        yc = self.ctx.empty(self.fc.sp.ndofs) if yc is None else yc
+        check(lib().b200pa_transfer_mult_transpose(self.h, _ptr(xf), _ptr(yc)))
+        return yc
+
+    def close(self):
+        if self.h:
+            lib().b200pa_transfer_destroy(self.h)
+            self.h = vp()
+
+
+class Multigrid:
+    """Multigrid (fem/multigrid.hpp) over forms[0] (coarsest) .. forms[-1], Chebyshev smoothers, CG coarse solve"""
+
+    def __init__(self, forms, transfers):
+        self.forms, self.transfers, self.ctx = forms, transfers, forms[0].ctx
+        self.h = vp()
+        fa = (vp * len(forms))(*[f.h for f in forms])
+        ta = (vp * max(len(transfers), 1))(*[t.h for t in transfers])
+        check(lib().b200pa_mg_create(len(forms), fa, ta, C.byref(self.h)))
+
+    def set_cycle(self, wcycle=False, pre=1, post=1):
+        check(lib().b200pa_mg_set_cycle(self.h, int(wcycle), int(pre), int(post)))
+
+    def set_coarse_solver(self, rel_tol, abs_tol, max_iter, jacobi=False):
+        check(lib().b200pa_mg_set_coarse_solver(self.h, C.c_double(rel_tol), C.c_double(abs_tol), int(max_iter), int(jacobi)))
+
+    def setup(self, order=None, max_eig=None):
+        n = len(self.forms)
+        o = None if order is None else _i32(order)
+        e = None if max_eig is None else _f64(max_eig)
+        assert (o is None or len(o) == n) and (e is None or len(e) == n)
+        check(lib().b200pa_mg_setup(self.h, _ptr(o), _ptr(e)))
+
+    def max_eig(self, level):
+        lib().b200pa_mg_max_eig.restype = C.c_double
+        return lib().b200pa_mg_max_eig(self.h, int(level))
+
+    def coarse_iterations(self):
+        return int(lib().b200pa_mg_coarse_iterations(self.h))
+
+    def mult(self, x, y=None):
+        y = self.ctx.empty(self.forms[-1].sp.ndofs) if y is None else y
+        check(lib().b200pa_mg_mult(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def pcg(self, b, x, rel_tol=0.0, abs_tol=0.0, max_iter=100, want_norms=True):
+        res = PcgResult()
+        norms = np.zeros(max_iter + 2) if want_norms else None
+        check(lib().b200pa_pcg_solve_mg(self.h, _ptr(b), _ptr(x), C.c_double(rel_tol), C.c_double(abs_tol), int(max_iter),
+                                        C.byref(res), _ptr(norms) if want_norms else None))
+        return res, (norms[:res.final_iter + 1] if want_norms else None)
+
+    def close(self):
+        if self.h:
+            lib().b200pa_mg_destroy(self.h)
             self.h = vp()
 
 

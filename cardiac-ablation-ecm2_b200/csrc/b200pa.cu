@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "elem_launch.cuh"
 #include "kernels_misc.cuh"
+#include "multigrid.cuh"
 #include "comm.cuh"
 
 namespace b200pa
@@ -200,6 +201,8 @@ struct HostPipe
 {
    int C = 0, T = 0, TS = 0, cs = 0;
    std::vector<std::vector<std::pair<int, int>>> up, down; // per chunk: merged dof ranges [i0, i1) to upload before / finalise after it
+   std::vector<int> down_first, down_count;                // per chunk: its completed tiles as a slice of d_tiles
+   b200pa::DevBuf d_tiles;
    cudaStream_t s_up = nullptr, s_down = nullptr;
    std::vector<cudaEvent_t> ev_up, ev_done;
    cudaEvent_t ev_start = nullptr, ev_end = nullptr;
@@ -211,6 +214,7 @@ struct HostPipe
       if (ev_end) { cudaEventDestroy(ev_end); }
       if (s_up) { cudaStreamDestroy(s_up); }
       if (s_down) { cudaStreamDestroy(s_down); }
+      d_tiles.release();
    }
 };
 
@@ -1273,10 +1277,10 @@ static int build_pipe(b200pa_space sp)
    // chunk size: a multiple of 64 elements (every kernel's batch size divides it; scalar q-data fields stay 16-byte aligned)
    // tuning knobs (environment, read when the plan is built): number of element chunks, dofs per tile
    const char *ec = getenv("B200PA_PIPE_CHUNKS"), *et = getenv("B200PA_PIPE_TILE");
-   int C = ec ? std::max(1, atoi(ec)) : 16;
+   int C = ec ? std::max(1, atoi(ec)) : 8;   // measured at configs[1] (profiles/r2i_e2e_sweep.json): 8 chunks, 32 K dofs per tile
    long long cs = ((ne + C - 1) / C + 63) / 64 * 64;
    C = (int)((ne + cs - 1) / cs);
-   const int TS = et ? std::max(1024, atoi(et)) : 32768;
+   const int TS = et ? std::max(1024, atoi(et) / 256 * 256) : 32768;
    const int T = (ndofs + TS - 1) / TS;
    hp->C = C; hp->T = T; hp->TS = TS; hp->cs = (int)cs;
    std::vector<int> gm((size_t)(ne * nd));
@@ -1300,12 +1304,24 @@ static int build_pipe(b200pa_space sp)
       const int i0 = t * TS, i1 = std::min(ndofs, (t + 1) * TS);
       if (!v.empty() && v.back().second == i0) { v.back().second = i1; } else { v.emplace_back(i0, i1); }
    };
+   std::vector<std::vector<int>> done_tiles(C);
    for (int t = 0; t < T; ++t)
    {
       // a tile no element touches (cannot happen for a conforming space) still has to travel: first / last chunk
       add(hp->up[first[t] < C ? first[t] : 0], t);
       add(hp->down[last[t] >= 0 ? last[t] : C - 1], t);
+      done_tiles[last[t] >= 0 ? last[t] : C - 1].push_back(t);
    }
+   std::vector<int> flat;
+   hp->down_first.assign(C, 0); hp->down_count.assign(C, 0);
+   for (int c = 0; c < C; ++c)
+   {
+      hp->down_first[c] = (int)flat.size(); hp->down_count[c] = (int)done_tiles[c].size();
+      flat.insert(flat.end(), done_tiles[c].begin(), done_tiles[c].end());
+   }
+   if (alloc(hp->d_tiles, sizeof(int) * std::max<size_t>(flat.size(), 1))) { delete hp; return 1; }
+   B200PA_CK(cudaMemcpyAsync(hp->d_tiles.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
    B200PA_CK(cudaStreamCreateWithFlags(&hp->s_up, cudaStreamNonBlocking));
    B200PA_CK(cudaStreamCreateWithFlags(&hp->s_down, cudaStreamNonBlocking));
    hp->ev_up.resize(C); hp->ev_done.resize(C);
@@ -1356,18 +1372,14 @@ static int form_mult_host_pipelined(b200pa_form f, bool constrained, const doubl
       a.pa_mass = f->has_mass ? f->pa_mass.as<double>() + e0 * q3 : nullptr;
       a.geo = (f->has_diff && f->factorised) ? sp->geo6.as<double>() + e0 * 6 : nullptr;
       if (run_element(ctx, sp->d1d, sp->q1d, EV_APPLY_L2S, a)) { return 1; }
-      for (const auto &r : hp.down[c])
+      if (hp.down_count[c] > 0)
       {
-         const int n = r.second - r.first;
-         const int grid = grid1d(ctx, n);
-         if (constrained)
-         {
-            k_segment_sum<true, false, false><<<grid, 256, 0, s>>>(n, off + r.first, yS, y + r.first, em + r.first, x + r.first, nullptr, nullptr, nullptr, nullptr, nullptr);
-         }
-         else
-         {
-            k_segment_sum<false, false, false><<<grid, 256, 0, s>>>(n, off + r.first, yS, y + r.first, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-         }
+         // ONE launch for all the tiles this chunk completes (they are scattered: vertex, edge, face and interior dofs of a
+         // blob of elements live in four different index ranges)
+         const int *tiles = hp.d_tiles.as<int>() + hp.down_first[c];
+         const int grid = hp.down_count[c] * (hp.TS / 256);
+         if (constrained) { k_segment_sum_tiles<true><<<grid, 256, 0, s>>>(tiles, hp.TS, sp->ndofs, off, yS, y, em, x); }
+         else { k_segment_sum_tiles<false><<<grid, 256, 0, s>>>(tiles, hp.TS, sp->ndofs, off, yS, y, nullptr, nullptr); }
          B200PA_LAUNCHED();
       }
       B200PA_CK(cudaEventRecord(hp.ev_done[c], s));
@@ -1880,5 +1892,343 @@ extern "C" int b200pa_form_set_comm(b200pa_form f, b200pa_comm c)
    B200PA_REQUIRE(f, "form is NULL");
    if (c && comm_validate(c, f->sp->ndofs)) { return 1; }
    f->comm = c;
+   return 0;
+}
+
+
+// ------------------------------------------------------------------ p-multigrid
+// Order-refinement transfer between two spaces on the same mesh (TensorProductPRefinementTransferOperator,
+// fem/transfer.cpp:2223-2296, 2542-2592) with the essential-dof handling of the RectangularConstrainedOperator a
+// GeometricMultigrid wraps it in (fem/multigrid.cpp:281-296, linalg/operator.cpp RectangularConstrainedOperator::Mult).
+struct b200pa_transfer_s
+{
+   b200pa_form fc = nullptr, ff = nullptr; // forms carry the spaces and the essential-dof masks of the two levels
+   DevBuf B;                                // [DF, DC] column-major
+   int DC = 0, DF = 0;
+};
+
+static TransferParams transfer_params(b200pa_transfer t)
+{
+   b200pa_space sc = t->fc->sp, sf = t->ff->sp;
+   TransferParams P;
+   P.NE = sc->ne; P.DC = t->DC; P.DF = t->DF; P.B = t->B.as<double>();
+   P.gmap_c = sc->gmap.as<int>(); P.gmap_f = sf->gmap.as<int>(); P.slot_f = sf->slot.as<int>(); P.off_f = sf->offsets.as<int>();
+   P.ess_c = t->fc->n_ess > 0 ? t->fc->ess_mask.as<unsigned char>() : nullptr;
+   P.ess_f = t->ff->n_ess > 0 ? t->ff->ess_mask.as<unsigned char>() : nullptr;
+   P.slot_c = sc->slot.as<int>();
+   return P;
+}
+
+extern "C" int b200pa_transfer_create(b200pa_form coarse, b200pa_form fine, const double *B_any, b200pa_transfer *out)
+{
+   B200PA_REQUIRE(coarse && fine && B_any && out, "transfer_create: NULL argument");
+   b200pa_space sc = coarse->sp, sf = fine->sp;
+   NEED_CTX(sc->ctx);
+   B200PA_REQUIRE(sc->ctx == sf->ctx && sc->ne == sf->ne, "transfer_create: the two spaces must live on the same mesh and context");
+   B200PA_REQUIRE(sc->d1d <= sf->d1d, "transfer_create: the first form is the COARSE (lower-order) level");
+   B200PA_REQUIRE(coarse->ess_mask.p && fine->ess_mask.p, "transfer_create: call b200pa_form_set_essential on both forms first (n_ess may be 0)");
+   b200pa_transfer t = new b200pa_transfer_s;
+   t->fc = coarse; t->ff = fine; t->DC = sc->d1d; t->DF = sf->d1d;
+   std::vector<double> hB;
+   if (to_host(sc->ctx, B_any, (size_t)t->DC * t->DF, hB) || alloc(t->B, sizeof(double) * t->DC * t->DF)) { delete t; return 1; }
+   B200PA_CK(cudaMemcpyAsync(t->B.p, hB.data(), sizeof(double) * hB.size(), cudaMemcpyHostToDevice, sc->ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(sc->ctx->stream));
+   if (need_scratch(sc)) { delete t; return 1; }
+   *out = t;
+   return 0;
+}
+
+extern "C" int b200pa_transfer_destroy(b200pa_transfer t)
+{
+   if (!t) { return 0; }
+   cudaSetDevice(t->fc->sp->ctx->device);
+   cudaStreamSynchronize(t->fc->sp->ctx->stream);
+   t->B.release();
+   delete t;
+   return 0;
+}
+
+static size_t transfer_smem(const b200pa_transfer t) { return sizeof(double) * ((size_t)t->DF * t->DC + 2 * (size_t)t->DF * t->DF * t->DF); }
+
+// y_fine = P x_coarse
+extern "C" int b200pa_transfer_mult(b200pa_transfer t, const double *xc_dev, double *yf_dev)
+{
+   B200PA_REQUIRE(t && xc_dev && yf_dev, "transfer_mult: NULL argument");
+   b200pa_ctx ctx = t->fc->sp->ctx;
+   NEED_CTX(ctx);
+   if (t->fc->sp->ne == 0) { return 0; }
+   const TransferParams P = transfer_params(t);
+   const int grid = (int)std::min<long long>(P.NE, (long long)ctx->num_sms * 8);
+   k_mg_prolong<<<grid, 128, transfer_smem(t), ctx->stream>>>(P, xc_dev, yf_dev);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+// y_coarse = P^T x_fine
+extern "C" int b200pa_transfer_mult_transpose(b200pa_transfer t, const double *xf_dev, double *yc_dev)
+{
+   B200PA_REQUIRE(t && xf_dev && yc_dev, "transfer_mult_transpose: NULL argument");
+   b200pa_space sc = t->fc->sp;
+   b200pa_ctx ctx = sc->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(!t->fc->comm && !t->ff->comm, "transfer: one GPU only");
+   if (sc->ne == 0) { return 0; }
+   const TransferParams P = transfer_params(t);
+   const int grid = (int)std::min<long long>(P.NE, (long long)ctx->num_sms * 8);
+   k_mg_restrict<<<grid, 128, transfer_smem(t), ctx->stream>>>(P, xf_dev, nullptr, sc->scratchE.as<double>());
+   B200PA_LAUNCHED();
+   k_mg_sum_zero<<<grid1d(ctx, sc->ndofs), 256, 0, ctx->stream>>>(sc->ndofs, sc->offsets.as<int>(), sc->scratchE.as<double>(), yc_dev, P.ess_c);
+   B200PA_LAUNCHED();
+   return 0;
+}
+
+// Multigrid (fem/multigrid.hpp): level 0 = coarsest.  Levels >= 1 are smoothed by OperatorChebyshevSmoother (order and
+// eigenvalue estimate per level, examples/ex26.cpp:90-105), level 0 is solved by CG (ex26.cpp:71-88: no preconditioner;
+// jacobi = 1 adds OperatorJacobiSmoother).
+struct b200pa_mg_s
+{
+   int nl = 0;
+   std::vector<b200pa_form> forms;
+   std::vector<b200pa_transfer> P;
+   std::vector<DevBuf> X, Y, R, Z, dinv;
+   std::vector<int> order;
+   std::vector<double> max_eig;
+   std::vector<std::vector<double>> coeffs;
+   double c_rel = 1e-2, c_abs = 0.0;
+   int c_maxit = 200, c_jacobi = 0, c_iters = 0;
+   int pre = 1, post = 1;
+   bool wcycle = false;
+   DevBuf ones;
+};
+
+extern "C" int b200pa_mg_create(int nlevels, const b200pa_form *forms, const b200pa_transfer *transfers, b200pa_mg *out)
+{
+   B200PA_REQUIRE(nlevels >= 1 && forms && out && (nlevels == 1 || transfers), "mg_create: bad arguments");
+   b200pa_ctx ctx = forms[0]->sp->ctx;
+   NEED_CTX(ctx);
+   b200pa_mg m = new b200pa_mg_s;
+   m->nl = nlevels;
+   m->forms.assign(forms, forms + nlevels);
+   if (nlevels > 1) { m->P.assign(transfers, transfers + nlevels - 1); }
+   m->X.resize(nlevels); m->Y.resize(nlevels); m->R.resize(nlevels); m->Z.resize(nlevels); m->dinv.resize(nlevels);
+   m->order.assign(nlevels, 2); m->max_eig.assign(nlevels, 0.0); m->coeffs.assign(nlevels, {});
+   auto bail = [&](const char *msg) { b200pa_mg_destroy(m); return fail(msg); };
+   for (int l = 0; l < nlevels; ++l)
+   {
+      b200pa_form f = forms[l];
+      if (!f || !f->cgmap.p || f->comm) { return bail("mg_create: every level needs an assembled one-GPU form with b200pa_form_set_essential called"); }
+      if (l > 0 && (transfers[l - 1]->fc != forms[l - 1] || transfers[l - 1]->ff != f)) { return bail("mg_create: transfers[l] must connect forms[l] (coarse) and forms[l+1] (fine)"); }
+      const size_t vb = sizeof(double) * (size_t)std::max(f->sp->ndofs, 1);
+      if (alloc(m->X[l], vb) || alloc(m->Y[l], vb) || alloc(m->R[l], vb) || alloc(m->Z[l], vb) || alloc(m->dinv[l], vb)) { b200pa_mg_destroy(m); return 1; }
+   }
+   *out = m;
+   return 0;
+}
+
+extern "C" int b200pa_mg_destroy(b200pa_mg m)
+{
+   if (!m) { return 0; }
+   if (!m->forms.empty() && m->forms[0])
+   {
+      cudaSetDevice(m->forms[0]->sp->ctx->device);
+      cudaStreamSynchronize(m->forms[0]->sp->ctx->stream);
+   }
+   for (auto *v : {&m->X, &m->Y, &m->R, &m->Z, &m->dinv}) { for (DevBuf &b : *v) { b.release(); } }
+   m->ones.release();
+   delete m;
+   return 0;
+}
+
+extern "C" int b200pa_mg_set_cycle(b200pa_mg m, int wcycle, int pre_smoothing_steps, int post_smoothing_steps)
+{
+   B200PA_REQUIRE(m && pre_smoothing_steps >= 0 && post_smoothing_steps >= 0, "mg_set_cycle: bad arguments");
+   m->wcycle = wcycle != 0; m->pre = pre_smoothing_steps; m->post = post_smoothing_steps;
+   return 0;
+}
+
+extern "C" int b200pa_mg_set_coarse_solver(b200pa_mg m, double rel_tol, double abs_tol, int max_iter, int jacobi)
+{
+   B200PA_REQUIRE(m && max_iter >= 0, "mg_set_coarse_solver: bad arguments");
+   m->c_rel = rel_tol; m->c_abs = abs_tol; m->c_maxit = max_iter; m->c_jacobi = jacobi;
+   return 0;
+}
+
+// (Re)builds the smoothers from the forms as currently assembled: Jacobi diagonals of all levels, Chebyshev coefficients
+// of levels >= 1 (max_eig[l] <= 0: the reference's power-method estimate, 10 steps, 1e-8, Vector::Randomize(12345)).
+// order / max_eig: arrays over the levels (entry 0 unused) or NULL for order 2 / power method everywhere.
+extern "C" int b200pa_mg_setup(b200pa_mg m, const int *order, const double *max_eig)
+{
+   B200PA_REQUIRE(m, "mg is NULL");
+   b200pa_ctx ctx = m->forms[0]->sp->ctx;
+   NEED_CTX(ctx);
+   for (int l = 0; l < m->nl; ++l)
+   {
+      b200pa_form f = m->forms[l];
+      const int n = f->sp->ndofs;
+      // the diagonal goes through Z[l] (free outside a cycle)
+      if (b200pa_form_assemble_diagonal(f, m->Z[l].as<double>())) { return 1; }
+      if (b200pa_jacobi_setup(ctx, n, m->Z[l].as<double>(), f->n_ess, f->ess.as<int>(), 1.0, m->dinv[l].as<double>())) { return 1; }
+      if (l == 0) { continue; }
+      m->order[l] = order ? order[l] : 2;
+      double lam = max_eig ? max_eig[l] : 0.0;
+      if (lam <= 0.0)
+      {
+         std::vector<double> v0((size_t)std::max(n, 1));
+         b200pa_randomize(12345, n, v0.data());
+         B200PA_CK(cudaMemcpyAsync(m->R[l].p, v0.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+         if (b200pa_power_method(f, m->dinv[l].as<double>(), m->R[l].as<double>(), 10, 1e-8, &lam)) { return 1; }
+      }
+      m->max_eig[l] = lam;
+      m->coeffs[l].assign(5, 0.0);
+      if (b200pa_chebyshev_coeffs(m->order[l], lam, m->coeffs[l].data())) { return 1; }
+   }
+   if (!m->c_jacobi)
+   {
+      const int n0 = m->forms[0]->sp->ndofs;
+      if (alloc(m->ones, sizeof(double) * (size_t)std::max(n0, 1))) { return 1; }
+      std::vector<double> one((size_t)std::max(n0, 1), 1.0);
+      B200PA_CK(cudaMemcpyAsync(m->ones.p, one.data(), sizeof(double) * one.size(), cudaMemcpyHostToDevice, ctx->stream));
+      B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   }
+   return 0;
+}
+
+extern "C" double b200pa_mg_max_eig(b200pa_mg m, int level) { return (m && level >= 0 && level < m->nl) ? m->max_eig[level] : 0.0; }
+extern "C" int b200pa_mg_coarse_iterations(b200pa_mg m) { return m ? m->c_iters : 0; }
+
+// MultigridBase::SmoothingStep (fem/multigrid.cpp:136-162): y = S x (zero) or y += S (x - A y)
+static int mg_smooth(b200pa_mg m, int l, bool zero)
+{
+   b200pa_form f = m->forms[l];
+   b200pa_ctx ctx = f->sp->ctx;
+   const int n = f->sp->ndofs;
+   double *X = m->X[l].as<double>(), *Y = m->Y[l].as<double>(), *R = m->R[l].as<double>(), *Z = m->Z[l].as<double>();
+   if (l == 0)
+   {
+      // the coarse solver: CG from the current Y (zero at this point of the cycle), iterative_mode = true as CGSolver's default
+      b200pa_pcg_result res;
+      const double *dinv = m->c_jacobi ? m->dinv[0].as<double>() : m->ones.as<double>();
+      if (!zero)
+      {
+         // a CGSolver used as a smoother after the first step: y += CG(x - A y)  (only reached with W-cycles / extra steps)
+         if (form_apply(f, Y, R, true, nullptr, nullptr)) { return 1; }
+         k_residual<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, X, R); B200PA_LAUNCHED();
+         B200PA_CK(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)n, ctx->stream));
+         if (b200pa_pcg_solve(f, dinv, R, Z, m->c_rel, m->c_abs, m->c_maxit, &res, nullptr)) { return 1; }
+         m->c_iters += res.final_iter;
+         return b200pa_add(ctx, n, Y, 1.0, Z, Y);
+      }
+      if (b200pa_pcg_solve(f, dinv, X, Y, m->c_rel, m->c_abs, m->c_maxit, &res, nullptr)) { return 1; }
+      m->c_iters += res.final_iter;
+      return 0;
+   }
+   const double *dinv = m->dinv[l].as<double>();
+   if (zero) { return cheb_apply(f, dinv, m->order[l], m->coeffs[l].data(), X, Y, nullptr, false, nullptr, 0); }
+   if (form_apply(f, Y, R, true, nullptr, nullptr)) { return 1; }
+   k_residual<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, X, R); B200PA_LAUNCHED();   // R = X - A Y
+   if (cheb_apply(f, dinv, m->order[l], m->coeffs[l].data(), R, Z, nullptr, false, nullptr, 0)) { return 1; }
+   return b200pa_add(ctx, n, Y, 1.0, Z, Y);
+}
+
+// MultigridBase::Cycle (fem/multigrid.cpp:164-220)
+static int mg_cycle(b200pa_mg m, int l)
+{
+   if (l == 0) { return mg_smooth(m, 0, true); }
+   b200pa_form f = m->forms[l];
+   b200pa_ctx ctx = f->sp->ctx;
+   const int n = f->sp->ndofs, nc = m->forms[l - 1]->sp->ndofs;
+   for (int i = 0; i < m->pre; ++i) { if (mg_smooth(m, l, !m->wcycle && i == 0)) { return 1; } }
+   // residual, restricted: X[l-1] = P^T (X[l] - A Y[l]); Y[l-1] = 0
+   if (form_apply(f, m->Y[l].as<double>(), m->R[l].as<double>(), true, nullptr, nullptr)) { return 1; }
+   k_residual<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, m->X[l].as<double>(), m->R[l].as<double>()); B200PA_LAUNCHED();
+   if (b200pa_transfer_mult_transpose(m->P[l - 1], m->R[l].as<double>(), m->X[l - 1].as<double>())) { return 1; }
+   B200PA_CK(cudaMemsetAsync(m->Y[l - 1].p, 0, sizeof(double) * (size_t)nc, ctx->stream));
+   if (mg_cycle(m, l - 1)) { return 1; }
+   if (m->wcycle && mg_cycle(m, l - 1)) { return 1; }
+   // prolongate and add
+   if (b200pa_transfer_mult(m->P[l - 1], m->Y[l - 1].as<double>(), m->Z[l].as<double>())) { return 1; }
+   if (b200pa_add(ctx, n, m->Y[l].as<double>(), 1.0, m->Z[l].as<double>(), m->Y[l].as<double>())) { return 1; }
+   for (int i = 0; i < m->post; ++i) { if (mg_smooth(m, l, false)) { return 1; } }
+   return 0;
+}
+
+// MultigridBase::Mult (fem/multigrid.cpp:107-134): one cycle from a zero initial guess, y = M x on the finest level
+extern "C" int b200pa_mg_mult(b200pa_mg m, const double *x_dev, double *y_dev)
+{
+   B200PA_REQUIRE(m && x_dev && y_dev, "mg_mult: NULL argument");
+   b200pa_form f = m->forms[m->nl - 1];
+   b200pa_ctx ctx = f->sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(m->nl == 1 || !m->coeffs[m->nl - 1].empty(), "mg_mult: call b200pa_mg_setup first");
+   const size_t vb = sizeof(double) * (size_t)f->sp->ndofs;
+   const int L = m->nl - 1;
+   B200PA_CK(cudaMemcpyAsync(m->X[L].p, x_dev, vb, cudaMemcpyDeviceToDevice, ctx->stream));
+   B200PA_CK(cudaMemsetAsync(m->Y[L].p, 0, vb, ctx->stream));
+   if (mg_cycle(m, L)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(y_dev, m->Y[L].p, vb, cudaMemcpyDeviceToDevice, ctx->stream));
+   return 0;
+}
+
+// CGSolver::Mult (linalg/solvers.cpp:869-1050) on the finest level's constrained operator with the multigrid cycle as the
+// preconditioner (examples/ex26.cpp:206-215); same scalar state / stopping rules as b200pa_pcg_solve.
+extern "C" int b200pa_pcg_solve_mg(b200pa_mg m, const double *b_dev, double *x_dev, double rel_tol, double abs_tol, int max_iter,
+                                   b200pa_pcg_result *res, double *norms_host)
+{
+   B200PA_REQUIRE(m && b_dev && x_dev && res, "pcg_solve_mg: NULL argument");
+   b200pa_form f = m->forms[m->nl - 1];
+   b200pa_space sp = f->sp;
+   b200pa_ctx ctx = sp->ctx;
+   NEED_CTX(ctx);
+   B200PA_REQUIRE(max_iter >= 0, "pcg_solve_mg: max_iter < 0");
+   const int n = sp->ndofs;
+   const size_t vb = sizeof(double) * (size_t)std::max(n, 1);
+   // the outer solver's vectors live apart from the form's (the coarse-level PCG and the smoothers use those)
+   DevBuf rb, db, zb, qb, stb, nb;
+   if (alloc(rb, vb) || alloc(db, vb) || alloc(zb, vb) || alloc(qb, vb) || alloc(stb, sizeof(PcgState)) || alloc(nb, sizeof(double) * ((size_t)max_iter + 2))) { return 1; }
+   struct Free { DevBuf *b[6]; ~Free() { for (DevBuf *x : b) { x->release(); } } } freer{{&rb, &db, &zb, &qb, &stb, &nb}};
+   double *r = rb.as<double>(), *d = db.as<double>(), *z = zb.as<double>(), *q = qb.as<double>();
+   PcgState *st = stb.as<PcgState>();
+   double *norms = nb.as<double>();
+   cudaStream_t s = ctx->stream;
+   const int grid = grid1d(ctx, n);
+   PcgState h0;
+   std::memset(&h0, 0, sizeof(h0));
+   h0.rel_tol = rel_tol; h0.abs_tol = abs_tol; h0.max_iter = max_iter; h0.iter = 1;
+   B200PA_CK(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, s));
+   B200PA_CK(cudaMemsetAsync(norms, 0, sizeof(double) * ((size_t)max_iter + 2), s));
+   // r = b - A x; z = M r; d = z; nom = (d, r)
+   if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
+   if (n > 0) { k_residual<<<grid, 256, 0, s>>>(n, b_dev, r); B200PA_LAUNCHED(); }
+   if (b200pa_mg_mult(m, r, z)) { return 1; }
+   k_dot_step<<<grid, 256, 0, s>>>(n, r, z, nullptr, ctx->d_partials, ctx->d_ticket, st, norms, 1); B200PA_LAUNCHED();
+   B200PA_CK(cudaMemcpyAsync(d, z, vb, cudaMemcpyDeviceToDevice, s));
+   if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, st)) { return 1; }
+   int *h_done = (int *)(ctx->h_result + 4);
+   for (int it = 1; it <= std::max(max_iter, 1); ++it)
+   {
+      // the cycle contains a nested solve with host synchronisation anyway: poll the outer state every iteration
+      B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200PA_CK(cudaStreamSynchronize(s));
+      if (*h_done) { break; }
+      if (n > 0) { k_pcg_update_plain<<<grid, 256, 0, s>>>(n, x_dev, r, q, d, st); B200PA_LAUNCHED(); }
+      if (b200pa_mg_mult(m, r, z)) { return 1; }
+      k_dot_step<<<grid, 256, 0, s>>>(n, r, z, nullptr, ctx->d_partials, ctx->d_ticket, st, norms, 2); B200PA_LAUNCHED();
+      if (n > 0) { k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st); B200PA_LAUNCHED(); }
+      if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, st)) { return 1; }
+   }
+   PcgState hs;
+   B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
+   B200PA_CK(cudaStreamSynchronize(s));
+   B200PA_REQUIRE(!hs.nonfinite, "pcg_solve_mg: non-finite (B r, r) or (A d, d)");
+   B200PA_REQUIRE(hs.done, "pcg_solve_mg: internal error (loop ended without a terminal state)");
+   res->final_iter = hs.final_iter;
+   res->converged = hs.converged;
+   res->initial_norm = hs.nom0 >= 0.0 ? sqrt(hs.nom0) : hs.nom0;
+   res->final_norm = (hs.nom0 < 0.0) ? hs.nom0 : sqrt(hs.betanom);
+   if (norms_host)
+   {
+      B200PA_CK(cudaMemcpyAsync(norms_host, norms, sizeof(double) * ((size_t)hs.final_iter + 1), cudaMemcpyDeviceToHost, s));
+      B200PA_CK(cudaStreamSynchronize(s));
+   }
    return 0;
 }

@@ -468,3 +468,27 @@ extern "C" int b200pa_basis(int p, int q1d, double *B, double *G, double *w1d, d
    }
    return 0;
 }
+
+
+// The 1-D matrix of the order-refinement transfer (TensorProductPRefinementTransferOperator, fem/transfer.cpp:2223-2262):
+// B[q + (pf+1) d] = d-th GLL-nodal Lagrange basis function of order pc at the q-th GLL node of order pf.
+extern "C" int b200pa_basis_transfer(int pc, int pf, double *B)
+{
+   if (pc < 1 || pf < pc || pf > 13 || !B) { return hfail("basis_transfer: orders out of range"); }
+   const int DC = pc + 1, DF = pf + 1;
+   double xc[16], xf[16];
+   gauss_lobatto(DC, xc);
+   gauss_lobatto(DF, xf);
+   for (int d = 0; d < DC; ++d)
+   {
+      double den = 1.0;
+      for (int m = 0; m < DC; ++m) { if (m != d) { den *= (xc[d] - xc[m]); } }
+      for (int q = 0; q < DF; ++q)
+      {
+         double val = 1.0;
+         for (int m = 0; m < DC; ++m) { if (m != d) { val *= (xf[q] - xc[m]); } }
+         B[q + DF * d] = val / den;
+      }
+   }
+   return 0;
+}

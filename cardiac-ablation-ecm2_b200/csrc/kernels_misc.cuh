@@ -86,6 +86,24 @@ __global__ void k_segment_sum(int ndofs, const int *__restrict__ offsets, const 
    }
 }
 
+// the same over a LIST of dof tiles (tile t = dofs [t TS, (t+1) TS)): one launch finishes all the tiles an element chunk of
+// the pipelined host-buffer apply completes (b200pa_form_mult_host), however scattered they are
+template <bool CONSTR>
+__global__ void k_segment_sum_tiles(const int *__restrict__ tiles, int TS, int ndofs, const int *__restrict__ offsets,
+                                    const double *__restrict__ yS, double *__restrict__ y, const unsigned char *__restrict__ ess_mask,
+                                    const double *__restrict__ x)
+{
+   const int bpt = TS / blockDim.x;                 // blocks per tile (TS is a multiple of the block size)
+   const int t = tiles[blockIdx.x / bpt];
+   const int i = t * TS + (blockIdx.x % bpt) * blockDim.x + threadIdx.x;
+   if (i >= ndofs) { return; }
+   double v = 0.0;
+   const int j1 = offsets[i + 1];
+   for (int j = offsets[i]; j < j1; ++j) { v += yS[j]; }
+   if (CONSTR && ess_mask[i]) { v = x[i]; }
+   y[i] = v;
+}
+
 // multi-GPU with the peer-memory exchange: shared dofs only get their local partial sum here (the exchange
 // kernel finishes them: remote contributions, constraint, their part of the dot); everything else is final
 template <bool CONSTR, bool DOT>

@@ -267,6 +267,36 @@ int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev, int order,
                                double *x_dev, double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
                                double *norms_host);
 
+/* ------------------------------------------------------ p-multigrid (one GPU) */
+/* Order-refinement transfer between two forms on the SAME mesh (coarse order <= fine order):
+ * TensorProductPRefinementTransferOperator::{Mult, MultTranspose} (fem/transfer.cpp:2223-2296, 2542-2592) wrapped
+ * in the RectangularConstrainedOperator a GeometricMultigrid gives it (fem/multigrid.cpp:281-296): essential dofs of
+ * either level (b200pa_form_set_essential) count as zero on input and are zeroed on output.
+ * B_any: [DF x DC] column-major, the coarse 1-D basis at the fine nodes in lexicographic order - the DofToQuad::B
+ * the reference operator builds (b200pa_basis_transfer for the synthetic builder's GLL-nodal H1 bases). */
+typedef struct b200pa_transfer_s *b200pa_transfer;
+int b200pa_transfer_create(b200pa_form coarse, b200pa_form fine, const double *B_any, b200pa_transfer *out);
+int b200pa_transfer_destroy(b200pa_transfer t);
+int b200pa_transfer_mult(b200pa_transfer t, const double *xc_dev, double *yf_dev);            /* prolongation */
+int b200pa_transfer_mult_transpose(b200pa_transfer t, const double *xf_dev, double *yc_dev);  /* restriction  */
+/* Multigrid (fem/multigrid.hpp, fem/multigrid.cpp:107-220; the hierarchy of examples/ex26.cpp): forms[0] is the coarsest
+ * level, transfers[l] connects forms[l] and forms[l+1].  Levels >= 1: OperatorChebyshevSmoother (b200pa_mg_setup: order and
+ * largest-eigenvalue estimate per level, <= 0 = the reference's power method); level 0: CGSolver to (rel_tol, abs_tol,
+ * max_iter), unpreconditioned as in ex26 or with OperatorJacobiSmoother (jacobi = 1).  b200pa_mg_setup must be called again
+ * after the forms are re-assembled.  b200pa_mg_mult = MultigridBase::Mult: one V- (or W-) cycle from a zero guess.
+ * b200pa_pcg_solve_mg = CGSolver::Mult on the finest constrained operator preconditioned by the cycle. */
+typedef struct b200pa_mg_s *b200pa_mg;
+int b200pa_mg_create(int nlevels, const b200pa_form *forms, const b200pa_transfer *transfers, b200pa_mg *out);
+int b200pa_mg_destroy(b200pa_mg m);
+int b200pa_mg_set_cycle(b200pa_mg m, int wcycle, int pre_smoothing_steps, int post_smoothing_steps);
+int b200pa_mg_set_coarse_solver(b200pa_mg m, double rel_tol, double abs_tol, int max_iter, int jacobi);
+int b200pa_mg_setup(b200pa_mg m, const int *order, const double *max_eig);
+double b200pa_mg_max_eig(b200pa_mg m, int level);
+int b200pa_mg_coarse_iterations(b200pa_mg m);
+int b200pa_mg_mult(b200pa_mg m, const double *x_dev, double *y_dev);
+int b200pa_pcg_solve_mg(b200pa_mg m, const double *b_dev, double *x_dev, double rel_tol, double abs_tol, int max_iter,
+                        b200pa_pcg_result *res, double *norms_host);
+
 /* ------------------------------------------------------ multi-GPU (one rank per GPU) */
 /* Shared-dof exchange ≙ DeviceConformingProlongationOperator::{Mult,MultTranspose}
  * (fem/pfespace.cpp:5259-5532; GroupCommunicator, general/communication.cpp:723-1120) and
@@ -359,6 +389,8 @@ int b200pa_randomize(int seed, long long n, double *out_host);
  * (fem/fe/fe_base.cpp:2619-2662, fem/intrules.cpp): B,G f64[q1d*d1d] column-major, w1d f64[q1d],
  * W f64[q1d^3] */
 int b200pa_basis(int p, int q1d, double *B, double *G, double *w1d, double *W, double *gll_nodes);
+/* the 1-D matrix of the order-refinement transfer pc -> pf for these bases (b200pa_transfer_create): [pf+1, pc+1] column-major */
+int b200pa_basis_transfer(int pc, int pf, double *B);
 
 #ifdef __cplusplus
 }
