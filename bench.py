@@ -503,14 +503,14 @@ def main():
                          "factorised form for affine meshes (b200pa_form_set_factorised)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="headline only (profiling / tuning runs)")
-    ap.add_argument("--legs", default="all", help="comma list of: factorised,bioheat,rf,sweep,c3,c5,parity,strong (default all)")
+    ap.add_argument("--legs", default="all", help="comma list of: factorised,bioheat,rf,sweep,c3,c5,parity,strong,mg (default all)")
     ap.add_argument("--c5-elems", type=int, default=C5_N, help="per-GPU N of the configs[4] legs (tests use a small one)")
     ap.add_argument("--budget-s", type=float, default=600.0, help="optional legs are skipped once the run is older than this")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
-    legs = set("factorised,bioheat,rf,sweep,c3,c5,parity,strong".split(",")) if args.legs == "all" else set(args.legs.split(","))
+    legs = set("factorised,bioheat,rf,sweep,c3,c5,parity,strong,mg".split(",")) if args.legs == "all" else set(args.legs.split(","))
     if args.no_extras:
         legs = set()
 
@@ -791,6 +791,55 @@ def main():
             S.close()
             return r
         guarded("c3", c3)
+
+    # ---- the electrostatic solve (pure diffusion, Dirichlet on two faces) to a tolerance: Jacobi-PCG against PCG
+    #      preconditioned by the p-multigrid cycle (orders 1 -> 2, Chebyshev smoothers, CG coarse solve: examples/ex26.cpp)
+    if world == 1 and "mg" in legs and p == 2:
+        def mg_leg():
+            from b200pa import partition
+            nn = min(n, 64)
+            GNm = (nn, nn, nn)
+            levels = []
+            for pp in (1, 2):
+                mm = partition.build_part(GNm, (1, 1, 1), 0, pp, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
+                bb = b200pa.basis(pp)
+                spp = b200pa.Space(ctx, pp + 1, pp + 2, mm["ne"], mm["ndofs"], mm["gather_map"], bb["B"], bb["G"])
+                spp.geometry_from_vertices(bb["W"], mm["vertices"], mm["elem_vertices"])
+                lat = mm["lattice"].reshape(-1, 3)
+                xyz = (lat // pp + bb["gll"][lat % pp]) / np.array(GNm, dtype=np.float64)
+                Tl = ctx.to_dev(37.0 + 20.0 * np.exp(-40.0 * ((xyz - 0.5) ** 2).sum(1)))
+                ff = b200pa.Form(spp)
+                ff.assemble_diffusion(spp.coeff_linear(PHYS["s0"], PHYS["as_"], 37.0, Tl))
+                ess = b200pa.essential_dofs(mm["bdr_attr"], [1, 6])
+                ff.set_essential(ess)
+                levels.append((spp, ff, mm, ess, lat))
+            spf, ffn, mf, ess, lat = levels[1]
+            T = b200pa.Transfer(levels[0][1], ffn, b200pa.basis_transfer(1, 2))
+            mg = b200pa.Multigrid([levels[0][1], ffn], [T])
+            mg.set_coarse_solver(1e-2, 0.0, 200, jacobi=True)
+            mg.setup()
+            phi_bc = np.zeros(mf["ndofs"])
+            phi_bc[ess] = PHYS["V"] * (1.0 - lat[ess, 2] / (2 * nn))
+            out = {"what": f"electrostatic solve div sigma(T) grad phi = 0 to rel 1e-8, order 2, hex {nn}^3, {mf['ndofs']} dofs: "
+                           "OperatorJacobiSmoother against the p-multigrid V-cycle (orders 1-2) as the CG preconditioner"}
+            for name in ("jacobi", "p_multigrid"):
+                def solve():
+                    phi = ctx.to_dev(phi_bc)
+                    rhs = ctx.zeros(mf["ndofs"])
+                    ffn.eliminate_rhs(phi, rhs)
+                    if name == "jacobi":
+                        return ffn.pcg(ffn.jacobi(), rhs, phi, 1e-8, 0.0, 5000, want_norms=False)[0]
+                    return mg.pcg(rhs, phi, 1e-8, 0.0, 500, want_norms=False)[0]
+                solve()
+                rr = [None]
+                ms = env.timed(lambda: rr.__setitem__(0, solve()), 1)
+                out[name] = {"ms": ms, "iters": int(rr[0].final_iter), "converged": bool(rr[0].converged)}
+            out["coarse_cg_iterations_total"] = mg.coarse_iterations()
+            mg.close(); T.close()
+            for spp, ff, *_ in levels:
+                ff.close(); spp.close()
+            return out
+        guarded("p_multigrid", mg_leg)
 
     # ---- configs[4]: N=199 per GPU (398^3 elements, 506 M dofs at 8 GPUs): weak leg at any N, incl. the one-GPU base
     c5n = args.c5_elems

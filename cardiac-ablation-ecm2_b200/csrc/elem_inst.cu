@@ -6,6 +6,10 @@
 #include "elem_launch.cuh"
 #include "pa_element_kernel.cuh"
 #include "pa_apply_kernel.cuh"
+#if B200PA_D == 7
+#include "pa_apply_dmma.cuh"
+#endif
+#include <cstdlib>
 
 #ifndef B200PA_D
 #error "compile with -DB200PA_D=<D1D> -DB200PA_Q=<Q1D>"
@@ -100,8 +104,44 @@ int run_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
    return (int)cudaGetLastError();
 }
 
+#if B200PA_D == 7
+// order 6, stored q-data: the variant with the row phases on the FP64 tensor cores (pa_apply_dmma.cuh).  B200PA_DMMA=0 in the
+// environment selects the DFMA kernel instead (read once; for A/B measurements)
+template <bool DIFF, bool MASS>
+int run_fused_dmma(const ElemArgs &a, int num_sms, cudaStream_t stream)
+{
+   auto kern = pa_apply_dmma_kernel<DIFF, MASS>;
+   int blocks_per_sm = 0;
+   {
+      struct ThisKernel {};
+      const int e = kernel_setup<ThisKernel>(kern, DmmaCfg::NT, DmmaCfg::SMEM_BYTES, &blocks_per_sm);
+      if (e) { return e; }
+   }
+   if (a.NE <= 0) { return 0; }
+   if (((((unsigned long long)a.pa_diff) | ((unsigned long long)a.pa_mass)) & 15ull)) { return (int)cudaErrorMisalignedAddress; }
+   ElemParams<D, Q> P;
+   fill_params(P, a);
+   const int grid = a.NE < num_sms * blocks_per_sm ? a.NE : num_sms * blocks_per_sm;
+   kern<<<grid, DmmaCfg::NT, DmmaCfg::SMEM_BYTES, stream>>>(P);
+   return (int)cudaGetLastError();
+}
+static bool use_dmma()
+{
+   static const bool on = [] { const char *e = getenv("B200PA_DMMA"); return !(e && e[0] == '0'); }();
+   return on;
+}
+#endif
+
 int run_apply_fused(const ElemArgs &a, int num_sms, cudaStream_t stream)
 {
+#if B200PA_D == 7
+   if (!a.geo && use_dmma())
+   {
+      if (a.pa_diff && a.pa_mass) { return run_fused_dmma<true, true>(a, num_sms, stream); }
+      if (a.pa_diff) { return run_fused_dmma<true, false>(a, num_sms, stream); }
+      if (a.pa_mass) { return run_fused_dmma<false, true>(a, num_sms, stream); }
+   }
+#endif
    if (a.pa_diff && a.geo) { return a.pa_mass ? run_fused<true, true, true>(a, num_sms, stream) : run_fused<true, false, true>(a, num_sms, stream); }
    if (a.pa_diff && a.pa_mass) { return run_fused<true, true, false>(a, num_sms, stream); }
    if (a.pa_diff) { return run_fused<true, false, false>(a, num_sms, stream); }

@@ -205,6 +205,7 @@ class PAOperator : public mfem::Operator
    friend class PCGSolver;
    friend class JacobiSmoother;
    friend class ChebyshevSmoother;
+   friend class PMultigrid;
 
    void Project(mfem::Coefficient *c, std::vector<double> &out)
    {
@@ -358,10 +359,80 @@ public:
    const JacobiSmoother &Jacobi() const { return jac; }
 };
 
+/// p-multigrid on the GPU: mfem::GeometricMultigrid over an order-refined FiniteElementSpaceHierarchy (fem/multigrid.hpp) with the
+/// smoothers and coarse solver of examples/ex26.cpp - OperatorChebyshevSmoother (order 2, power-method estimate) on the upper
+/// levels, unpreconditioned CG (rel. tol. 1e-2, 200 iterations) on the coarsest - for the diffusion (+ mass) operator.  The
+/// order-refinement transfers use the 1-D matrices TensorProductPRefinementTransferOperator builds (fem/transfer.cpp:2240-2262).
+/// A Solver: Mult is one V-cycle from a zero guess (MultigridBase::Mult); b200::PCGSolver fuses it as its preconditioner.
+class PMultigrid : public mfem::Solver
+{
+   std::vector<std::unique_ptr<PAOperator>> ops;
+   std::vector<b200pa_transfer> transfers;
+   b200pa_mg mg = nullptr;
+   mutable DeviceBuffer d_x, d_y;
+   friend class PCGSolver;
+public:
+   PMultigrid(const mfem::FiniteElementSpaceHierarchy &h, mfem::Coefficient *kdiff, mfem::Coefficient *cmass, const mfem::Array<int> &ess_bdr,
+              int cheb_order = 2, bool factorised = false)
+      : mfem::Solver(h.GetFinestFESpace().GetVSize(), false)
+   {
+      const int nl = h.GetNumLevels();
+      bool have_ess = false;
+      for (int i = 0; i < ess_bdr.Size(); i++) { have_ess = have_ess || ess_bdr[i]; }
+      std::vector<b200pa_form> forms;
+      for (int l = 0; l < nl; l++)
+      {
+         const mfem::FiniteElementSpace &fes = h.GetFESpaceAtLevel(l);
+         mfem::Array<int> ess;
+         if (have_ess) { fes.GetEssentialTrueDofs(ess_bdr, ess); }
+         ops.emplace_back(new PAOperator(fes, kdiff, cmass, ess, factorised));
+         forms.push_back(ops.back()->form);
+      }
+      for (int l = 0; l + 1 < nl; l++)
+      {
+         const mfem::FiniteElementSpace &lf = h.GetFESpaceAtLevel(l), &hf = h.GetFESpaceAtLevel(l + 1);
+         MFEM_VERIFY(lf.GetMesh() == hf.GetMesh(), "b200::PMultigrid: order refinement only (the levels share one mesh)");
+         const mfem::TensorBasisElement *htel = dynamic_cast<const mfem::TensorBasisElement *>(hf.GetTypicalFE());
+         MFEM_VERIFY(htel, "b200::PMultigrid: tensor-product elements expected");
+         const mfem::Array<int> &hdofmap = htel->GetDofMap();
+         const mfem::IntegrationRule &irn = hf.GetTypicalFE()->GetNodes();
+         mfem::IntegrationRule irLex = irn;
+         for (int i = 0; i < irn.GetNPoints(); ++i) { const int j = hdofmap[i] >= 0 ? hdofmap[i] : -1 - hdofmap[i]; irLex.IntPoint(i) = irn.IntPoint(j); }
+         const mfem::DofToQuad &maps = lf.GetTypicalFE()->GetDofToQuad(irLex, mfem::DofToQuad::TENSOR);
+         b200pa_transfer t = nullptr;
+         Check(b200pa_transfer_create(forms[l], forms[l + 1], maps.B.HostRead(), &t));
+         transfers.push_back(t);
+      }
+      Check(b200pa_mg_create(nl, forms.data(), transfers.data(), &mg));
+      Check(b200pa_mg_set_cycle(mg, 0, 1, 1));
+      Check(b200pa_mg_set_coarse_solver(mg, 1e-2, 0.0, 200, 0));
+      std::vector<int> order(nl, cheb_order);
+      Check(b200pa_mg_setup(mg, order.data(), nullptr));
+   }
+   ~PMultigrid()
+   {
+      b200pa_mg_destroy(mg);
+      for (b200pa_transfer t : transfers) { b200pa_transfer_destroy(t); }
+   }
+   void SetCycleType(bool wcycle, int pre, int post) { Check(b200pa_mg_set_cycle(mg, wcycle ? 1 : 0, pre, post)); }
+   void SetCoarseSolver(double rel_tol, double abs_tol, int max_iter, bool jacobi) { Check(b200pa_mg_set_coarse_solver(mg, rel_tol, abs_tol, max_iter, jacobi ? 1 : 0)); Check(b200pa_mg_setup(mg, nullptr, nullptr)); }
+   void SetOperator(const mfem::Operator &) override {}
+   const PAOperator &FineOperator() const { return *ops.back(); }
+   double GetMaxEigEstimate(int level) const { return b200pa_mg_max_eig(mg, level); }
+   /// one cycle: y = M x (MultigridBase::Mult, fem/multigrid.cpp:107-134)
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      d_x.Upload(x.HostRead(), sizeof(double) * height);
+      d_y.Resize(sizeof(double) * height);
+      Check(b200pa_mg_mult(mg, d_x.D(), d_y.D()));
+      d_y.Download(y.HostWrite(), sizeof(double) * height);
+   }
+};
+
 /// mfem::CGSolver on the GPU (linalg/solvers.cpp:869-1050): an mfem::IterativeSolver - it can be handed wherever the
 /// reference takes an IterativeSolver& - whose Mult runs the whole loop device-resident on a b200::PAOperator.
-///   SetPreconditioner   b200::JacobiSmoother or b200::ChebyshevSmoother (fused into the loop); none = plain CG, as in the
-///                       reference; any other Solver aborts - there is no CPU fallback.
+///   SetPreconditioner   b200::JacobiSmoother, b200::ChebyshevSmoother or b200::PMultigrid (fused into the loop); none = plain
+///                       CG, as in the reference; any other Solver aborts - there is no CPU fallback.
 ///   SetPrintLevel       the reference's PrintLevel flags print the reference's lines from the recorded (B r, r) history.
 ///   SetMonitor          MonitorResidual / MonitorSolution are called for every iteration AFTER the solve with the recorded
 ///                       norms; the vectors they receive are the final residual and solution (the loop keeps its iterates
@@ -384,8 +455,8 @@ public:
 
    void SetPreconditioner(mfem::Solver &pr) override
    {
-      MFEM_VERIFY(dynamic_cast<JacobiSmoother *>(&pr) || dynamic_cast<ChebyshevSmoother *>(&pr),
-                  "b200::PCGSolver: the preconditioner must be a b200::JacobiSmoother or b200::ChebyshevSmoother (no CPU fallback)");
+      MFEM_VERIFY(dynamic_cast<JacobiSmoother *>(&pr) || dynamic_cast<ChebyshevSmoother *>(&pr) || dynamic_cast<PMultigrid *>(&pr),
+                  "b200::PCGSolver: the preconditioner must be a b200::JacobiSmoother, ChebyshevSmoother or PMultigrid (no CPU fallback)");
       mfem::IterativeSolver::SetPreconditioner(pr);
    }
    void SetOperator(const mfem::Operator &o) override
@@ -405,7 +476,17 @@ public:
       const ChebyshevSmoother *cheb = dynamic_cast<const ChebyshevSmoother *>(prec);
       if (jac && !jac->GetOperator()) { const_cast<JacobiSmoother *>(jac)->SetOperator(*op); }
       if (cheb && !cheb->Jacobi().GetOperator()) { const_cast<ChebyshevSmoother *>(cheb)->SetOperator(*op); }
-      if (cheb)
+      const PMultigrid *pmg = dynamic_cast<const PMultigrid *>(prec);
+      if (pmg)
+      {
+         MFEM_VERIFY(&pmg->FineOperator() == op, "b200::PCGSolver: the operator must be the multigrid's finest-level operator (PMultigrid::FineOperator)");
+         DeviceBuffer db, dx;
+         db.Upload(b.HostRead(), sizeof(double) * height);
+         dx.Upload(x.HostRead(), sizeof(double) * height);
+         Check(b200pa_pcg_solve_mg(pmg->mg, db.D(), dx.D(), rel_tol, abs_tol, max_iter, &res, norms.data()));
+         dx.Download(x.HostReadWrite(), sizeof(double) * height);
+      }
+      else if (cheb)
       {
          DeviceBuffer db, dx;
          db.Upload(b.HostRead(), sizeof(double) * height);

@@ -767,6 +767,175 @@ static int dump_markers(int argc, char **argv)
    return 0;
 }
 
+// -------------------------------------------------------------------- dump_mg
+// dump_mg OUT kind nx ny nz bc orders...: the p-multigrid of examples/ex26.cpp (GeometricMultigrid over an order-refined
+// FiniteElementSpaceHierarchy, OperatorChebyshevSmoother of order 2 on the upper levels, unpreconditioned CG on the
+// coarsest) for the diffusion + mass operator with function coefficients.  Per level: the space tables and q-data; per
+// transfer: its 1-D matrix, P x and P^T x (raw and with the essential-dof constraints); one V-cycle; PCG preconditioned by it.
+struct RefMG : public GeometricMultigrid
+{
+   FunctionCoefficient kc, mc;
+   Array<double> eigs;
+   RefMG(FiniteElementSpaceHierarchy &h, Array<int> &ess_bdr) : GeometricMultigrid(h, ess_bdr), kc(kfun), mc(mfun)
+   {
+      for (int l = 0; l < h.GetNumLevels(); ++l)
+      {
+         FiniteElementSpace &fes = h.GetFESpaceAtLevel(l);
+         BilinearForm *form = new BilinearForm(&fes);
+         form->SetAssemblyLevel(AssemblyLevel::PARTIAL);
+         form->AddDomainIntegrator(new DiffusionIntegrator(kc));
+         form->AddDomainIntegrator(new MassIntegrator(mc));
+         form->Assemble();
+         bfs.Append(form);
+         OperatorPtr opr; opr.SetType(Operator::ANY_TYPE);
+         Array<int> none;
+         const Array<int> &ess = essentialTrueDofs.Size() ? *essentialTrueDofs[l] : none;
+         bfs[l]->FormSystemMatrix(ess, opr);
+         opr.SetOperatorOwner(false);
+         if (l == 0)
+         {
+            CGSolver *pcg = new CGSolver();
+            pcg->SetPrintLevel(-1); pcg->SetMaxIter(200); pcg->SetRelTol(sqrt(1e-4)); pcg->SetAbsTol(0.0);
+            pcg->SetOperator(*opr.Ptr());
+            AddLevel(opr.Ptr(), pcg, true, true);
+            eigs.Append(0.0);
+         }
+         else
+         {
+            Vector diag(fes.GetTrueVSize());
+            bfs[l]->AssembleDiagonal(diag);
+            // the estimate OperatorChebyshevSmoother's power-method constructor makes (linalg/solvers.cpp:497-511), recorded
+            OperatorJacobiSmoother invD(diag, ess, 1.0);
+            ProductOperator dp(&invD, opr.Ptr(), false, false);
+            PowerMethod pm;
+            Vector ev(fes.GetTrueVSize());
+            const double lam = pm.EstimateLargestEigenvalue(dp, ev, 10, 1e-8, 12345);
+            eigs.Append(lam);
+            AddLevel(opr.Ptr(), new OperatorChebyshevSmoother(*opr, diag, ess, 2, lam), true, true);
+         }
+      }
+   }
+   const Operator *ConstrainedP(int l) const { return prolongations[l]; }
+   const Array<int> &Ess(int l) const { static Array<int> none; return essentialTrueDofs.Size() ? *essentialTrueDofs[l] : none; }
+   BilinearForm *Form(int l) { return bfs[l]; }
+};
+
+static int dump_mg(int argc, char **argv)
+{
+   if (argc < 9) { cerr << "dump_mg OUT kind nx ny nz bc(none|zfaces|all) order0 order1 ...\n"; return 2; }
+   Dumper D(argv[2]);
+   const string kind = argv[3];
+   const int nx = atoi(argv[4]), ny = atoi(argv[5]), nz = atoi(argv[6]);
+   const string bc = argv[7];
+   vector<int> orders;
+   for (int i = 8; i < argc; i++) { orders.push_back(atoi(argv[i])); }
+   Device device("cpu");
+   Mesh *mesh = new Mesh(make_mesh(kind, nx, ny, nz, 1.0, 1.0, 1.0));
+   vector<FiniteElementCollection *> fecs;
+   fecs.push_back(new H1_FECollection(orders[0], 3));
+   FiniteElementSpace *coarse = new FiniteElementSpace(mesh, fecs[0]);
+   FiniteElementSpaceHierarchy h(mesh, coarse, true, true);
+   for (size_t l = 1; l < orders.size(); l++)
+   {
+      fecs.push_back(new H1_FECollection(orders[l], 3));
+      h.AddOrderRefinedLevel(fecs.back());
+   }
+   Array<int> ess_bdr(mesh->bdr_attributes.Max()); ess_bdr = 0;
+   if (bc == "all") { ess_bdr = 1; }
+   else if (bc == "zfaces") { ess_bdr[0] = 1; ess_bdr[5] = 1; }
+   RefMG mg(h, ess_bdr);
+   mg.SetCycleType(Multigrid::CycleType::VCYCLE, 1, 1);
+   const int NL = h.GetNumLevels(), NE = mesh->GetNE();
+   D.iscalar("nlevels", NL); D.iscalar("NE", NE);
+   {
+      Vector vx(3 * mesh->GetNV());
+      for (int i = 0; i < mesh->GetNV(); i++) { for (int d = 0; d < 3; d++) { vx(3 * i + d) = mesh->GetVertex(i)[d]; } }
+      D.vec("vertices", vx);
+      Array<int> ev(8 * NE);
+      for (int e = 0; e < NE; e++) { const int *v = mesh->GetElement(e)->GetVertices(); for (int j = 0; j < 8; j++) { ev[8 * e + j] = v[j]; } }
+      D.arr("elem_vertices", ev);
+   }
+   for (int l = 0; l < NL; l++)
+   {
+      FiniteElementSpace &fes = h.GetFESpaceAtLevel(l);
+      const FiniteElement &el = *fes.GetTypicalFE();
+      const IntegrationRule &ir = DiffusionIntegrator::GetRule(el, el);
+      const DofToQuad &maps = el.GetDofToQuad(ir, DofToQuad::TENSOR);
+      const string t = to_string(l);
+      D.iscalar("order" + t, orders[l]); D.iscalar("ndofs" + t, fes.GetNDofs());
+      D.arr("B" + t, maps.B); D.arr("G" + t, maps.G); D.arr("W" + t, ir.GetWeights());
+      const ElementRestriction *R = dynamic_cast<const ElementRestriction *>(fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+      D.arr("gather_map" + t, R->GatherMap());
+      QuadratureSpace qs(*mesh, ir);
+      CoefficientVector kq(mg.kc, qs, CoefficientStorage::COMPRESSED), mq(mg.mc, qs, CoefficientStorage::COMPRESSED);
+      D.vec("kq" + t, kq); D.vec("mq" + t, mq);
+      D.arr("ess" + t, mg.Ess(l));
+      D.scalar("max_eig" + t, mg.eigs[l]);
+   }
+   for (int l = 0; l + 1 < NL; l++)
+   {
+      FiniteElementSpace &lf = h.GetFESpaceAtLevel(l), &hf = h.GetFESpaceAtLevel(l + 1);
+      // the 1-D matrix as TensorProductPRefinementTransferOperator's constructor forms it (fem/transfer.cpp:2240-2262)
+      const FiniteElement &el = *lf.GetTypicalFE();
+      const TensorBasisElement *htel = dynamic_cast<const TensorBasisElement *>(hf.GetTypicalFE());
+      const Array<int> &hdofmap = htel->GetDofMap();
+      const IntegrationRule &irn = hf.GetTypicalFE()->GetNodes();
+      IntegrationRule irLex = irn;
+      for (int i = 0; i < irn.GetNPoints(); ++i) { const int j = hdofmap[i] >= 0 ? hdofmap[i] : -1 - hdofmap[i]; irLex.IntPoint(i) = irn.IntPoint(j); }
+      const DofToQuad &maps = el.GetDofToQuad(irLex, DofToQuad::TENSOR);
+      const string t = to_string(l);
+      D.arr("PB" + t, maps.B);
+      Vector xc(lf.GetNDofs()), xf(hf.GetNDofs()), yf(hf.GetNDofs()), yc(lf.GetNDofs());
+      xc.Randomize(11 + l); xf.Randomize(23 + l);
+      D.vec("xc" + t, xc); D.vec("xf" + t, xf);
+      h.GetProlongationAtLevel(l)->Mult(xc, yf); D.vec("P_xc" + t, yf);
+      h.GetProlongationAtLevel(l)->MultTranspose(xf, yc); D.vec("Pt_xf" + t, yc);
+      mg.ConstrainedP(l)->Mult(xc, yf); D.vec("Pc_xc" + t, yf);
+      mg.ConstrainedP(l)->MultTranspose(xf, yc); D.vec("Pct_xf" + t, yc);
+   }
+   // one V-cycle and the preconditioned solve on the finest level
+   FiniteElementSpace &ff = h.GetFinestFESpace();
+   const int n = ff.GetNDofs();
+   Vector x(n); x.Randomize(1);
+   {
+      const Array<int> &ess = mg.Ess(NL - 1);
+      for (int i = 0; i < ess.Size(); i++) { x[ess[i]] = 0.0; }   // a residual of the constrained system vanishes there
+   }
+   D.vec("x", x);
+   Vector y(n); y = 0.0;
+   mg.Mult(x, y); D.vec("vcycle_x", y);
+   {
+      GridFunction xg(&ff); xg = 0.0;
+      LinearForm b(&ff); ConstantCoefficient one(1.0);
+      b.AddDomainIntegrator(new DomainLFIntegrator(one)); b.Assemble();
+      OperatorPtr A; Vector X, B;
+      // (GeometricMultigrid::FormFineLinearSystem dereferences essentialTrueDofs.Last(), which does not exist without
+      //  essential boundaries: go through the form directly - the same call with the same list)
+      Array<int> ess_fine(mg.Ess(NL - 1));
+      mg.Form(NL - 1)->FormLinearSystem(ess_fine, xg, b, A, X, B);
+      D.vec("B_rhs", B);
+      for (int pass = 0; pass < 2; pass++)
+      {
+         CGSolver cg; NormRecorder rec;
+         cg.SetRelTol(pass == 0 ? 0.0 : 1e-8); cg.SetAbsTol(0.0); cg.SetMaxIter(pass == 0 ? 3 : 500); cg.SetPrintLevel(-1);
+         cg.SetOperator(*A); cg.SetPreconditioner(mg); cg.SetMonitor(rec);
+         Vector Xk(X); Xk = 0.0;
+         cg.Mult(B, Xk);
+         if (pass == 0) { D.vec("X_mgpcg3", Xk); D.f64("mgpcg3_norms", rec.norms.data(), rec.norms.size()); }
+         else { D.vec("X_mgpcg_tol", Xk); D.iscalar("mgpcg_tol_iters", cg.GetNumIterations()); D.iscalar("mgpcg_tol_converged", cg.GetConverged()); }
+      }
+      // Jacobi-PCG iteration count on the same system, for the record
+      OperatorJacobiSmoother M(*mg.Form(NL - 1), mg.Ess(NL - 1));
+      CGSolver cg; cg.SetRelTol(1e-8); cg.SetAbsTol(0.0); cg.SetMaxIter(5000); cg.SetPrintLevel(-1);
+      cg.SetOperator(*A); cg.SetPreconditioner(M);
+      Vector Xj(X); Xj = 0.0; cg.Mult(B, Xj);
+      D.iscalar("jacobi_pcg_tol_iters", cg.GetNumIterations());
+   }
+   cout << "dump_mg ok: levels=" << NL << " NE=" << NE << " fine ndofs=" << n << setprecision(17) << " |M x|=" << y.Norml2() << endl;
+   for (auto f : fecs) { (void)f; }
+   return 0;
+}
+
 // ------------------------------------------------------------------ load_check
 // The reference loading the product's wire formats: Mesh(file) + GridFunction(mesh, file); dumps what it sees so that
 // tests/test_wire_formats.py can compare with the builder (numbering, boundary attributes, values, an L2 norm).
@@ -813,6 +982,7 @@ int main(int argc, char **argv)
    if (cmd == "time_apply") { return time_apply(argc, argv); }
    if (cmd == "load_check") { return load_check(argc, argv); }
    if (cmd == "dump_markers") { return dump_markers(argc, argv); }
+   if (cmd == "dump_mg") { return dump_mg(argc, argv); }
    if (cmd == "ex1") { return ex1(argc, argv); }
    if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }
    cerr << "usage: ref_driver dump_case|dump_bioheat|time_bioheat|time_apply|ex1|--check-inline ...\n";

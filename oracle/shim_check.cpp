@@ -463,6 +463,90 @@ static int rf_case(int p, int nx, int nsteps, bool factorised)
    return ok ? 0 : 1;
 }
 
+// (f)4 of SURVEY.md 8: p-multigrid.  The reference: GeometricMultigrid over an order-refined hierarchy with the smoothers and
+// coarse solver of examples/ex26.cpp (for diffusion + mass), as the preconditioner of CGSolver; against b200::PMultigrid + PCGSolver.
+struct RefMG : public GeometricMultigrid
+{
+   RefMG(FiniteElementSpaceHierarchy &h, Array<int> &ess_bdr, Coefficient &kc, Coefficient &mc) : GeometricMultigrid(h, ess_bdr)
+   {
+      for (int l = 0; l < h.GetNumLevels(); ++l)
+      {
+         FiniteElementSpace &fes = h.GetFESpaceAtLevel(l);
+         BilinearForm *form = new BilinearForm(&fes);
+         form->SetAssemblyLevel(AssemblyLevel::PARTIAL);
+         form->AddDomainIntegrator(new mfem::DiffusionIntegrator(kc));
+         form->AddDomainIntegrator(new mfem::MassIntegrator(mc));
+         form->Assemble();
+         bfs.Append(form);
+         OperatorPtr opr; opr.SetType(Operator::ANY_TYPE);
+         bfs[l]->FormSystemMatrix(*essentialTrueDofs[l], opr);
+         opr.SetOperatorOwner(false);
+         if (l == 0)
+         {
+            CGSolver *pcg = new CGSolver();
+            pcg->SetPrintLevel(-1); pcg->SetMaxIter(200); pcg->SetRelTol(sqrt(1e-4)); pcg->SetAbsTol(0.0);
+            pcg->SetOperator(*opr.Ptr());
+            AddLevel(opr.Ptr(), pcg, true, true);
+         }
+         else
+         {
+            Vector diag(fes.GetTrueVSize());
+            bfs[l]->AssembleDiagonal(diag);
+            AddLevel(opr.Ptr(), new OperatorChebyshevSmoother(*opr, diag, *essentialTrueDofs[l], 2), true, true);
+         }
+      }
+   }
+};
+
+static int mg_case(int nx, int pmax)
+{
+   Mesh *mesh = new Mesh(Mesh::MakeCartesian3D(nx, nx, nx + 1, Element::HEXAHEDRON, 1.0, 0.8, 0.6));
+   for (int i = 0; i < mesh->GetNV(); ++i) { real_t *v = mesh->GetVertex(i); v[1] += 0.2 * v[0]; v[2] += 0.3 * v[0]; }
+   vector<FiniteElementCollection *> fecs;
+   fecs.push_back(new H1_FECollection(1, 3));
+   FiniteElementSpaceHierarchy h(mesh, new FiniteElementSpace(mesh, fecs[0]), true, true);
+   for (int p = 2; p <= pmax; p *= 2) { fecs.push_back(new H1_FECollection(p, 3)); h.AddOrderRefinedLevel(fecs.back()); }
+   FunctionCoefficient kc(kfun), mc(mfun);
+   Array<int> ess_bdr(mesh->bdr_attributes.Max()); ess_bdr = 0; ess_bdr[0] = 1; ess_bdr[5] = 1;
+   FiniteElementSpace &ff = h.GetFinestFESpace();
+   const int n = ff.GetNDofs();
+   RefMG M0(h, ess_bdr, kc, mc);
+   M0.SetCycleType(Multigrid::CycleType::VCYCLE, 1, 1);
+   b200::PMultigrid M2(h, &kc, &mc, ess_bdr);
+   Array<int> ess; ff.GetEssentialTrueDofs(ess_bdr, ess);
+   // one cycle
+   Vector x(n); x.Randomize(1);
+   for (int i = 0; i < ess.Size(); i++) { x[ess[i]] = 0.0; }
+   Vector y0(n), y2(n); y0 = 0.0;
+   M0.Mult(x, y0); M2.Mult(x, y2);
+   const double e_cycle = rel(y2, y0);
+   // preconditioned solve
+   GridFunction xg(&ff); xg = 0.0;
+   LinearForm b(&ff); ConstantCoefficient one(1.0);
+   b.AddDomainIntegrator(new DomainLFIntegrator(one)); b.Assemble();
+   Vector b_copy(b);
+   OperatorHandle A0; Vector X0, B0;
+   M0.FormFineLinearSystem(xg, b, A0, X0, B0);
+   Vector B2(b_copy); M2.FineOperator().EliminateRHS(xg, B2);
+   CGSolver cg0; cg0.SetRelTol(1e-8); cg0.SetAbsTol(0.0); cg0.SetMaxIter(500); cg0.SetPrintLevel(-1);
+   cg0.SetOperator(*A0); cg0.SetPreconditioner(M0);
+   Vector Xa(n); Xa = 0.0; cg0.Mult(B0, Xa);
+   b200::PCGSolver cg2; cg2.SetRelTol(1e-8); cg2.SetAbsTol(0.0); cg2.SetMaxIter(500); cg2.SetPrintLevel(-1);
+   cg2.SetPreconditioner(M2); cg2.SetOperator(M2.FineOperator());
+   Vector Xb(n); Xb = 0.0; cg2.Mult(B2, Xb);
+   // Jacobi-PCG on the same system for the iteration-count comparison
+   b200::JacobiSmoother J2; b200::PCGSolver cgj; cgj.SetRelTol(1e-8); cgj.SetAbsTol(0.0); cgj.SetMaxIter(5000); cgj.SetPrintLevel(-1);
+   cgj.SetPreconditioner(J2); cgj.SetOperator(M2.FineOperator());
+   Vector Xj(n); Xj = 0.0; cgj.Mult(B2, Xj);
+   const double e_sol = rel(Xb, Xa);
+   const bool ok = e_cycle <= 1e-8 && abs(cg0.GetNumIterations() - cg2.GetNumIterations()) <= 1 && cg2.GetConverged() && e_sol <= 1e-6 &&
+                   cg2.GetNumIterations() < cgj.GetNumIterations();
+   cout << "{\"kind\":\"shim_mg\",\"levels\":" << h.GetNumLevels() << ",\"ndofs\":" << n << ",\"vcycle\":" << e_cycle << ",\"iters_ref\":" << cg0.GetNumIterations()
+        << ",\"iters_gpu\":" << cg2.GetNumIterations() << ",\"iters_gpu_jacobi\":" << cgj.GetNumIterations() << ",\"solution\":" << e_sol
+        << ",\"ok\":" << (ok ? "true" : "false") << "}" << endl;
+   return ok ? 0 : 1;
+}
+
 static void on_segv(int sig)
 {
    void *bt[64];
@@ -482,6 +566,7 @@ int main(int argc, char **argv)
    if (cmd == "apply" && argc >= 6) { return apply_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true) | apply_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), false); }
    if (cmd == "ex1") { return ex1_case(argc > 2 ? atoi(argv[2]) : 3, argc > 3 ? atoi(argv[3]) : 3); }
    if (cmd == "bioheat" && argc >= 5) { return bioheat_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), false) | bioheat_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true); }
+   if (cmd == "mg" && argc >= 4) { return mg_case(atoi(argv[2]), atoi(argv[3])); }
    if (cmd == "surface" && argc >= 4) { return surface_case(atoi(argv[2]), atoi(argv[3])); }
    if (cmd == "rf" && argc >= 5) { return rf_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), false) | rf_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true); }
    cerr << "usage: shim_check apply p nx ny nz | ex1 [order refinements] | bioheat p nx steps | surface p nx | rf p nx steps\n";

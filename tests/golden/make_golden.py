@@ -14,6 +14,7 @@ Fixtures (all float64 / int32, reference layouts):
   bioheat_p2_n4.npz   the RF + bioheat coupled step of SURVEY §3.2/3.3 on a 4^3 mesh
   bioheat_steps_p2_n4.npz   three consecutive coupled steps (T^{n+1} feeds k(T), sigma(T) of the next one)
   markers_<tag>.npz   element-attribute markers: y = A x and the diagonal for four marker combinations (`dump_markers`)
+  mg_<tag>.npz        p-multigrid: per-level tables and q-data, transfer matrices and P x / P^T x, one V-cycle, MG-PCG (`dump_mg`)
 """
 import os
 import subprocess
@@ -71,6 +72,15 @@ def markers():
         print("markers", tag, sum(v.nbytes for v in d.values()) // 1024, "KiB raw")
 
 
+def multigrid():
+    """p-multigrid (examples/ex26.cpp hierarchy, diffusion + mass): mg_<tag>.npz"""
+    for tag, c in {"skew222_z_p124": ("skew", 2, 2, 2, "zfaces", 1, 2, 4), "cart322_none_p123": ("cart", 3, 2, 2, "none", 1, 2, 3),
+                   "skew322_all_p13": ("skew", 3, 2, 2, "all", 1, 3)}.items():
+        d = run(["dump_mg"] + list(c))
+        np.savez_compressed(os.path.join(HERE, f"mg_{tag}.npz"), **d)
+        print("mg", tag, sum(v.nbytes for v in d.values()) // 1024, "KiB raw")
+
+
 def main():
     if not os.path.exists(DRIVER):
         sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle ref` in the build container")
@@ -95,11 +105,14 @@ def main():
     d = run(["dump_bioheat_steps", 2, 4, 12, 3])
     np.savez_compressed(os.path.join(HERE, "bioheat_steps_p2_n4.npz"), **d)
     markers()
+    multigrid()
     print("done")
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "markers":   # only the fixtures added in round 2
         markers()
+    elif len(sys.argv) > 1 and sys.argv[1] == "multigrid":
+        multigrid()
     else:
         main()

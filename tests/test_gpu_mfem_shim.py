@@ -84,3 +84,12 @@ def test_rf_coupled_operator_through_mfem_ode_solver(p, n):
     for r in recs:
         assert r["ok"] and r["T_rel_diff_fixed_iters"] <= 1e-9 and r["phi_rel_diff"] <= 1e-8
         assert abs(r["iters_T_ref"] - r["iters_T_gpu"]) <= 2 and abs(r["iters_phi_ref"] - r["iters_phi_gpu"]) <= 2
+
+
+@pytest.mark.parametrize("n,pmax", [(3, 2), (2, 4)])
+def test_p_multigrid_through_mfem(n, pmax):
+    """SURVEY 8(f)4: b200::PMultigrid (order-refined hierarchy, Chebyshev smoothers, CG coarse solve, V-cycle on the GPU) as
+    the preconditioner of b200::PCGSolver against mfem::GeometricMultigrid + CGSolver composed as examples/ex26.cpp"""
+    r = run(["mg", n, pmax])[0]
+    assert r["ok"] and r["vcycle"] <= 1e-8 and abs(r["iters_ref"] - r["iters_gpu"]) <= 1
+    assert r["iters_gpu"] < r["iters_gpu_jacobi"]
