@@ -1181,6 +1181,8 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
       // peer-memory path: non-shared dofs are finished by the segmented reduction (constraint + their part of the
       // dot -> *dot_out); the exchange kernel finishes the shared ones (their part of the dot -> dot_out[1])
       const unsigned char *shm = comm_shared_mask(f->comm);
+      // the shared dofs' partial sums leave first; the full reduction then overlaps their flight (and absorbs rank skew)
+      if (comm_px_send_from_slots(f->comm, off, yS, done)) { return 1; }
       if (constrained && dot_out)
       {
          k_segment_sum_mg<true, true><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, ctx->d_partials, ctx->d_ticket, dot_out, done);
@@ -1198,8 +1200,8 @@ static int form_apply(b200pa_form f, const double *x, double *y, bool constraine
          k_segment_sum_mg<false, false><<<grid, 256, 0, ctx->stream>>>(sp->ndofs, off, yS, y, em, x, shm, nullptr, nullptr, nullptr, done);
       }
       B200PA_LAUNCHED();
-      return comm_exchange_sum_apply(f->comm, y, done, (constrained || dot_out) ? x : nullptr, constrained ? em : nullptr,
-                                     dot_out ? dot_out + 1 : nullptr);
+      return comm_px_recv_apply(f->comm, y, done, (constrained || dot_out) ? x : nullptr, constrained ? em : nullptr,
+                                dot_out ? dot_out + 1 : nullptr);
    }
    if (f->comm)
    {

@@ -191,6 +191,41 @@ __global__ void k_px_send(int n, const int *__restrict__ ldof, const unsigned ch
    }
 }
 
+// The same send straight from the slot-order scratch of the operator apply: the local partial sum of a shared dof is its
+// segment of y_S, summed here (ascending element order, as the segmented reduction does for everybody a moment later) and
+// stored into the neighbours' mailboxes BEFORE the full E->L reduction runs - the messages fly while that kernel streams
+// the whole scratch, and a neighbour that is a little ahead or behind finds the data (or its slack) already there.
+__global__ void k_px_sumsend(int n, const int *__restrict__ ldof, const unsigned char *__restrict__ nbr_of, const int *__restrict__ offsets,
+                             const double *__restrict__ yS, const __grid_constant__ PxPeers P, unsigned long long epoch,
+                             unsigned int *ticket, const int *done)
+{
+   if (done && *done) { return; }
+   const int par = (int)(epoch & 1ull);
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      const int l = ldof[i];
+      double v = 0.0;
+      const int j1 = offsets[l + 1];
+      for (int j = offsets[l]; j < j1; ++j) { v += yS[j]; }
+      const int k = nbr_of[i];
+      P.recv[k][par * P.parity_stride[k] + (i - P.off[k])] = v;
+   }
+   __threadfence_system();
+   __shared__ bool last;
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+      last = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (last)
+   {
+      __threadfence_system();
+      if (threadIdx.x < P.n_nbr) { st_release_sys(P.flag[threadIdx.x], epoch); }
+   }
+}
+
 // wait for every neighbour's data of this epoch, then the ascending-rank sum (as k_unpack)
 // Optional epilogue for the operator apply (x != null): ConstrainedOperator fix-up of the shared dofs and their
 // owned part of the dot x.y, reduced deterministically into *dot_out.
@@ -517,6 +552,36 @@ int comm_exchange_sum_apply(b200pa_comm c, double *y, const int *done, const dou
    return exchange(c, y, 0, done, ep);
 }
 int comm_exchange_owner(b200pa_comm c, double *x) { return exchange(c, x, 1, nullptr); }
+
+// peer path, operator apply: first half (before the full segmented reduction) ...
+int comm_px_send_from_slots(b200pa_comm c, const int *offsets, const double *yS, const int *done)
+{
+   b200pa_ctx ctx = c->ctx;
+   if (c->n_send == 0) { return 0; }
+   const int bs = 256;
+   const int g = std::min((c->n_send + bs - 1) / bs, ctx->num_sms * 8);
+   const unsigned long long epoch = ++c->epoch_x;
+   k_px_sumsend<<<g, bs, 0, ctx->stream>>>(c->n_send, c->send_ldof.as<int>(), c->send_nbr.as<unsigned char>(), offsets, yS, c->peers, epoch,
+                                           c->px_ticket.as<unsigned int>(), done);
+   B200PA_LAUNCHED();
+   return 0;
+}
+// ... and second half: wait for the neighbours' data of the epoch the send opened, finish the shared dofs of y
+int comm_px_recv_apply(b200pa_comm c, double *y, const int *done, const double *x, const unsigned char *ess_mask, double *dot_out)
+{
+   b200pa_ctx ctx = c->ctx;
+   if (c->n_send == 0) { return 0; }
+   const int bs = 256;
+   const unsigned long long epoch = c->epoch_x;
+   const char *mb = (const char *)c->mailbox;
+   const int g2 = std::max(1, std::min((c->n_shared + bs - 1) / bs, ctx->num_sms * 8));
+   const double *recv = (const double *)(mb + c->mb_recv) + (size_t)(epoch & 1ull) * (size_t)c->n_send;
+   k_px_recv<<<g2, bs, 0, ctx->stream>>>(c->n_shared, c->sh_ldof.as<int>(), c->sh_off.as<int>(), c->sh_src.as<int>(), recv, y, 0,
+                                         (const unsigned long long *)(mb + c->mb_flags_x), c->peers, epoch, c->px_err.as<int>(), done,
+                                         x, ess_mask, c->owner_mask.as<unsigned char>(), ctx->d_partials, ctx->d_ticket, dot_out);
+   B200PA_LAUNCHED();
+   return 0;
+}
 const int *comm_px_err_ptr(b200pa_comm c) { return (c && c->px) ? c->px_err.as<int>() : nullptr; }
 int comm_px_check(b200pa_comm c, const char *where)
 {

@@ -18,6 +18,10 @@ bool comm_px(b200pa_comm c);
 const unsigned char *comm_shared_mask(b200pa_comm c);
 int comm_exchange_sum_apply(b200pa_comm c, double *yL_dev, const int *done, const double *x_dev, const unsigned char *ess_mask,
                             double *dot_out);
+// peer path, operator apply in two halves around the segmented reduction: the partial sums of the shared dofs leave for the
+// neighbours straight from the slot-order scratch, the receive + finish runs after the reduction (comm.cu)
+int comm_px_send_from_slots(b200pa_comm c, const int *offsets_dev, const double *yS_dev, const int *done);
+int comm_px_recv_apply(b200pa_comm c, double *yL_dev, const int *done, const double *x_dev, const unsigned char *ess_mask, double *dot_out);
 // peer-memory path: device error word raised by a timed-out wait (nullptr when the path is off) and the check the
 // host-synchronous entry points run after their final stream synchronisation (nonzero + message when it was raised)
 const int *comm_px_err_ptr(b200pa_comm c);
