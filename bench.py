@@ -591,8 +591,9 @@ def main():
     ynorm2 = P.global_sqnorm(y)
 
     # ---- e2e: the same apply through the host-buffer C-ABI entry point (pinned host x, y)
-    xp = torch.from_numpy(P.xh).pin_memory()
-    yp = torch.empty(nd, dtype=torch.float64).pin_memory()
+    xp = ctx.pinned(nd, fill=P.xh)          # page-locked, on the NUMA node this rank's GPU hangs off
+    yp = ctx.pinned(nd)
+    host_node = ctx.host_node(xp)
     for _ in range(3):
         form.mult_host(xp, yp)
     Ke = max(3, min(K, 20))
@@ -613,7 +614,9 @@ def main():
                                                              if comm.p2p_enabled() else "NCCL send/recv + all-reduce")),
         "e2e": {"value": global_dofs * Ke / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * nd,
                 "d2h_bytes_per_step": 8 * nd, "ms_per_step": ms_e2e / Ke,
-                "api": "b200pa_form_mult_host (pinned host x -> H2D -> apply -> D2H -> pinned host y)"},
+                "api": "b200pa_form_mult_host (pinned host x -> H2D -> apply -> D2H -> pinned host y)",
+                "host_buffers": "b200pa_host_alloc: page-locked, " + (f"first-touched on NUMA node {host_node} of this rank's GPU" if host_node >= 0
+                                                                       else "placement left to the kernel (no NUMA information for the GPU)")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
@@ -630,14 +633,14 @@ def main():
     # ---- e2e of what an application calls: one PCG solve through the host-buffer entry point (b, x cross PCIe once per solve)
     if legs:
         rhs0 = P.rhs(form)
-        bp = rhs0.cpu().pin_memory()
-        xs = torch.empty(nd, dtype=torch.float64).pin_memory()
+        bp = ctx.pinned(nd, fill=rhs0.cpu().numpy())
+        xs = ctx.pinned(nd)
         dinv0 = form.jacobi()
         its = 20
 
-        xs.zero_()
+        xs[:] = 0.0
         form.pcg(dinv0, bp, xs, 0.0, 0.0, its, want_norms=False, host=True)
-        xs.zero_()
+        xs[:] = 0.0
         ms_sh = env.timed(lambda: form.pcg(dinv0, bp, xs, 0.0, 0.0, its, want_norms=False, host=True), 1)
         line["e2e_pcg"] = {"value": global_dofs * its / (ms_sh * 1e-3) / 1e9, "unit": "GDOF/s (dofs x PCG iterations / s)", "iters": its,
                            "ms_per_solve": ms_sh, "h2d_bytes_per_solve": 16 * nd, "d2h_bytes_per_solve": 8 * nd,

@@ -31,7 +31,7 @@ class PcgResult(C.Structure):
 # every symbol include/b200pa.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = """
 b200pa_version b200pa_last_error b200pa_launch_count
-b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset b200pa_copy
+b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset b200pa_copy b200pa_host_alloc b200pa_host_free b200pa_host_node
 b200pa_restrict_mult b200pa_restrict_mult_transpose b200pa_diffusion_setup b200pa_mass_setup
 b200pa_diffusion_apply b200pa_mass_apply b200pa_diffusion_diag b200pa_mass_diag b200pa_qvalues
 b200pa_qphysgrad b200pa_domain_lf b200pa_dot b200pa_add b200pa_jacobi_setup b200pa_jacobi_mult
@@ -245,6 +245,23 @@ class Context:
         import torch
         with torch.cuda.stream(self.torch_stream):
             return torch.zeros(int(n), dtype=dtype or torch.float64, device=self.device)
+
+    def pinned(self, n, fill=None):
+        """float64 numpy vector in page-locked host memory on the GPU's NUMA node (b200pa_host_alloc) for the *_host entry
+        points; freed when the array (and every view of it) is gone.  `.numa_node` of the owner: -1 = kernel default"""
+        import weakref
+        p = vp()
+        check(lib().b200pa_host_alloc(self.h, C.c_size_t(8 * int(n)), C.byref(p)))
+        buf = (C.c_double * int(n)).from_address(p.value)
+        a = np.ctypeslib.as_array(buf)
+        h, addr = self.h, p.value
+        weakref.finalize(buf, lambda: lib().b200pa_host_free(h, vp(addr)))
+        if fill is not None:
+            a[:] = fill
+        return a
+
+    def host_node(self, a):
+        return int(lib().b200pa_host_node(_ptr(a)))
 
     def to_host(self, t):
         self.sync()

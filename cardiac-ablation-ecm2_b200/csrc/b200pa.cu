@@ -7,6 +7,13 @@
 #include <cmath>
 #include <cstdlib>
 #include <utility>
+#include <mutex>
+#include <vector>
+#include <string>
+#include <cctype>
+#include <cstdio>
+#include <sched.h>
+#include <sys/mman.h>
 
 #include "common.cuh"
 #include "elem_launch.cuh"
@@ -271,6 +278,7 @@ extern "C" int b200pa_ctx_create(int device, void *stream, b200pa_ctx *out)
    B200PA_CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
    B200PA_CK(cudaMalloc(&c->d_result, sizeof(double) * 8));
    B200PA_CK(cudaMallocHost(&c->h_result, sizeof(double) * 8));
+   for (cudaEvent_t &e : c->ev_poll) { B200PA_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
    B200PA_CK(cudaDeviceSynchronize());
    *out = c;
    return 0;
@@ -282,6 +290,7 @@ extern "C" int b200pa_ctx_destroy(b200pa_ctx c)
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFreeHost(c->h_result);
+   for (cudaEvent_t e : c->ev_poll) { if (e) { cudaEventDestroy(e); } }
    if (c->own_stream) { cudaStreamDestroy(c->stream); }
    delete c;
    return 0;
@@ -300,6 +309,104 @@ extern "C" int b200pa_malloc(b200pa_ctx c, size_t bytes, void **out)
    B200PA_CK(cudaSetDevice(c->device));
    B200PA_CK(cudaMalloc(out, bytes ? bytes : 8));
    return 0;
+}
+// ---- page-locked host memory on the NUMA node the GPU hangs off (≙ MemoryType::HOST_PINNED, general/mem_manager.cpp:
+// cudaMallocHost; the reference leaves placement to the first-touch policy of whichever core the rank happens to run on).
+// With one rank per GPU, vectors that cross PCIe on every call should not also cross the socket interconnect: the pages are
+// first-touched by this thread while it is pinned to the cores of the GPU's node, then registered with the driver.
+static int gpu_numa_node(int device)
+{
+   char bus[32] = {0};
+   if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+   for (char *c = bus; *c; c++) { *c = (char)tolower(*c); }
+   char path[128];
+   snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+   FILE *f = fopen(path, "r");
+   if (!f) { return -1; }
+   int node = -1;
+   if (fscanf(f, "%d", &node) != 1) { node = -1; }
+   fclose(f);
+   return node;
+}
+static bool numa_node_cpus(int node, cpu_set_t *set)
+{
+   char path[96];
+   snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+   FILE *f = fopen(path, "r");
+   if (!f) { return false; }
+   CPU_ZERO(set);
+   int a, b, n = 0;
+   while (fscanf(f, "%d", &a) == 1)
+   {
+      b = a;
+      int ch = fgetc(f);
+      if (ch == '-') { if (fscanf(f, "%d", &b) != 1) { break; } ch = fgetc(f); }
+      for (int i = a; i <= b && i < CPU_SETSIZE; i++) { CPU_SET(i, set); n++; }
+      if (ch != ',') { break; }
+   }
+   fclose(f);
+   return n > 0;
+}
+struct HostBlock { void *p; size_t bytes; int node; };
+static std::mutex g_host_mu;
+static std::vector<HostBlock> g_host_blocks;
+
+extern "C" int b200pa_host_alloc(b200pa_ctx c, size_t bytes, void **out)
+{
+   B200PA_REQUIRE(c && out, "host_alloc: NULL argument");
+   B200PA_CK(cudaSetDevice(c->device));
+   const size_t len = ((bytes ? bytes : 8) + 4095) & ~(size_t)4095;
+   void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+   B200PA_REQUIRE(p != MAP_FAILED, "host_alloc: mmap failed");
+   const int node = gpu_numa_node(c->device);
+   cpu_set_t old, near;
+   bool moved = false;
+   if (node >= 0 && numa_node_cpus(node, &near) && sched_getaffinity(0, sizeof(old), &old) == 0)
+   {
+      cpu_set_t both;                              // stay inside whatever cpuset the rank was given
+      CPU_AND(&both, &old, &near);
+      moved = CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0;
+   }
+   for (size_t o = 0; o < len; o += 4096) { ((volatile char *)p)[o] = 0; }   // first touch: pages land on this core's node
+   if (moved) { sched_setaffinity(0, sizeof(old), &old); }
+   cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+   if (e != cudaSuccess)
+   {
+      munmap(p, len);
+      return fail(std::string("host_alloc: cudaHostRegister: ") + cudaGetErrorString(e));
+   }
+   {
+      std::lock_guard<std::mutex> g(g_host_mu);
+      g_host_blocks.push_back({p, len, moved ? node : -1});
+   }
+   *out = p;
+   return 0;
+}
+extern "C" int b200pa_host_free(b200pa_ctx c, void *p)
+{
+   if (!p) { return 0; }
+   B200PA_REQUIRE(c, "host_free: ctx is NULL");
+   HostBlock blk{nullptr, 0, -1};
+   {
+      std::lock_guard<std::mutex> g(g_host_mu);
+      for (size_t i = 0; i < g_host_blocks.size(); i++)
+      {
+         if (g_host_blocks[i].p == p) { blk = g_host_blocks[i]; g_host_blocks.erase(g_host_blocks.begin() + i); break; }
+      }
+   }
+   B200PA_REQUIRE(blk.p, "host_free: pointer was not returned by b200pa_host_alloc");
+   B200PA_CK(cudaSetDevice(c->device));
+   B200PA_CK(cudaStreamSynchronize(c->stream));
+   B200PA_CK(cudaHostUnregister(p));
+   munmap(p, blk.bytes);
+   return 0;
+}
+/* NUMA node the block was placed on, -1 if the placement was left to the kernel's default policy */
+extern "C" int b200pa_host_node(const void *p)
+{
+   std::lock_guard<std::mutex> g(g_host_mu);
+   for (const HostBlock &b : g_host_blocks) { if (b.p == p) { return b.node; } }
+   return -1;
 }
 extern "C" int b200pa_free(b200pa_ctx c, void *p)
 {
@@ -1558,6 +1665,40 @@ extern "C" int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, dou
 }
 
 // -------------------------------------------------------------------------- PCG
+// The PCG loops keep their scalars on the device; the host only needs to learn that the solve has ended.  Reading the
+// flag back with a stream synchronisation drains the queue and costs ~0.4 ms of idle GPU per poll (measured at 8 M dofs:
+// iteration 9 of a poll-every-8 loop took 1.24 ms instead of 0.86).  So the read-back of block k is only WAITED for after
+// block k+1 has been enqueued: the GPU never runs dry, and a finished solve costs at most two blocks of kernels that
+// return at once on the flag.
+struct DonePoller
+{
+   b200pa_ctx ctx;
+   const int *d_done, *d_err;   // device flags: terminal state reached | peer-memory wait timed out (may be NULL)
+   int posted = 0, pending = -1;
+   int *slot(int i) const { return (int *)(ctx->h_result + 4) + 2 * i; }
+   DonePoller(b200pa_ctx c, const int *done, const int *err) : ctx(c), d_done(done), d_err(err)
+   {
+      for (int i = 0; i < 2; i++) { slot(i)[0] = slot(i)[1] = 0; }
+   }
+   // enqueue a read-back; returns 1 when an EARLIER read-back says the loop can stop, 0 to go on, -1 on a CUDA error
+   int post()
+   {
+      const int k = posted++ & 1;
+      cudaStream_t s = ctx->stream;
+      if (cudaMemcpyAsync(slot(k), d_done, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) { return -1; }
+      if (d_err && cudaMemcpyAsync(slot(k) + 1, d_err, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) { return -1; }
+      if (cudaEventRecord(ctx->ev_poll[k], s) != cudaSuccess) { return -1; }
+      int stop = 0;
+      if (pending >= 0)
+      {
+         if (cudaEventSynchronize(ctx->ev_poll[pending]) != cudaSuccess) { return -1; }
+         stop = slot(pending)[0] || slot(pending)[1];
+      }
+      pending = k;
+      return stop;
+   }
+};
+
 extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const double *b_dev, double *x_dev, double rel_tol,
                                 double abs_tol, int max_iter, b200pa_pcg_result *res, double *norms_host)
 {
@@ -1618,10 +1759,8 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
 
    // the loop (:952-1027).  Scalars stay on the device; the host only polls `done` every few
    // iterations (kernels after convergence return immediately on the flag).
-   int *h_done = (int *)(ctx->h_result + 4); // [0] done, [1] peer-memory time-out word
-   h_done[0] = h_done[1] = 0;
-   const int *px_err = f->comm ? comm_px_err_ptr(f->comm) : nullptr;
-   const int poll = 8;
+   DonePoller poller(ctx, &st->done, f->comm ? comm_px_err_ptr(f->comm) : nullptr);
+   const int poll = 4;
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
       k_pcg_update<<<grid, 256, 0, s>>>(n, x_dev, r, z, d, dinv_dev, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
@@ -1633,10 +1772,9 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
       if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
       if (it % poll == 0)
       {
-         B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
-         if (px_err) { B200PA_CK(cudaMemcpyAsync(h_done + 1, px_err, sizeof(int), cudaMemcpyDeviceToHost, s)); }
-         B200PA_CK(cudaStreamSynchronize(s));
-         if (*h_done || h_done[1]) { break; }
+         const int stop = poller.post();
+         B200PA_REQUIRE(stop >= 0, "pcg_solve: convergence-flag read-back failed");
+         if (stop) { break; }
       }
    }
    PcgState hs;
@@ -1835,10 +1973,8 @@ extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev,
    B200PA_CK(cudaMemcpyAsync(d, z, vb, cudaMemcpyDeviceToDevice, s));
    if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
    if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
-   int *h_done = (int *)(ctx->h_result + 4); // [0] done, [1] peer-memory time-out word
-   h_done[0] = h_done[1] = 0;
-   const int *px_err = f->comm ? comm_px_err_ptr(f->comm) : nullptr;
-   const int poll = 4;
+   DonePoller poller(ctx, &st->done, f->comm ? comm_px_err_ptr(f->comm) : nullptr);
+   const int poll = 2;
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
       if (n > 0) { k_pcg_update_plain<<<grid, 256, 0, s>>>(n, x_dev, r, q, d, st); B200PA_LAUNCHED(); }
@@ -1849,10 +1985,9 @@ extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev,
       if (!fused_scalars && reduce_step(&st->dot_b, 3)) { return 1; }
       if (it % poll == 0)
       {
-         B200PA_CK(cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
-         if (px_err) { B200PA_CK(cudaMemcpyAsync(h_done + 1, px_err, sizeof(int), cudaMemcpyDeviceToHost, s)); }
-         B200PA_CK(cudaStreamSynchronize(s));
-         if (*h_done || h_done[1]) { break; }
+         const int stop = poller.post();
+         B200PA_REQUIRE(stop >= 0, "pcg_solve: convergence-flag read-back failed");
+         if (stop) { break; }
       }
    }
    PcgState hs;

@@ -74,6 +74,7 @@ struct b200pa_ctx_s
    unsigned int *d_ticket = nullptr;
    double *d_result = nullptr;   // [8]
    double *h_result = nullptr;   // pinned [8]
+   cudaEvent_t ev_poll[2] = {nullptr, nullptr}; // PCG convergence-flag read-backs in flight (DonePoller)
 };
 
 namespace b200pa

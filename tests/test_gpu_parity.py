@@ -388,5 +388,19 @@ def test_mult_host_pipelined_equals_device_apply(ctx, p, n):
             yh = np.full(m["ndofs"], np.nan)     # pageable host memory works too (copies just do not overlap)
             f.mult_host(xh, yh, constrained=constrained)
             assert np.array_equal(yh, yd)
+            xn, yn = ctx.pinned(m["ndofs"], fill=xh), ctx.pinned(m["ndofs"], fill=np.nan)   # b200pa_host_alloc: NUMA-local, page-locked
+            f.mult_host(xn, yn, constrained=constrained)
+            assert np.array_equal(yn, yd) and ctx.host_node(xn) >= -1
+            del xn, yn
         f.close()
     sp.close()
+
+
+def test_host_alloc_rejects_foreign_pointers(ctx):
+    """b200pa_host_free only takes what b200pa_host_alloc returned; blocks are usable as ordinary host memory"""
+    a = ctx.pinned(1000, fill=3.0)
+    assert a.sum() == 3000.0 and a.ctypes.data % 4096 == 0
+    other = np.zeros(8)
+    assert b200pa.lib().b200pa_host_free(ctx.h, b200pa._ptr(other)) != 0
+    assert b"not returned by b200pa_host_alloc" in b200pa.lib().b200pa_last_error()
+    assert b200pa.lib().b200pa_host_node(b200pa._ptr(other)) == -1
