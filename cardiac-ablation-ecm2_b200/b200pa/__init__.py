@@ -31,7 +31,7 @@ class PcgResult(C.Structure):
 # every symbol include/b200pa.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = """
 b200pa_version b200pa_last_error b200pa_launch_count
-b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset b200pa_copy b200pa_host_alloc b200pa_host_free b200pa_host_node
+b200pa_ctx_create b200pa_ctx_destroy b200pa_ctx_sync b200pa_ctx_stream b200pa_ctx_upload b200pa_ctx_download b200pa_malloc b200pa_free b200pa_memset b200pa_copy b200pa_host_alloc b200pa_host_free b200pa_host_node b200pa_paraview_save
 b200pa_restrict_mult b200pa_restrict_mult_transpose b200pa_diffusion_setup b200pa_mass_setup
 b200pa_diffusion_apply b200pa_mass_apply b200pa_diffusion_diag b200pa_mass_diag b200pa_qvalues
 b200pa_qphysgrad b200pa_domain_lf b200pa_dot b200pa_add b200pa_jacobi_setup b200pa_jacobi_mult
@@ -164,6 +164,22 @@ def write_gridfunction(path, p, values):
     """GridFunction::Save of a scalar H1 order-p field in the builder's L-dof numbering"""
     v = _f64(values)
     check(lib().b200pa_write_gridfunction(str(path).encode(), int(p), C.c_longlong(v.size), _ptr(v)))
+
+
+def paraview_save(prefix_path, collection, mesh, p, fields, cycle=0, time=0.0, rank=0, nranks=1, levels_of_detail=None,
+                  high_order=True, fmt="binary", attributes=None, append=None):
+    """ParaViewDataCollection::Save for a mesh dict of hex_build / partition.build_part (gather_map, vertices,
+    elem_vertices) and {name: host values in L-dof numbering}; fmt: ascii | binary | binary32"""
+    names = sorted(fields)                     # the reference's field map iterates in name order
+    vals = [_f64(fields[n]) for n in names]
+    gm, vx, ev = _i32(mesh["gather_map"]), _f64(mesh["vertices"]), _i32(mesh["elem_vertices"])
+    at = None if attributes is None else _i32(attributes)
+    c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    c_vals = (vp * len(names))(*[v.ctypes.data for v in vals])
+    check(lib().b200pa_paraview_save(str(prefix_path).encode(), str(collection).encode(), int(cycle), C.c_double(time), int(rank), int(nranks),
+                                     int(p), C.c_longlong(mesh["ne"]), C.c_longlong(mesh["ndofs"]), _ptr(gm), _ptr(vx), _ptr(ev), _ptr(at),
+                                     len(names), c_names, c_vals, int(p if levels_of_detail is None else levels_of_detail), int(bool(high_order)),
+                                     {"ascii": 0, "binary": 1, "binary32": 2}[fmt], int(cycle > 0 if append is None else append)))
 
 
 def chebyshev_coeffs(order, max_eig):

@@ -376,6 +376,19 @@ int b200pa_comm_allreduce_sum(b200pa_comm c, double *vals_dev, int n);
  * its L-dof numbering (host values).  GLVis / the reference load both; the loaded space has the builder's numbering. */
 int b200pa_hex_write_mesh(const char *path, int nx, int ny, int nz, double sx, double sy, double sz, int skew);
 int b200pa_write_gridfunction(const char *path, int p, long long n, const double *values_host);
+/* ParaViewDataCollection::Save (fem/datacollection.hpp:584, fem/datacollection.cpp:887-1083; Mesh::PrintVTU,
+ * mesh/mesh.cpp:12683-12890) for a hexahedral mesh without nodal GridFunction and scalar H1 fields of order p given in
+ * the L-dof numbering of gather_map (host arrays): writes <prefix_path><collection>/Cycle%06d/proc%06d.vtu for this rank
+ * and, on rank 0, Cycle%06d/data.pvtu and <collection>.pvd.  Every element carries (levels_of_detail+1)^3 uniformly
+ * spaced points; high_order != 0: one VTK Lagrange hexahedron of order levels_of_detail per element (the reference's
+ * SetHighOrderOutput(true)), else levels_of_detail^3 linear hexahedra.  format: 0 ascii, 1 binary (base64 Float64),
+ * 2 binary32 (base64 Float32) - VTKFormat; zlib compression is not offered (compression level 0).
+ * attributes: int32[ne] or NULL (all 1).  append = 0 starts a new .pvd (the first Save of a collection), 1 adds this
+ * cycle to the existing one.  With several ranks every rank calls this with its own piece; only rank 0 needs nranks. */
+int b200pa_paraview_save(const char *prefix_path, const char *collection, int cycle, double time, int rank, int nranks,
+                         int p, long long ne, long long ndofs, const int *gather_map, const double *vertices,
+                         const int *elem_vertices, const int *attributes, int nfields, const char *const *names,
+                         const double *const *values_host, int levels_of_detail, int high_order, int format, int append);
 int b200pa_hex_sizes(int nx, int ny, int nz, int p, long long *ne, long long *nv, long long *ndofs);
 int b200pa_hex_build(int nx, int ny, int nz, int p, double sx, double sy, double sz, int skew,
                      int *gather_map, int *elem_vertices, double *vertices, int *elem_ijk,

@@ -972,6 +972,50 @@ static int load_check(int argc, char **argv)
    return 0;
 }
 
+// ------------------------------------------------------------------ paraview
+// ParaViewDataCollection::Save by the unmodified reference for a mesh + fields the product wrote in the reference's own
+// text formats (so both writers see the same numbering and values): `cycles` saves at cycle c, time 0.25 c, field c
+// scaled by (1 + c).   paraview OUTDIR NAME mesh_file format(ascii|binary|binary32) high_order lod cycles name=gf_file ...
+static int paraview(int argc, char **argv)
+{
+   if (argc < 10) { cerr << "paraview OUTDIR NAME mesh_file ascii|binary|binary32 high_order lod cycles name=gf_file ...\n"; return 2; }
+   Device device("cpu");
+   Mesh mesh(argv[4], 1, 1);
+   const string fmt = argv[5];
+   const bool high_order = atoi(argv[6]) != 0;
+   const int lod = atoi(argv[7]), cycles = atoi(argv[8]);
+   vector<unique_ptr<GridFunction>> gfs;
+   vector<string> names;
+   for (int i = 9; i < argc; i++)
+   {
+      const string a = argv[i];
+      const size_t eq = a.find('=');
+      MFEM_VERIFY(eq != string::npos, "name=gf_file expected");
+      ifstream gin(a.substr(eq + 1));
+      MFEM_VERIFY(gin.good(), "cannot open the GridFunction file");
+      gfs.emplace_back(new GridFunction(&mesh, gin));
+      names.push_back(a.substr(0, eq));
+   }
+   ParaViewDataCollection pv(argv[3], &mesh);
+   pv.SetPrefixPath(argv[2]);
+   pv.SetLevelsOfDetail(lod);
+   pv.SetHighOrderOutput(high_order);
+   pv.SetDataFormat(fmt == "ascii" ? VTKFormat::ASCII : fmt == "binary32" ? VTKFormat::BINARY32 : VTKFormat::BINARY);
+   pv.SetCompressionLevel(0);
+   for (size_t i = 0; i < gfs.size(); i++) { pv.RegisterField(names[i], gfs[i].get()); }
+   vector<Vector> base;
+   for (auto &g : gfs) { base.emplace_back(*g); }
+   for (int c = 0; c < cycles; c++)
+   {
+      for (size_t i = 0; i < gfs.size(); i++) { gfs[i]->Set(1.0 + c, base[i]); }
+      pv.SetCycle(c);
+      pv.SetTime(0.25 * c);
+      pv.Save();
+   }
+   cout << "paraview ok: NE=" << mesh.GetNE() << " fields=" << gfs.size() << endl;
+   return 0;
+}
+
 int main(int argc, char **argv)
 {
    const string cmd = argc > 1 ? argv[1] : "";
@@ -983,6 +1027,7 @@ int main(int argc, char **argv)
    if (cmd == "load_check") { return load_check(argc, argv); }
    if (cmd == "dump_markers") { return dump_markers(argc, argv); }
    if (cmd == "dump_mg") { return dump_mg(argc, argv); }
+   if (cmd == "paraview") { return paraview(argc, argv); }
    if (cmd == "ex1") { return ex1(argc, argv); }
    if (cmd == "--check-inline" && argc > 2) { return check_inline(argv[2]); }
    cerr << "usage: ref_driver dump_case|dump_bioheat|time_bioheat|time_apply|ex1|--check-inline ...\n";

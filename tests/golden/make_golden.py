@@ -15,6 +15,8 @@ Fixtures (all float64 / int32, reference layouts):
   bioheat_steps_p2_n4.npz   three consecutive coupled steps (T^{n+1} feeds k(T), sigma(T) of the next one)
   markers_<tag>.npz   element-attribute markers: y = A x and the diagonal for four marker combinations (`dump_markers`)
   mg_<tag>.npz        p-multigrid: per-level tables and q-data, transfer matrices and P x / P^T x, one V-cycle, MG-PCG (`dump_mg`)
+  paraview_<tag>.npz  every file ParaViewDataCollection::Save wrote (`paraview`) for a mesh + fields handed over in the
+                      reference's text formats, as byte arrays keyed by relative path ('/' -> '|')
 """
 import os
 import subprocess
@@ -81,6 +83,51 @@ def multigrid():
         print("mg", tag, sum(v.nbytes for v in d.values()) // 1024, "KiB raw")
 
 
+# tag: (p, dims, size, skew, format, high_order, levels_of_detail, cycles)
+PARAVIEW = {
+    "p2_skew322_ascii_ho": (2, (3, 2, 2), (1.0, 0.7, 0.4), True, "ascii", 1, 2, 2),
+    "p3_cart221_binary_ho": (3, (2, 2, 1), (1.0, 1.0, 0.5), False, "binary", 1, 3, 1),
+    "p2_cart222_binary32_lo": (2, (2, 2, 2), (1.0, 1.0, 1.0), False, "binary32", 0, 2, 2),
+    "p1_skew211_ascii_lo": (1, (2, 1, 1), (2.0, 1.0, 1.0), True, "ascii", 0, 1, 1),
+    "p2_skew212_binary_lod4": (2, (2, 1, 2), (1.0, 1.0, 1.0), True, "binary", 1, 4, 1),
+}
+
+
+def paraview_fields(m, p, dims):
+    """the nodal fields both writers are given: name -> values in the builder's L-dof numbering"""
+    sys.path.insert(0, os.path.join(ROOT, "cardiac-ablation-ecm2_b200"))
+    import b200pa
+    lat = m["lattice"].reshape(-1, 3)
+    xyz = (lat // p + b200pa.basis(p)["gll"][lat % p]) / np.asarray(dims, dtype=np.float64)
+    return {"T": 37.0 + 20.0 * np.exp(-4.0 * ((xyz - 0.5) ** 2).sum(1)),
+            "phi": 30.0 * (1.0 - xyz[:, 2]) + np.sin(3.0 * xyz[:, 0]) * xyz[:, 1]}
+
+
+def paraview():
+    sys.path.insert(0, os.path.join(ROOT, "cardiac-ablation-ecm2_b200"))
+    import b200pa
+    for tag, (p, dims, size, skew, fmt, ho, lod, cycles) in PARAVIEW.items():
+        m = b200pa.hex_build(*dims, p, *size, skew=skew)
+        fields = paraview_fields(m, p, dims)
+        with tempfile.TemporaryDirectory() as t:
+            mesh_file = os.path.join(t, "slab.mesh")
+            b200pa.write_mesh(mesh_file, *dims, *size, skew=skew)
+            args = []
+            for name, v in fields.items():
+                b200pa.write_gridfunction(os.path.join(t, name + ".gf"), p, v)
+                args.append(f"{name}={os.path.join(t, name + '.gf')}")
+            out = os.path.join(t, "out") + "/"
+            subprocess.run([DRIVER, "paraview", out, "ablation", mesh_file, fmt, str(ho), str(lod), str(cycles)] + args, check=True,
+                           stdout=subprocess.DEVNULL)
+            files = {}
+            for dp, _, fns in os.walk(out):
+                for fn in fns:
+                    full = os.path.join(dp, fn)
+                    files[os.path.relpath(full, out).replace("/", "|")] = np.frombuffer(open(full, "rb").read(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(HERE, f"paraview_{tag}.npz"), **files)
+        print("paraview", tag, sorted(files), sum(v.nbytes for v in files.values()) // 1024, "KiB raw")
+
+
 def main():
     if not os.path.exists(DRIVER):
         sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle ref` in the build container")
@@ -106,6 +153,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "bioheat_steps_p2_n4.npz"), **d)
     markers()
     multigrid()
+    paraview()
     print("done")
 
 
@@ -114,5 +162,7 @@ if __name__ == "__main__":
         markers()
     elif len(sys.argv) > 1 and sys.argv[1] == "multigrid":
         multigrid()
+    elif len(sys.argv) > 1 and sys.argv[1] == "paraview":
+        paraview()
     else:
         main()
