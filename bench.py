@@ -449,10 +449,22 @@ class Problem:
         return {"ms_per_iter": ms1 / its, "iters": its, "gdof_per_s": self.global_dofs * its / (ms1 * 1e-3) / 1e9,
                 "ms_per_iter_marginal": marginal, "gdof_per_s_marginal": self.global_dofs / (marginal * 1e-3) / 1e9}
 
-    def implicit_step(self, form, rhs, rel_tol, max_iter, collective=True):
-        """k(T) q-data + PA set-up + Jacobi diagonal + PCG: (ms, result).  rel_tol = 0: exactly max_iter iterations"""
+    def implicit_step(self, form, rhs, rel_tol, max_iter, collective=True, with_rhs=False):
+        """k(T) q-data + PA set-up + Jacobi diagonal + PCG: (ms, result).  rel_tol = 0: exactly max_iter iterations.
+        with_rhs: the right-hand side is assembled inside the timed region as well: the perfusion source
+        through the load-vector kernel, its shared-dof sums, and (rho c / dt) M T^n through the mass-only form"""
         env, sp = self.env, self.sp
         T1 = self.T0.clone()
+        fm = None
+        if with_rhs:
+            import numpy as np
+            fm = env.b.Form(sp)
+            fm.assemble_mass(np.array([PHYS["rc"] / PHYS["dt"]]))
+            fm.set_essential(None)
+            if getattr(form, "_comm", None) is not None:
+                fm.set_comm(form._comm)
+            src1 = env.ctx.to_dev(np.array([PHYS["wbcb"] * PHYS["Ta"]]))
+            lf, mt, rhs2 = env.ctx.empty(self.nd), env.ctx.empty(self.nd), env.ctx.empty(self.nd)
 
         def step():
             k2 = sp.coeff_linear(PHYS["k0"], PHYS["ak"], 37.0, self.T0, out=self.kq)
@@ -460,12 +472,21 @@ class Problem:
                 form.assemble_mass(self.mq)
             # diffusion q-data and the Jacobi diagonal in one pass over the q-points (two passes on non-affine meshes)
             d2 = form.jacobi_from(form.assemble_diffusion_with_diagonal(k2, self.diag))
+            b = rhs
+            if with_rhs:
+                sp.domain_lf(src1, out=lf)
+                if getattr(form, "_comm", None) is not None:
+                    form._comm.exchange_sum(lf)
+                fm.mult(self.T0, mt)
+                b = env.ctx.add(lf, 1.0, mt, out=rhs2)
             T1.copy_(self.T0)
-            return form.pcg(d2, rhs, T1, rel_tol, 0.0, max_iter, want_norms=False)[0]
+            return form.pcg(d2, b, T1, rel_tol, 0.0, max_iter, want_norms=False)[0]
 
         step()
         res = [None]
         ms = env.timed(lambda: res.__setitem__(0, step()), 1, collective)
+        if fm is not None:
+            fm.close()
         return ms, res[0]
 
     def close(self):
@@ -475,7 +496,7 @@ class Problem:
         self.env.free()
 
 
-def leg_bioheat(P, form, collective=True, fixed_iters=10):
+def leg_bioheat(P, form, collective=True, fixed_iters=10, with_rhs=False):
     """PCG iteration time + the implicit bioheat step to tolerance and at a fixed iteration count"""
     rhs = P.rhs(form)
     out = {"pcg": P.pcg_times(form, rhs, 20, collective)}
@@ -486,6 +507,12 @@ def leg_bioheat(P, form, collective=True, fixed_iters=10):
     out["bioheat_step_fixed"] = {"ms": ms, "pcg_iters": res.final_iter,
                                  "what": f"the same step with exactly {fixed_iters} PCG iterations (comparable across GPU counts: "
                                          "the iteration count to tolerance grows with the global mesh)"}
+    if not with_rhs:
+        return out
+    ms, res = P.implicit_step(form, rhs, 1e-8, 500, collective, with_rhs=True)
+    out["bioheat_step_with_rhs"] = {"ms": ms, "pcg_iters": res.final_iter, "converged": bool(res.converged),
+                                    "what": "SURVEY 8(d)(ii): k(T) q-data + PA set-up + Jacobi diagonal + right-hand side (perfusion source "
+                                            "load vector + (rho c/dt) M T^n) + PCG to rel 1e-8"}
     return out
 
 
@@ -697,7 +724,7 @@ def main():
 
     # ---- PCG iteration time and the implicit bioheat step on the headline configuration
     if "bioheat" in legs:
-        bh = leg_bioheat(P, form)
+        bh = leg_bioheat(P, form, with_rhs=True)
         line.update(bh)
         solo = line_extra.pop("_solo", None)
         if solo is not None:
@@ -789,7 +816,7 @@ def main():
             t = S.apply_times(S.form, 10, 3)
             r = {"what": "configs[2]: RF-ablation coupled step, order 2, hex 155^3, 30,080,231 dofs, one GPU", "dofs": S.nd,
                  "apply": S.roofline(t), "setup_s": S.setup_s}
-            r.update(leg_bioheat(S, S.form))
+            r.update(leg_bioheat(S, S.form, with_rhs=True))
             r["rf_step"] = rf_leg(S, (nn, nn, nn))
             S.close()
             return r

@@ -592,8 +592,9 @@ static int time_apply(int argc, char **argv)
    Vector x(ND), y(ND); x.Randomize(1); y = 0.0;
    x.UseDevice(true); y.UseDevice(true);
    for (int i = 0; i < warm; i++) { a.Mult(x, y); }
+   MFEM_DEVICE_SYNC;   // no-op on the CPU devices; with the reference's CUDA backend (make refcuda) the kernels are asynchronous
    vector<double> ts(reps);
-   for (int i = 0; i < reps; i++) { t0 = now(); a.Mult(x, y); ts[i] = now() - t0; }
+   for (int i = 0; i < reps; i++) { t0 = now(); a.Mult(x, y); MFEM_DEVICE_SYNC; ts[i] = now() - t0; }
    double tsum = 0, tmin = 1e300, tmax = 0;
    for (double t : ts) { tsum += t; tmin = min(tmin, t); tmax = max(tmax, t); }
    double t_pcg = 0.0;
@@ -604,7 +605,8 @@ static int time_apply(int argc, char **argv)
       CGSolver cg; cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(pcg_iters); cg.SetPrintLevel(-1);
       cg.SetOperator(a); cg.SetPreconditioner(M);
       Vector X(ND); X = 0.0;
-      t0 = now(); cg.Mult(x, X); t_pcg = now() - t0;
+      MFEM_DEVICE_SYNC;
+      t0 = now(); cg.Mult(x, X); MFEM_DEVICE_SYNC; t_pcg = now() - t0;
    }
    int nthreads = 1;
 #ifdef _OPENMP
