@@ -8,7 +8,7 @@ communicator object / transport the timed region uses.  Every rank solves the se
 """
 import numpy as np
 
-from . import Form, Space, basis, essential_dofs, hex_build, partition, randomize
+from . import Comm, Form, Multigrid, Space, Transfer, basis, basis_transfer, essential_dofs, hex_build, partition, randomize
 
 
 def _field(lat):
@@ -105,5 +105,88 @@ def partitioned_vs_serial(ctx, comm, rank, world, p=2, GN=(8, 6, 4), full=True):
     comm.check_p2p()
     dist.barrier()   # nobody re-sets the communicator's tables while a peer is still inside its last exchange
     for h in (f, sp, fs, sps):
+        h.close()
+    return out
+
+
+def _level_comm(ctx, like, rank, world):
+    """one communicator per multigrid level (the shared-dof tables differ per order), on the transport `like` uses"""
+    import torch.distributed as dist
+    if like.p2p_enabled():
+        return Comm(ctx, None, rank, world)          # peer memory only
+    ids = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    return Comm(ctx, ids[0], rank, world)
+
+
+def multigrid_partitioned_vs_serial(ctx, comm, rank, world, orders=(1, 2, 3), GN=(6, 4, 4)):
+    """p-multigrid across ranks == the same hierarchy on one GPU (transfers, one V-cycle, MG-preconditioned CG), with the
+    serial run's eigenvalue estimates handed to both so that the two cycles are the same polynomial.  `comm` only selects
+    the transport; every level gets a communicator of its own."""
+    import torch.distributed as dist
+    grid = partition.GRIDS[world]
+    L = len(orders)
+    par, ser, comms = [], [], []
+    for p in orders:
+        m = partition.build_part(GN, grid, rank, p, size=(1.0, 0.7, 0.4), skew=True)
+        c = _level_comm(ctx, comm, rank, world)
+        c.set_tables(m["ndofs"], *partition.shared_tables(m, grid, p))
+        comms.append(c)
+        par.append((m,) + _setup(ctx, m, p, [1, 6], c))
+        ms = hex_build(*GN, p, 1.0, 0.7, 0.4, skew=True)
+        ser.append((ms,) + _setup(ctx, ms, p, [1, 6]))
+    gid = [partition.global_ids(x[0], GN, p) for x, p in zip(par, orders)]
+    gs = [partition.global_ids(dict(lattice=x[0]["lattice"]), GN, p) for x, p in zip(ser, orders)]
+    T = [Transfer(par[l][2], par[l + 1][2], basis_transfer(orders[l], orders[l + 1])) for l in range(L - 1)]
+    Ts = [Transfer(ser[l][2], ser[l + 1][2], basis_transfer(orders[l], orders[l + 1])) for l in range(L - 1)]
+    out = {"orders": list(orders), "global_mesh": list(GN)}
+
+    def cmp(l, loc, serial, tol, what):
+        a = ctx.to_host(loc)
+        s = np.empty(ser[l][0]["ndofs"])
+        s[gs[l]] = ctx.to_host(serial)
+        err = float(np.max(np.abs(a - s[gid[l]])) / max(np.max(np.abs(s)), 1e-300))
+        assert err <= tol, f"rank {rank}: multigrid {what}: rel err {err:.3e} > {tol:.1e}"
+        return err
+
+    rng = np.random.default_rng(5)
+    errs = []
+    for l in range(L - 1):
+        xc, xf = rng.random(ser[l][0]["ndofs"]), rng.random(ser[l + 1][0]["ndofs"])      # lattice-indexed global vectors
+        errs.append(cmp(l + 1, T[l].mult(ctx.to_dev(xc[gid[l]])), Ts[l].mult(ctx.to_dev(xc[gs[l]])), 1e-13, f"prolongation {l}"))
+        errs.append(cmp(l, T[l].mult_transpose(ctx.to_dev(xf[gid[l + 1]])), Ts[l].mult_transpose(ctx.to_dev(xf[gs[l + 1]])), 1e-12,
+                        f"restriction {l}"))
+    out["transfer_rel_err"] = max(errs)
+    mgs = Multigrid([x[2] for x in ser], Ts)
+    mgs.set_coarse_solver(1e-10, 0.0, 500)
+    mgs.setup()
+    eig = [mgs.max_eig(l) for l in range(L)]
+    mg = Multigrid([x[2] for x in par], T)
+    mg.set_coarse_solver(1e-10, 0.0, 500)
+    mg.setup()                                     # its own power method across the ranks ...
+    own = [mg.max_eig(l) for l in range(1, L)]
+    assert all(abs(a - b) <= 0.05 * b for a, b in zip(own, eig[1:])), f"rank {rank}: eigenvalue estimates {own} vs serial {eig[1:]}"
+    gl = [None] * world
+    dist.all_gather_object(gl, own)
+    assert all(g == gl[0] for g in gl), "eigenvalue estimates differ between ranks"
+    mg.setup(max_eig=eig)                          # ... then the serial estimates, so that both cycles are the same operator
+    n, ns = par[-1][0]["ndofs"], ser[-1][0]["ndofs"]
+    b = rng.random(ns)
+    ess_s = np.zeros(ns, bool)
+    ess_s[essential_dofs(ser[-1][0]["bdr_attr"], [1, 6])] = True
+    b[gs[-1][ess_s]] = 0.0                          # a right-hand side of the eliminated system
+    out["vcycle_rel_err"] = cmp(L - 1, mg.mult(ctx.to_dev(b[gid[-1]])), mgs.mult(ctx.to_dev(b[gs[-1]])), 1e-8, "V-cycle")
+    X, Xs = ctx.zeros(n), ctx.zeros(ns)
+    r, nrm = mg.pcg(ctx.to_dev(b[gid[-1]]), X, 1e-10, 0.0, 100)
+    rs, nrms = mgs.pcg(ctx.to_dev(b[gs[-1]]), Xs, 1e-10, 0.0, 100)
+    assert r.converged and rs.converged and abs(r.final_iter - rs.final_iter) <= 1, (r.final_iter, rs.final_iter)
+    out["mgpcg_iters"] = [int(r.final_iter), int(rs.final_iter)]
+    out["mgpcg_rel_err"] = cmp(L - 1, X, Xs, 1e-7, "MG-PCG solution")
+    k = min(len(nrm), len(nrms), 4)
+    assert np.max(np.abs(nrm[:k] - nrms[:k]) / nrms[0]) <= 1e-7
+    for c in comms:
+        c.check_p2p()
+    dist.barrier()
+    for h in [mg, mgs] + T + Ts + [x[2] for x in par + ser] + [x[1] for x in par + ser] + comms:
         h.close()
     return out

@@ -1665,6 +1665,24 @@ extern "C" int b200pa_form_eliminate_rhs(b200pa_form f, const double *x_dev, dou
 }
 
 // -------------------------------------------------------------------------- PCG
+// multi-GPU PCG: all-reduce of one partial dot + the scalar step that consumes it (1: after the initial residual, 2: beta,
+// 3: alpha's denominator) - one launch over peer memory, or NCCL + a 1-thread kernel
+static int pcg_reduce_step(b200pa_form f, PcgState *st, double *norms, double *val, int step)
+{
+   cudaStream_t s = f->sp->ctx->stream;
+   bool handled = false;
+   // peer path: d.Ad arrives in two local parts (non-shared dofs: dot_b, shared dofs: dot_b2)
+   const double *extra = (step == 3 && comm_px(f->comm)) ? &st->dot_b2 : nullptr;
+   if (comm_allreduce_scalar_step(f->comm, val, step, st, norms, &handled, extra)) { return 1; }
+   if (handled) { return 0; }
+   if (comm_allreduce_sum_dev(f->comm, val, 1)) { return 1; }
+   if (step == 1) { k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms); }
+   else if (step == 2) { k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms); }
+   else { k_pcg_scalar_den<<<1, 1, 0, s>>>(st); }
+   B200PA_LAUNCHED();
+   return 0;
+}
+
 // The PCG loops keep their scalars on the device; the host only needs to learn that the solve has ended.  Reading the
 // flag back with a stream synchronisation drains the queue and costs ~0.4 ms of idle GPU per poll (measured at 8 M dofs:
 // iteration 9 of a poll-every-8 loop took 1.24 ms instead of 0.86).  So the read-back of block k is only WAITED for after
@@ -1738,20 +1756,7 @@ extern "C" int b200pa_pcg_solve(b200pa_form f, const double *dinv_dev, const dou
    k_pcg_init<<<grid, 256, 0, s>>>(n, b_dev, dinv_dev, r, d, own, ctx->d_partials, ctx->d_ticket, st, ep_norms);
    B200PA_LAUNCHED();
    // multi-GPU: all-reduce + scalar step, one launch over peer memory or NCCL + a 1-thread kernel
-   auto reduce_step = [&](double *val, int step) -> int
-   {
-      bool handled = false;
-      // peer path: d.Ad arrives in two local parts (non-shared dofs: dot_b, shared dofs: dot_b2)
-      const double *extra = (step == 3 && comm_px(f->comm)) ? &st->dot_b2 : nullptr;
-      if (comm_allreduce_scalar_step(f->comm, val, step, st, norms, &handled, extra)) { return 1; }
-      if (handled) { return 0; }
-      if (comm_allreduce_sum_dev(f->comm, val, 1)) { return 1; }
-      if (step == 1) { k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms); }
-      else if (step == 2) { k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms); }
-      else { k_pcg_scalar_den<<<1, 1, 0, s>>>(st); }
-      B200PA_LAUNCHED();
-      return 0;
-   };
+   auto reduce_step = [&](double *val, int step) -> int { return pcg_reduce_step(f, st, norms, val, step); };
    if (!fused_scalars && reduce_step(&st->dot_a, 1)) { return 1; }
    // z = A d; den = (z, d)                                                   (:921-938)
    if (form_apply(f, d, z, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
@@ -1842,6 +1847,22 @@ extern "C" int b200pa_chebyshev_coeffs(int order, double max_eig, double *coeffs
 // z = p(Dinv A) Dinv r: OperatorChebyshevSmoother::Mult, linalg/solvers.cpp:623-657, on the constrained operator.
 // st != NULL: called from the PCG - kernels return at once when st->done is set, and the last term carries the
 // reduction (r, z) with scalar step `scalar_step` as its epilogue when `norms_ep` is given.
+// (a, b) of two consistent L-vectors of the form's space, on the host: every dof counted once
+static int form_dot_host(b200pa_form f, const double *a, const double *b, double *out)
+{
+   b200pa_ctx ctx = f->sp->ctx;
+   const int n = f->sp->ndofs;
+   if (!f->comm) { return b200pa_dot(ctx, n, a, b, out); }
+   k_dot_masked<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, a, b, comm_owner_mask(f->comm), ctx->d_partials, ctx->d_ticket, ctx->d_result);
+   B200PA_LAUNCHED();
+   if (comm_allreduce_sum_dev(f->comm, ctx->d_result, 1)) { return 1; }
+   B200PA_CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+   B200PA_CK(cudaStreamSynchronize(ctx->stream));
+   if (comm_px_check(f->comm, "dot")) { return 1; }
+   *out = ctx->h_result[0];
+   return 0;
+}
+
 static int cheb_apply(b200pa_form f, const double *dinv, int order, const double *coeffs, const double *r, double *z, PcgState *st,
                       bool want_dot, double *norms_ep, int scalar_step)
 {
@@ -1884,14 +1905,14 @@ extern "C" int b200pa_chebyshev_mult(b200pa_form f, const double *dinv_dev, int 
 
 // PowerMethod::EstimateLargestEigenvalue (linalg/operator.cpp:871-928) for Dinv * A, the operator the reference's
 // OperatorChebyshevSmoother hands it (linalg/solvers.cpp:497-511).  v0_dev: start vector (the reference:
-// Vector::Randomize(seed), b200pa_randomize), overwritten.  One GPU (the reference's serial PowerMethod).
+// Vector::Randomize(seed), b200pa_randomize), overwritten.  With a communicator on the form v0 must be a consistent
+// L-vector and the inner products count every dof once (owner mask + all-reduce); every rank gets the same estimate.
 extern "C" int b200pa_power_method(b200pa_form f, const double *dinv_dev, double *v0_dev, int num_steps, double tolerance, double *max_eig)
 {
    B200PA_REQUIRE(f && dinv_dev && v0_dev && max_eig, "power_method: NULL argument");
    b200pa_space sp = f->sp;
    b200pa_ctx ctx = sp->ctx;
    NEED_CTX(ctx);
-   B200PA_REQUIRE(!f->comm, "power_method: one GPU only (pass the estimate to the other ranks)");
    B200PA_REQUIRE(f->cgmap.p, "power_method: call b200pa_form_set_essential first (n_ess may be 0)");
    const int n = sp->ndofs;
    if (need_work(f)) { return 1; }
@@ -1903,10 +1924,10 @@ extern "C" int b200pa_power_method(b200pa_form f, const double *dinv_dev, double
    for (int iter = 0; iter < num_steps && !rc; ++iter)
    {
       double normV0 = 0.0, eigenvalueNew = 0.0;
-      rc = b200pa_dot(ctx, n, a, a, &normV0);
+      rc = form_dot_host(f, a, a, &normV0);
       if (rc) { break; }
       if (n > 0) { k_div_scalar<<<grid1d(ctx, n), 256, 0, ctx->stream>>>(n, a, sqrt(normV0)); g_launches++; }
-      rc = form_apply(f, a, t, true, nullptr, nullptr) || b200pa_jacobi_mult(ctx, n, dinv_dev, t, b) || b200pa_dot(ctx, n, a, b, &eigenvalueNew);
+      rc = form_apply(f, a, t, true, nullptr, nullptr) || b200pa_jacobi_mult(ctx, n, dinv_dev, t, b) || form_dot_host(f, a, b, &eigenvalueNew);
       if (rc) { break; }
       const double diff = std::fabs((eigenvalueNew - eigenvalue) / eigenvalue);
       eigenvalue = eigenvalueNew;
@@ -1952,19 +1973,7 @@ extern "C" int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev,
    const bool fused_scalars = (f->comm == nullptr);
    double *ep_norms = fused_scalars ? norms : nullptr;
    PcgState *ep_st = fused_scalars ? st : nullptr;
-   auto reduce_step = [&](double *val, int step) -> int
-   {
-      bool handled = false;
-      const double *extra = (step == 3 && comm_px(f->comm)) ? &st->dot_b2 : nullptr;
-      if (comm_allreduce_scalar_step(f->comm, val, step, st, norms, &handled, extra)) { return 1; }
-      if (handled) { return 0; }
-      if (comm_allreduce_sum_dev(f->comm, val, 1)) { return 1; }
-      if (step == 1) { k_pcg_scalar_init<<<1, 1, 0, s>>>(st, norms); }
-      else if (step == 2) { k_pcg_scalar_beta<<<1, 1, 0, s>>>(st, norms); }
-      else { k_pcg_scalar_den<<<1, 1, 0, s>>>(st); }
-      B200PA_LAUNCHED();
-      return 0;
-   };
+   auto reduce_step = [&](double *val, int step) -> int { return pcg_reduce_step(f, st, norms, val, step); };
    // r = b - A x; z = B r; d = z; nom = (d, r)
    if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
    if (n > 0) { k_residual<<<grid, 256, 0, s>>>(n, b_dev, r); B200PA_LAUNCHED(); }
@@ -2098,6 +2107,9 @@ extern "C" int b200pa_transfer_mult(b200pa_transfer t, const double *xc_dev, dou
    const int grid = (int)std::min<long long>(P.NE, (long long)ctx->num_sms * 8);
    k_mg_prolong<<<grid, 128, transfer_smem(t), ctx->stream>>>(P, xc_dev, yf_dev);
    B200PA_LAUNCHED();
+   // partitioned: both sides of an interface interpolate the same polynomial, but through different elements; the owner's
+   // value is broadcast so that the copies of a shared dof stay bit-identical (consistent L-vector)
+   if (t->ff->comm && comm_exchange_owner(t->ff->comm, yf_dev)) { return 1; }
    return 0;
 }
 
@@ -2108,14 +2120,18 @@ extern "C" int b200pa_transfer_mult_transpose(b200pa_transfer t, const double *x
    b200pa_space sc = t->fc->sp;
    b200pa_ctx ctx = sc->ctx;
    NEED_CTX(ctx);
-   B200PA_REQUIRE(!t->fc->comm && !t->ff->comm, "transfer: one GPU only");
+   B200PA_REQUIRE((t->fc->comm == nullptr) == (t->ff->comm == nullptr), "transfer: both levels need a communicator, or neither");
    if (sc->ne == 0) { return 0; }
    const TransferParams P = transfer_params(t);
+   // partitioned: every fine dof contributes once globally - through the rank that owns it
+   const unsigned char *own_f = t->ff->comm ? comm_owner_mask(t->ff->comm) : nullptr;
    const int grid = (int)std::min<long long>(P.NE, (long long)ctx->num_sms * 8);
-   k_mg_restrict<<<grid, 128, transfer_smem(t), ctx->stream>>>(P, xf_dev, nullptr, sc->scratchE.as<double>());
+   k_mg_restrict<<<grid, 128, transfer_smem(t), ctx->stream>>>(P, xf_dev, own_f, sc->scratchE.as<double>());
    B200PA_LAUNCHED();
    k_mg_sum_zero<<<grid1d(ctx, sc->ndofs), 256, 0, ctx->stream>>>(sc->ndofs, sc->offsets.as<int>(), sc->scratchE.as<double>(), yc_dev, P.ess_c);
    B200PA_LAUNCHED();
+   // the coarse dofs on the interface got the contributions of this rank's fine dofs only
+   if (t->fc->comm && comm_exchange_sum(t->fc->comm, yc_dev, nullptr)) { return 1; }
    return 0;
 }
 
@@ -2153,7 +2169,8 @@ extern "C" int b200pa_mg_create(int nlevels, const b200pa_form *forms, const b20
    for (int l = 0; l < nlevels; ++l)
    {
       b200pa_form f = forms[l];
-      if (!f || !f->cgmap.p || f->comm) { return bail("mg_create: every level needs an assembled one-GPU form with b200pa_form_set_essential called"); }
+      if (!f || !f->cgmap.p) { return bail("mg_create: every level needs an assembled form with b200pa_form_set_essential called"); }
+      if ((f->comm == nullptr) != (forms[0]->comm == nullptr)) { return bail("mg_create: every level needs a communicator (one per level: the shared-dof tables differ), or none"); }
       if (l > 0 && (transfers[l - 1]->fc != forms[l - 1] || transfers[l - 1]->ff != f)) { return bail("mg_create: transfers[l] must connect forms[l] (coarse) and forms[l+1] (fine)"); }
       const size_t vb = sizeof(double) * (size_t)std::max(f->sp->ndofs, 1);
       if (alloc(m->X[l], vb) || alloc(m->Y[l], vb) || alloc(m->R[l], vb) || alloc(m->Z[l], vb) || alloc(m->dinv[l], vb)) { b200pa_mg_destroy(m); return 1; }
@@ -2213,6 +2230,9 @@ extern "C" int b200pa_mg_setup(b200pa_mg m, const int *order, const double *max_
          std::vector<double> v0((size_t)std::max(n, 1));
          b200pa_randomize(12345, n, v0.data());
          B200PA_CK(cudaMemcpyAsync(m->R[l].p, v0.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+         // partitioned: the owners' random values win, which makes the start vector a consistent L-vector (the estimate
+         // then differs from the serial one in the digits a 10-step power method does not resolve anyway)
+         if (f->comm && comm_exchange_owner(f->comm, m->R[l].as<double>())) { return 1; }
          if (b200pa_power_method(f, m->dinv[l].as<double>(), m->R[l].as<double>(), 10, 1e-8, &lam)) { return 1; }
       }
       m->max_eig[l] = lam;
@@ -2337,9 +2357,16 @@ extern "C" int b200pa_pcg_solve_mg(b200pa_mg m, const double *b_dev, double *x_d
    if (form_apply(f, x_dev, r, true, nullptr, nullptr)) { return 1; }
    if (n > 0) { k_residual<<<grid, 256, 0, s>>>(n, b_dev, r); B200PA_LAUNCHED(); }
    if (b200pa_mg_mult(m, r, z)) { return 1; }
-   k_dot_step<<<grid, 256, 0, s>>>(n, r, z, nullptr, ctx->d_partials, ctx->d_ticket, st, norms, 1); B200PA_LAUNCHED();
+   // one GPU: the scalar steps run as epilogues of the reductions; partitioned: all-reduce + scalar step after them
+   const bool fused_scalars = (f->comm == nullptr);
+   const unsigned char *own = f->comm ? comm_owner_mask(f->comm) : nullptr;
+   double *ep_norms = fused_scalars ? norms : nullptr;
+   PcgState *ep_st = fused_scalars ? st : nullptr;
+   k_dot_step<<<grid, 256, 0, s>>>(n, r, z, own, ctx->d_partials, ctx->d_ticket, st, ep_norms, 1); B200PA_LAUNCHED();
+   if (!fused_scalars && pcg_reduce_step(f, st, norms, &st->dot_a, 1)) { return 1; }
    B200PA_CK(cudaMemcpyAsync(d, z, vb, cudaMemcpyDeviceToDevice, s));
-   if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, st)) { return 1; }
+   if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+   if (!fused_scalars && pcg_reduce_step(f, st, norms, &st->dot_b, 3)) { return 1; }
    int *h_done = (int *)(ctx->h_result + 4);
    for (int it = 1; it <= std::max(max_iter, 1); ++it)
    {
@@ -2349,13 +2376,16 @@ extern "C" int b200pa_pcg_solve_mg(b200pa_mg m, const double *b_dev, double *x_d
       if (*h_done) { break; }
       if (n > 0) { k_pcg_update_plain<<<grid, 256, 0, s>>>(n, x_dev, r, q, d, st); B200PA_LAUNCHED(); }
       if (b200pa_mg_mult(m, r, z)) { return 1; }
-      k_dot_step<<<grid, 256, 0, s>>>(n, r, z, nullptr, ctx->d_partials, ctx->d_ticket, st, norms, 2); B200PA_LAUNCHED();
+      k_dot_step<<<grid, 256, 0, s>>>(n, r, z, own, ctx->d_partials, ctx->d_ticket, st, ep_norms, 2); B200PA_LAUNCHED();
+      if (!fused_scalars && pcg_reduce_step(f, st, norms, &st->dot_a, 2)) { return 1; }
       if (n > 0) { k_pcg_direction<<<grid, 256, 0, s>>>(n, z, d, st); B200PA_LAUNCHED(); }
-      if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, st)) { return 1; }
+      if (form_apply(f, d, q, true, &st->dot_b, &st->done, 3, ep_st)) { return 1; }
+      if (!fused_scalars && pcg_reduce_step(f, st, norms, &st->dot_b, 3)) { return 1; }
    }
    PcgState hs;
    B200PA_CK(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, s));
    B200PA_CK(cudaStreamSynchronize(s));
+   if (comm_px_check(f->comm, "pcg_solve_mg")) { return 1; }
    B200PA_REQUIRE(!hs.nonfinite, "pcg_solve_mg: non-finite (B r, r) or (A d, d)");
    B200PA_REQUIRE(hs.done, "pcg_solve_mg: internal error (loop ended without a terminal state)");
    res->final_iter = hs.final_iter;

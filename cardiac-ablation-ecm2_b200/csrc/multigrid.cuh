@@ -142,6 +142,18 @@ __global__ void k_mg_sum_zero(int ndofs, const int *__restrict__ offsets, const 
    }
 }
 
+// (a, b) over the dofs this rank owns (mask == NULL: all)
+__global__ void k_dot_masked(int n, const double *__restrict__ a, const double *__restrict__ b, const unsigned char *__restrict__ own_mask,
+                             double *partials, unsigned int *ticket, double *out)
+{
+   double acc = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      if (!own_mask || own_mask[i]) { acc = fma(a[i], b[i], acc); }
+   }
+   grid_sum(acc, partials, ticket, out);
+}
+
 // (r, z) over the owned dofs + the PCG scalar step that consumes it (1: after the initial residual, 2: in the loop), for
 // preconditioners that are not fused into a vector pass of the loop (the multigrid cycle)
 __global__ void k_dot_step(int n, const double *__restrict__ r, const double *__restrict__ z, const unsigned char *__restrict__ own_mask,

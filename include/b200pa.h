@@ -261,7 +261,8 @@ int b200pa_pcg_solve_host(b200pa_form f, const double *dinv_dev, const double *b
  *   b200pa_chebyshev_coeffs : ::Setup's polynomial coefficients (:571-621); host arithmetic, needs no device
  *   b200pa_power_method     : PowerMethod::EstimateLargestEigenvalue (linalg/operator.cpp:871-928) of Dinv*A, the
  *                             estimate the smoother's second constructor computes (:497-511: 10 steps, 1e-8, start
- *                             vector Vector::Randomize(12345) - b200pa_randomize); v0_dev is overwritten; one GPU
+ *                             vector Vector::Randomize(12345) - b200pa_randomize); v0_dev is overwritten; with a
+ *                             communicator on the form v0 must be a consistent L-vector
  *   b200pa_chebyshev_mult   : ::Mult (:623-657): y = p(Dinv A) Dinv x; dinv = b200pa_jacobi_setup(damping 1)
  *   b200pa_pcg_solve_chebyshev : CGSolver::Mult with that smoother as the preconditioner (same result struct,
  *                             stopping rule and residual history as b200pa_pcg_solve) */
@@ -274,7 +275,7 @@ int b200pa_pcg_solve_chebyshev(b200pa_form f, const double *dinv_dev, int order,
                                double *x_dev, double rel_tol, double abs_tol, int max_iter, b200pa_pcg_result *res,
                                double *norms_host);
 
-/* ------------------------------------------------------ p-multigrid (one GPU) */
+/* ------------------------------------------------------ p-multigrid */
 /* Order-refinement transfer between two forms on the SAME mesh (coarse order <= fine order):
  * TensorProductPRefinementTransferOperator::{Mult, MultTranspose} (fem/transfer.cpp:2223-2296, 2542-2592) wrapped
  * in the RectangularConstrainedOperator a GeometricMultigrid gives it (fem/multigrid.cpp:281-296): essential dofs of
@@ -291,7 +292,12 @@ int b200pa_transfer_mult_transpose(b200pa_transfer t, const double *xf_dev, doub
  * largest-eigenvalue estimate per level, <= 0 = the reference's power method); level 0: CGSolver to (rel_tol, abs_tol,
  * max_iter), unpreconditioned as in ex26 or with OperatorJacobiSmoother (jacobi = 1).  b200pa_mg_setup must be called again
  * after the forms are re-assembled.  b200pa_mg_mult = MultigridBase::Mult: one V- (or W-) cycle from a zero guess.
- * b200pa_pcg_solve_mg = CGSolver::Mult on the finest constrained operator preconditioned by the cycle. */
+ * b200pa_pcg_solve_mg = CGSolver::Mult on the finest constrained operator preconditioned by the cycle.
+ * Partitioned meshes: give EVERY level's form a communicator of its own (b200pa_form_set_comm; the shared-dof tables
+ * differ per order) before b200pa_mg_create.  Vectors are consistent L-vectors on every level: the prolongation
+ * broadcasts the owners' values of shared fine dofs, the restriction counts every fine dof once (through its owner) and
+ * sums the coarse interface dofs across ranks, smoothers / coarse CG / outer CG use the all-reduced dots; the power
+ * method starts from the owners' random values, so every rank gets the same eigenvalue estimate. */
 typedef struct b200pa_mg_s *b200pa_mg;
 int b200pa_mg_create(int nlevels, const b200pa_form *forms, const b200pa_transfer *transfers, b200pa_mg *out);
 int b200pa_mg_destroy(b200pa_mg m);

@@ -34,10 +34,12 @@ def main():
     r = selfcheck.partitioned_vs_serial(ctx, comm, rank, world, p)
     want_p2p = os.environ.get("B200PA_NO_P2P", "0") != "1"
     assert comm.p2p_enabled() == want_p2p, f"transport: peer-memory path enabled={comm.p2p_enabled()}, expected {want_p2p}"
+    g = selfcheck.multigrid_partitioned_vs_serial(ctx, comm, rank, world, orders=(1, 2, 3) if p != 3 else (1, 3))
     if rank == 0:
         print(f"MULTI_OK world={world} p={p} p2p={comm.p2p_enabled()} apply={r['apply_rel_err']:.2e} diag={r['diag_rel_err']:.2e} "
               f"pcg={r['pcg15_rel_err']:.2e} cheb={r['cheb_pcg6_rel_err']:.2e} fact={r['factorised_apply_rel_err']:.2e} "
-              f"its={r['pcg_iters_to_1e-8']}", flush=True)
+              f"its={r['pcg_iters_to_1e-8']} mg_transfer={g['transfer_rel_err']:.2e} mg_vcycle={g['vcycle_rel_err']:.2e} "
+              f"mg_pcg={g['mgpcg_rel_err']:.2e} mg_its={g['mgpcg_iters']}", flush=True)
     comm.close()
     ctx.close()
     dist.destroy_process_group()
