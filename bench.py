@@ -824,14 +824,14 @@ def main():
 
     # ---- the electrostatic solve (pure diffusion, Dirichlet on two faces) to a tolerance: Jacobi-PCG against PCG
     #      preconditioned by the p-multigrid cycle (orders 1 -> 2, Chebyshev smoothers, CG coarse solve: examples/ex26.cpp)
-    if world == 1 and "mg" in legs and p == 2:
+    if "mg" in legs and p == 2:
         def mg_leg():
-            from b200pa import partition
+            from b200pa import partition, selfcheck
             nn = min(n, 64)
-            GNm = (nn, nn, nn)
-            levels = []
+            GNm = (nn * grid[0], nn * grid[1], nn * grid[2])
+            levels, lcomms = [], []
             for pp in (1, 2):
-                mm = partition.build_part(GNm, (1, 1, 1), 0, pp, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
+                mm = partition.build_part(GNm, grid, rank, pp, want=("gather_map", "elem_vertices", "vertices", "bdr_attr", "lattice"))
                 bb = b200pa.basis(pp)
                 spp = b200pa.Space(ctx, pp + 1, pp + 2, mm["ne"], mm["ndofs"], mm["gather_map"], bb["B"], bb["G"])
                 spp.geometry_from_vertices(bb["W"], mm["vertices"], mm["elem_vertices"])
@@ -842,6 +842,11 @@ def main():
                 ff.assemble_diffusion(spp.coeff_linear(PHYS["s0"], PHYS["as_"], 37.0, Tl))
                 ess = b200pa.essential_dofs(mm["bdr_attr"], [1, 6])
                 ff.set_essential(ess)
+                if comm is not None:      # one communicator per level (the shared-dof tables differ per order), same transport
+                    lc = selfcheck._level_comm(ctx, comm, rank, world)
+                    lc.set_tables(mm["ndofs"], *partition.shared_tables(mm, grid, pp))
+                    ff.set_comm(lc)
+                    lcomms.append(lc)
                 levels.append((spp, ff, mm, ess, lat))
             spf, ffn, mf, ess, lat = levels[1]
             T = b200pa.Transfer(levels[0][1], ffn, b200pa.basis_transfer(1, 2))
@@ -849,9 +854,10 @@ def main():
             mg.set_coarse_solver(1e-2, 0.0, 200, jacobi=True)
             mg.setup()
             phi_bc = np.zeros(mf["ndofs"])
-            phi_bc[ess] = PHYS["V"] * (1.0 - lat[ess, 2] / (2 * nn))
-            out = {"what": f"electrostatic solve div sigma(T) grad phi = 0 to rel 1e-8, order 2, hex {nn}^3, {mf['ndofs']} dofs: "
-                           "OperatorJacobiSmoother against the p-multigrid V-cycle (orders 1-2) as the CG preconditioner"}
+            phi_bc[ess] = PHYS["V"] * (1.0 - lat[ess, 2] / (2 * GNm[2]))
+            out = {"what": f"electrostatic solve div sigma(T) grad phi = 0 to rel 1e-8, order 2, hex {GNm[0]}x{GNm[1]}x{GNm[2]}, "
+                           f"{global_dofs_of(GNm, 2)} dofs on {world} GPU(s): OperatorJacobiSmoother against the p-multigrid V-cycle "
+                           "(orders 1-2) as the CG preconditioner"}
             for name in ("jacobi", "p_multigrid"):
                 def solve():
                     phi = ctx.to_dev(phi_bc)
@@ -868,6 +874,9 @@ def main():
             mg.close(); T.close()
             for spp, ff, *_ in levels:
                 ff.close(); spp.close()
+            for lc in lcomms:
+                lc.check_p2p()
+                lc.close()
             return out
         guarded("p_multigrid", mg_leg)
 
