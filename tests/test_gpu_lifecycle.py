@@ -21,7 +21,7 @@ def one_cycle(ctx, p):
         sp.set_attributes(1 + (np.arange(m["ne"]) % 3))
         nq = m["ne"] * (pp + 2) ** 3
         f = b200pa.Form(sp)
-        f.set_markers(1, [1, 0, 1])
+        f.set_markers(0, [1, 0, 1])      # diffusion acts on attributes 1 and 3 only; the mass term keeps every diagonal entry positive
         f.assemble_diffusion(0.5 + np.random.default_rng(1).random(nq))
         f.assemble_mass(np.array([3.6]))
         f.set_essential(b200pa.essential_dofs(m["bdr_attr"], [1, 6]))
