@@ -194,6 +194,20 @@ def run_reference_cpu(p, n, reps, warm):
     raise RuntimeError("ref_driver failed: " + out.stderr[-400:])
 
 
+def run_reference_cuda(p, n, reps, warm):
+    """the reference's OWN CUDA backend on the same GPU (oracle/_ref/ref_driver_cuda = the unmodified sources compiled with
+    nvcc -x cu for sm_100 by `make -C oracle refcuda`; optional - None when it was not built): a second baseline reported
+    inside the cpu_baseline leg, never on the product path"""
+    drv = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "ref_driver_cuda")
+    if not os.path.exists(drv):
+        return None
+    out = subprocess.run([drv, "time_apply", str(p), str(n), str(reps), str(warm), "cuda"], capture_output=True, text=True, timeout=600)
+    for line in out.stdout.splitlines():
+        if line.startswith("{"):
+            return json.loads(line)
+    return None
+
+
 def run_reference_bioheat(p, n, iters):
     """the reference's own composition of the coupled RF + bioheat step (oracle/ref_driver.cpp `bioheat`)"""
     drv = ref_driver_path()
@@ -763,6 +777,16 @@ def main():
                 # full-size parity: same mesh, same numbering, same x = Randomize(1), same operator
                 line["parity_vs_reference_cpu"] = {"ref_y_norm": r["y_norm"], "gpu_y_norm": float(np.sqrt(ynorm2)),
                                                    "rel_diff": abs(np.sqrt(ynorm2) - r["y_norm"]) / r["y_norm"]}
+                try:
+                    rc = run_reference_cuda(p, n, 10, 3)
+                    if rc is not None:
+                        line["cpu_baseline"]["reference_cuda_backend_same_gpu"] = {
+                            "value": rc["ndofs"] / rc["t_apply_mean"] / 1e9, "unit": "GDOF/s", "ms_per_apply": rc["t_apply_mean"] * 1e3,
+                            "y_norm": rc["y_norm"], "rel_diff_vs_this_library": abs(np.sqrt(ynorm2) - rc["y_norm"]) / rc["y_norm"],
+                            "what": "the reference's own CUDA kernels (unmodified sources, nvcc -x cu, sm_100; BilinearForm(PARTIAL)::Mult "
+                                    "under Device(\"cuda\")) on this GPU, same workload and input vector; 10 applies after 3 warm-ups"}
+                except Exception as e:  # noqa: BLE001
+                    line["cpu_baseline"]["reference_cuda_backend_same_gpu"] = {"failed": str(e)[:200]}
                 if "rf_step" in line and args.ops == "both":
                     rb = run_reference_bioheat(p, n, 20)
                     t_ref = sum(rb[k] for k in ("t_coef", "t_asm_e", "t_cg_e", "t_joule", "t_asm_t", "t_rhs", "t_cg_t"))
