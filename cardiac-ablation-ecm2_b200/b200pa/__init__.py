@@ -270,8 +270,8 @@ class Context:
         check(lib().b200pa_host_alloc(self.h, C.c_size_t(8 * int(n)), C.byref(p)))
         buf = (C.c_double * int(n)).from_address(p.value)
         a = np.ctypeslib.as_array(buf)
-        h, addr = self.h, p.value
-        weakref.finalize(buf, lambda: lib().b200pa_host_free(h, vp(addr)))
+        addr = p.value
+        weakref.finalize(buf, lambda: lib().b200pa_host_free(None, vp(addr)))   # may run after the context is closed
         if fill is not None:
             a[:] = fill
         return a

@@ -347,7 +347,7 @@ static bool numa_node_cpus(int node, cpu_set_t *set)
    fclose(f);
    return n > 0;
 }
-struct HostBlock { void *p; size_t bytes; int node; };
+struct HostBlock { void *p; size_t bytes; int node; int device; };
 static std::mutex g_host_mu;
 static std::vector<HostBlock> g_host_blocks;
 
@@ -377,7 +377,7 @@ extern "C" int b200pa_host_alloc(b200pa_ctx c, size_t bytes, void **out)
    }
    {
       std::lock_guard<std::mutex> g(g_host_mu);
-      g_host_blocks.push_back({p, len, moved ? node : -1});
+      g_host_blocks.push_back({p, len, moved ? node : -1, c->device});
    }
    *out = p;
    return 0;
@@ -385,8 +385,8 @@ extern "C" int b200pa_host_alloc(b200pa_ctx c, size_t bytes, void **out)
 extern "C" int b200pa_host_free(b200pa_ctx c, void *p)
 {
    if (!p) { return 0; }
-   B200PA_REQUIRE(c, "host_free: ctx is NULL");
-   HostBlock blk{nullptr, 0, -1};
+   (void)c; // the block remembers its device: it may outlive the context it was allocated through
+   HostBlock blk{nullptr, 0, -1, 0};
    {
       std::lock_guard<std::mutex> g(g_host_mu);
       for (size_t i = 0; i < g_host_blocks.size(); i++)
@@ -395,8 +395,8 @@ extern "C" int b200pa_host_free(b200pa_ctx c, void *p)
       }
    }
    B200PA_REQUIRE(blk.p, "host_free: pointer was not returned by b200pa_host_alloc");
-   B200PA_CK(cudaSetDevice(c->device));
-   B200PA_CK(cudaStreamSynchronize(c->stream));
+   B200PA_CK(cudaSetDevice(blk.device));
+   B200PA_CK(cudaDeviceSynchronize());      // no copy may still be reading or writing the pages
    B200PA_CK(cudaHostUnregister(p));
    munmap(p, blk.bytes);
    return 0;

@@ -65,7 +65,7 @@ int b200pa_memset(b200pa_ctx ctx, void *dev, int value, size_t bytes);
  * the rank runs on).  For the *_host entry points below at one rank per GPU: the vectors cross PCIe on every call and
  * should not cross the socket interconnect as well.  b200pa_host_node: node the block sits on, -1 = kernel default. */
 int b200pa_host_alloc(b200pa_ctx ctx, size_t bytes, void **out_host);
-int b200pa_host_free(b200pa_ctx ctx, void *host);
+int b200pa_host_free(b200pa_ctx ctx, void *host);   /* ctx may be NULL (the block remembers its device); waits for the device */
 int b200pa_host_node(const void *host);
 /* device-to-device copy of n doubles on the context's stream (Vector::operator=, linalg/vector.cpp:203-240) */
 int b200pa_copy(b200pa_ctx ctx, long long n, const double *src_dev, double *dst_dev);
