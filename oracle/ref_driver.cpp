@@ -580,6 +580,7 @@ static int time_apply(int argc, char **argv)
       });
       T0.ProjectCoefficient(Tinit);
       QuadratureFunction Tq(qs); Tq.ProjectGridFunction(T0);
+      Tq.HostRead(); kq.HostWrite(); mq.HostWrite();   // under Device("cuda") the projection ran on the device
       for (int i = 0; i < Tq.Size(); i++) { kq(i) = P.k0 * (1.0 + P.ak * (Tq(i) - 37.0)); mq(i) = P.rc / P.dt + P.wbcb; }
    }
    QuadratureFunctionCoefficient kc(kq), mc(mq);
