@@ -211,12 +211,14 @@ struct HostPipe
    std::vector<int> down_first, down_count;                // per chunk: its completed tiles as a slice of d_tiles
    b200pa::DevBuf d_tiles;
    cudaStream_t s_up = nullptr, s_down = nullptr;
-   std::vector<cudaEvent_t> ev_up, ev_done;
+   std::vector<cudaEvent_t> ev_up, ev_done, ev_down;
    cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+   bool trace = false;
    ~HostPipe()
    {
       for (cudaEvent_t e : ev_up) { cudaEventDestroy(e); }
       for (cudaEvent_t e : ev_done) { cudaEventDestroy(e); }
+      for (cudaEvent_t e : ev_down) { cudaEventDestroy(e); }
       if (ev_start) { cudaEventDestroy(ev_start); }
       if (ev_end) { cudaEventDestroy(ev_end); }
       if (s_up) { cudaStreamDestroy(s_up); }
@@ -1433,14 +1435,19 @@ static int build_pipe(b200pa_space sp)
    B200PA_CK(cudaStreamSynchronize(ctx->stream));
    B200PA_CK(cudaStreamCreateWithFlags(&hp->s_up, cudaStreamNonBlocking));
    B200PA_CK(cudaStreamCreateWithFlags(&hp->s_down, cudaStreamNonBlocking));
-   hp->ev_up.resize(C); hp->ev_done.resize(C);
+   // B200PA_PIPE_TRACE=1: timed events + one line per call on stderr with the time (ms after the start) at which every
+   // chunk's x tiles were up, its kernels were done and its y tiles were down - the tuning aid behind the numbers above
+   hp->trace = getenv("B200PA_PIPE_TRACE") != nullptr;
+   const unsigned evf = hp->trace ? cudaEventDefault : cudaEventDisableTiming;
+   hp->ev_up.resize(C); hp->ev_done.resize(C); hp->ev_down.resize(C);
    for (int c = 0; c < C; ++c)
    {
-      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_up[c], cudaEventDisableTiming));
-      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_done[c], cudaEventDisableTiming));
+      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_up[c], evf));
+      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_done[c], evf));
+      B200PA_CK(cudaEventCreateWithFlags(&hp->ev_down[c], evf));
    }
-   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
-   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_end, cudaEventDisableTiming));
+   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_start, evf));
+   B200PA_CK(cudaEventCreateWithFlags(&hp->ev_end, evf));
    sp->pipe = hp;
    return 0;
 }
@@ -1500,12 +1507,28 @@ static int form_mult_host_pipelined(b200pa_form f, bool constrained, const doubl
       {
          B200PA_CK(cudaMemcpyAsync(y_host + r.first, y + r.first, sizeof(double) * (size_t)(r.second - r.first), cudaMemcpyDeviceToHost, hp.s_down));
       }
+      if (hp.trace) { B200PA_CK(cudaEventRecord(hp.ev_down[c], hp.s_down)); }
    }
    // the compute stream continues only after the last tile has left (w2 may be reused by the next call)
    B200PA_CK(cudaEventRecord(hp.ev_end, hp.s_down));
    B200PA_CK(cudaStreamWaitEvent(s, hp.ev_end, 0));
    B200PA_CK(cudaStreamSynchronize(hp.s_down));
    B200PA_CK(cudaStreamSynchronize(s));
+   if (hp.trace)
+   {
+      std::string line = "b200pa pipe trace (ms after start; chunk: x up | kernels done | y down, ranges up/down):";
+      for (int c = 0; c < hp.C; ++c)
+      {
+         float tu = 0, td = 0, tw = 0;
+         cudaEventElapsedTime(&tu, hp.ev_start, hp.ev_up[c]);
+         cudaEventElapsedTime(&td, hp.ev_start, hp.ev_done[c]);
+         cudaEventElapsedTime(&tw, hp.ev_start, hp.ev_down[c]);
+         char buf[160];
+         snprintf(buf, sizeof(buf), "  %d: %.3f | %.3f | %.3f (%zu/%zu)", c, tu, td, tw, hp.up[c].size(), hp.down[c].size());
+         line += buf;
+      }
+      fprintf(stderr, "%s\n", line.c_str());
+   }
    return 0;
 }
 
