@@ -93,3 +93,24 @@ def test_p_multigrid_through_mfem(n, pmax):
     r = run(["mg", n, pmax])[0]
     assert r["ok"] and r["vcycle"] <= 1e-8 and abs(r["iters_ref"] - r["iters_gpu"]) <= 1
     assert r["iters_gpu"] < r["iters_gpu_jacobi"]
+
+
+def test_example_application_runs(tmp_path):
+    """examples/rf_ablation.cpp - a stock MFEM application (mesh, spaces, BackwardEulerSolver, ParaViewDataCollection are the
+    reference's) whose operator / solver classes come from the binding - linked against the unmodified reference: it heats
+    the slab, its PCG solves converge, and the reference's own ParaView writer saves the fields the GPU produced"""
+    import re
+    exe = os.path.join(ROOT, "oracle", "_ref", "rf_ablation")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/rf_ablation not built (needs the reference tree: make -C oracle ref)")
+    out = subprocess.run([exe, "-n", "12", "-o", "2", "-dt", "0.5", "-tf", "3", "-vs", "2", "-pv"], capture_output=True, text=True, timeout=600,
+                         cwd=str(tmp_path), env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    steps = re.findall(r"step (\d+), t = ([\d.]+) s: max T = ([\d.eE+-]+) C, PCG iterations phi / T: (\d+) / (\d+)", out.stdout)
+    assert len(steps) >= 3
+    temps = [float(s[2]) for s in steps]
+    assert temps[0] > 37.0 and all(b > a for a, b in zip(temps, temps[1:]))            # Joule heating
+    assert all(0 < int(s[3]) < 500 and 0 < int(s[4]) < 500 for s in steps)             # both solves converged within the cap
+    assert "Iteration :" in out.stdout and "Average reduction factor" in out.stdout    # IterativeSolver print level 3, replayed
+    assert os.path.exists(tmp_path / "rf_ablation" / "rf_ablation.pvd")
+    assert len(list((tmp_path / "rf_ablation").glob("Cycle*/proc000000.vtu"))) >= 3
