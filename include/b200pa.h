@@ -223,7 +223,11 @@ int b200pa_form_mult(b200pa_form f, const double *x_dev, double *y_dev);
 int b200pa_form_mult_phases(b200pa_form f, const double *x_dev, double *y_dev, int phases);
 /* ConstrainedOperator::Mult (linalg/operator.cpp:586-646, 710-714) */
 int b200pa_form_constrained_mult(b200pa_form f, const double *x_dev, double *y_dev);
-/* the same two with HOST vectors: copies x up, applies, copies y back, synchronises */
+/* the same two with HOST vectors: copies x up, applies, copies y back, synchronises.  One GPU, >= 2^20 dofs: pipelined -
+ * x tiles up, element chunks, E->L reduction of the tiles a chunk completes and y tiles down overlap on three streams
+ * (page-locked vectors, e.g. b200pa_host_alloc, let the copies run asynchronously).  Environment: B200PA_NO_PIPELINE=1
+ * selects the serial route, B200PA_PIPE_CHUNKS / B200PA_PIPE_TILE the plan (default 8 chunks, 32768 dofs per tile),
+ * B200PA_PIPE_TRACE=1 prints the per-chunk timeline of every call on stderr. */
 int b200pa_form_mult_host(b200pa_form f, int constrained, const double *x_host, double *y_host);
 /* PABilinearFormExtension::AssembleDiagonal (fem/bilinearform_ext.cpp:370-454) */
 int b200pa_form_assemble_diagonal(b200pa_form f, double *diag_dev);
