@@ -63,3 +63,26 @@ def test_shared_memory_layout_model_of_the_kernel():
         m = re.search(r"static constexpr int %s = ([^;]+);" % name, new)
         vals = [int(v) for v in re.findall(r"\? (\d+)", m.group(1))] + [int(re.findall(r": (\d+)$", m.group(1).strip())[0])]
         assert vals == [ss.KERNEL[D][col] for D in (2, 3, 4, 5, 6, 7)], (name, vals)
+
+
+def test_grouped_lane_maps_gain_little(capsys):
+    """tools/smem_strides.py alt: giving every half-warp whole slabs in the row phases removes at most ~7 % of a batch's
+    shared-memory wavefronts at p = 4 and nothing at p = 3, 5 - the evidence DESIGN.md 4.1 cites for keeping the packed maps"""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import smem_strides as ss
+    ss.alt()
+    out = capsys.readouterr().out
+    best = {}
+    cur = None
+    for line in out.splitlines():
+        m = re.match(r"p=(\d) NEB=\d+: shipped .* all phases (\d+)", line)
+        if m:
+            cur = int(m.group(1))
+            best[cur] = [int(m.group(2)), 0]
+        m = re.search(r"change ([+-]\d+) wavefronts", line)
+        if m:
+            best[cur][1] = min(best[cur][1], int(m.group(1)))
+    assert set(best) == {3, 4, 5}
+    assert best[3][1] == 0 and best[5][1] == 0                      # only worse there
+    assert 0.05 <= -best[4][1] / best[4][0] <= 0.08                 # 102 of 1378 wavefronts at p = 4

@@ -9,6 +9,7 @@ source page of profiles' r1e / r1h captures): 1486 modelled vs 1471 measured wav
 
     python tools/smem_strides.py report          # wavefronts / ideal per phase for the configuration in the kernel
     python tools/smem_strides.py search D NEB    # search (RQ, SQ, ES, SXS, BS, maps) for one order (minutes)
+    python tools/smem_strides.py alt             # the "whole slabs per half-warp" lane maps for the row phases at p = 3..5
 """
 import sys
 
@@ -152,8 +153,60 @@ def search(D, NEB):
     print("best without changing the lane maps:", [t for t in out if t[2]["mapA"] == "qy" and t[2]["mapC"] == "dx"][0])
 
 
+def alt():
+    """Row phases with WHOLE slabs per half-warp (floor(16/Q) slabs x Q rows for A / C1, floor(16/D) slabs x D columns for
+    C2, the other lanes idle) instead of tasks packed into consecutive lanes: within a half-warp the addresses are then
+    s*SQ + qy*RQ (+ const), which an odd SQ and a suitable element stride ES make conflict-free - but the idle lanes cost
+    half-warps.  Prints the row-phase wavefronts per batch next to the shipped configuration's: the gain is 6-7 % of a
+    batch's wavefronts at p = 4 and nothing elsewhere, which is why the kernel keeps the packed maps."""
+    for D, ES_list in ((4, (345, 346, 349)), (5, (564, 565, 569)), (6, (886, 887, 889))):
+        NEB, SXS, RQ, SQ, ES0, BS, mA, mC, QES, QMS = KERNEL[D]
+        Q, nsl = D + 1, NEB * D
+        Q2 = Q * Q
+        NT = ((NEB * Q2 + 31) // 32) * 32
+        FS = D * SQ
+        GA, GC = max(1, 16 // Q), max(1, 16 // D)
+        base = phases(D, Q, NEB, SXS, RQ, SQ, ES0, BS, mA, mC, QES, QMS)
+        rows = ("A.w", "C1.r", "C1.w", "C2.r", "B.r", "B.w")
+        print(f"p={D - 1} NEB={NEB}: shipped " + " ".join(f"{k}={base[k][0]}" for k in rows) + f" | all phases {sum(v[0] for v in base.values())}")
+        for ES in ES_list:
+            res = {}
+
+            def add(name, fn, nl):
+                L = [fn(l) for l in range(((nl + 31) // 32) * 32)]
+                r = res.setdefault(name, 0)
+                res[name] = r + sum(cost(L[s0:s0 + NT]) for s0 in range(0, len(L), NT))
+
+            def task(l, G, W):
+                h, j = divmod(l, 16)
+                slab = G * h + j // W
+                return (slab, j % W) if j < G * W and slab < nsl else None
+
+            sE = lambda t, f, a, b: (t // D) * ES + f * FS + (t % D) * SQ + a * RQ + b
+            nlA, nlC = ((nsl + GA - 1) // GA) * 16, ((nsl + GC - 1) // GC) * 16
+            for f in range(3):
+                for qx in range(Q):
+                    fn = lambda l: (lambda t: None if t is None else sE(t[0], f, t[1], qx))(task(l, GA, Q))
+                    add("A.w", fn, nlA)
+                    add("C1.r", fn, nlA)
+            for f in range(2):
+                for dx in range(D):
+                    add("C1.w", lambda l: (lambda t: None if t is None else sE(t[0], f, t[1], dx))(task(l, GA, Q)), nlA)
+                for qy in range(Q):
+                    add("C2.r", lambda l: (lambda t: None if t is None else sE(t[0], f, qy, t[1]))(task(l, GC, D)), nlC)
+            for f in range(3):
+                for dz in range(D):
+                    fn = lambda l: (l // Q2) * ES + f * FS + dz * SQ + ((l % Q2) // Q) * RQ + (l % Q2) % Q if l < NEB * Q2 else None
+                    add("B.r", fn, NEB * Q2)
+                    add("B.w", fn, NEB * Q2)
+            delta = sum(res[k] - base[k][0] for k in rows)
+            print(f"      slabs per half-warp, ES={ES}: " + " ".join(f"{k}={res[k]}" for k in rows) + f" | change {delta:+d} wavefronts per batch")
+
+
 if __name__ == "__main__":
     if len(sys.argv) >= 4 and sys.argv[1] == "search":
         search(int(sys.argv[2]), int(sys.argv[3]))
+    elif len(sys.argv) >= 2 and sys.argv[1] == "alt":
+        alt()
     else:
         report()
